@@ -1,0 +1,39 @@
+"""Import the UNMODIFIED reference modules from /root/reference (only possible in the build container).
+
+TEST INFRASTRUCTURE ONLY.  Used by oracle/make_golden.py and by the `-m "not gpu"` tests that pin the
+numpy restatements in oracle/*.py against the real reference.  Never imported by the product package.
+
+`sofacontrol/utils.py:5` does `import osqp` at module top; osqp is absent here and only
+`Polyhedron(with_reproject=True)` touches it, so an empty stub module is injected.
+`sofacontrol/SSM/ssm.py` needs jax and is NOT importable; see oracle/ssm_np.py.
+"""
+import os
+import sys
+import types
+import warnings
+
+REFERENCE_ROOT = os.environ.get("SRC_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "sofacontrol"))
+
+
+def load():
+    """Returns a namespace with the reference modules: tpwl, pod, ilqr, config, utils, measurement_models."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    if "osqp" not in sys.modules:
+        sys.modules["osqp"] = types.ModuleType("osqp")
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import sofacontrol.utils as utils
+        import sofacontrol.mor.pod as pod
+        import sofacontrol.tpwl.tpwl as tpwl
+        import sofacontrol.lqr.ilqr as ilqr
+        import sofacontrol.lqr.config as config
+        import sofacontrol.measurement_models as measurement_models
+    return types.SimpleNamespace(utils=utils, pod=pod, tpwl=tpwl, ilqr=ilqr, config=config,
+                                 measurement_models=measurement_models, root=REFERENCE_ROOT)

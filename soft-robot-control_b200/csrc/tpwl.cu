@@ -1,0 +1,417 @@
+// tpwl.cu -- TPWL model: nearest-point selection, exponential weights, linearisation (gather / weighted bank
+// blend + discretisation) and batched rollout.  Reference: sofacontrol/tpwl/tpwl.py (see include/srcb200.h).
+#include "tpwl.cuh"
+
+namespace srcb {
+
+int dgemm_device(int transA, long long M, long long N, long long K, double alpha, const double* A, long long lda,
+                 const double* B, long long ldb, double* C, long long ldc, cudaStream_t st);
+
+int check_tpwl_model(const srcb200_tpwl_model* s) {
+    if (!s) return fail(SRCB200_E_NULL, "tpwl model is NULL");
+    if (s->n < 2 || (s->n & 1) || s->m < 1 || s->P < 1 || s->nz < 0)
+        return fail(SRCB200_E_DIM, "tpwl dims invalid: n=%d m=%d nz=%d P=%d", s->n, s->m, s->nz, s->P);
+    if (s->n > 128 || s->m > 32 || s->nz > 32)
+        return fail(SRCB200_E_DIM, "tpwl dims beyond kernel limits (n<=128, m<=32, nz<=32): n=%d m=%d nz=%d", s->n, s->m, s->nz);
+    if (!s->qT || !s->vT || !s->A || !s->B || !s->d) return fail(SRCB200_E_NULL, "tpwl model has NULL bank pointers");
+    if (s->nz > 0 && (!s->H || !s->z_ref)) return fail(SRCB200_E_NULL, "tpwl output model has NULL H/z_ref");
+    if (s->method != SRCB200_TPWL_NN && s->method != SRCB200_TPWL_WEIGHTING)
+        return fail(SRCB200_E_METHOD, "tpwl method should be nn or weighting");               // tpwl.py:268
+    if (s->discr_method < SRCB200_DISCR_FE || s->discr_method > SRCB200_DISCR_NONE)
+        return fail(SRCB200_E_METHOD, "self.discr_method must be in [fe, be, bil, zoh]");     // tpwl.py:295
+    if (s->discr_method == SRCB200_DISCR_ZOH)
+        return fail(SRCB200_E_METHOD, "zoh is only available through a pre-discretised bank (discr_method NONE)");
+    return 0;
+}
+
+constexpr int kSel = 128;   // threads per CTA for selection / rollout kernels
+
+// ---- nearest point ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSel)
+tpwl_nearest_kernel(TpwlDev M, long long count, const double* __restrict__ x, int* __restrict__ idx,
+                    double* __restrict__ dist) {
+    extern __shared__ double sm[];
+    __shared__ double red_d[kSel / 32];
+    __shared__ int red_i[kSel / 32];
+    double* sx = sm;
+    for (long long s = blockIdx.x; s < count; s += gridDim.x) {
+        for (int i = threadIdx.x; i < M.n; i += kSel) sx[i] = x[s * M.n + i];
+        __syncthreads();
+        double dmin;
+        const int bi = tpwl_nearest<kSel>(M, sx, nullptr, red_d, red_i, &dmin);
+        if (threadIdx.x == 0) {
+            idx[s] = bi;
+            if (dist) dist[s] = dmin;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- exponential weights (tpwl.py:170-191) --------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ double cta_sum(double v, double* red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; ++k) s += red[k];
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(kSel)
+tpwl_weights_kernel(TpwlDev M, long long count, const double* __restrict__ x, long long xstride,
+                    double* __restrict__ w) {
+    extern __shared__ double sm[];
+    __shared__ double red_d[kSel / 32];
+    __shared__ int red_i[kSel / 32];
+    double* sx = sm;
+    double* sd = sm + M.n;   // P distances
+    for (long long s = blockIdx.x; s < count; s += gridDim.x) {
+        for (int i = threadIdx.x; i < M.n; i += kSel) sx[i] = x[s * xstride + i];
+        __syncthreads();
+        double dmin;
+        const int bi = tpwl_nearest<kSel>(M, sx, sd, red_d, red_i, &dmin);
+        __syncthreads();
+        double* ws = w + s * (long long)M.P;
+        if (dmin == 0.0) {
+            for (int p = threadIdx.x; p < M.P; p += kSel) ws[p] = (p == bi) ? 1.0 : 0.0;
+        } else {
+            double part = 0.0;
+            for (int p = threadIdx.x; p < M.P; p += kSel) {
+                // np.exp(-beta * dist / m): ((-beta) * dist) / m
+                const double e = exp(__ddiv_rn(__dmul_rn(-M.beta, sd[p]), dmin));
+                sd[p] = e;
+                part += e;
+            }
+            const double tot = cta_sum<kSel>(part, red_d);
+            for (int p = threadIdx.x; p < M.P; p += kSel) ws[p] = __ddiv_rn(sd[p], tot);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- gather the selected bank entries (nn) ---------------------------------------------------------------------
+__global__ void tpwl_gather_kernel(TpwlDev M, long long count, const int* __restrict__ idx, double* __restrict__ A,
+                                   double* __restrict__ B, double* __restrict__ d) {
+    const long long nn = (long long)M.n * M.n, nm = (long long)M.n * M.m, n = M.n;
+    for (long long s = blockIdx.x; s < count; s += gridDim.x) {
+        const long long p = idx[s];
+        if (A) for (int e = threadIdx.x; e < nn; e += blockDim.x) A[s * nn + e] = M.A[p * nn + e];
+        if (B) for (int e = threadIdx.x; e < nm; e += blockDim.x) B[s * nm + e] = M.B[p * nm + e];
+        if (d) for (int e = threadIdx.x; e < n; e += blockDim.x) d[s * n + e] = M.d[p * n + e];
+    }
+}
+
+// ---- batched discretisation (fe / be / bil) ---------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT)
+discretize_kernel(int n, int m, int method, long long count, double dt, const double* Ac,
+                  const double* Bc, const double* dc, double* Ad,
+                  double* Bd, double* dd) {
+    extern __shared__ double sm[];
+    double* sA = sm;
+    double* sB = sA + n * n;
+    double* sd = sB + n * m;
+    double* scr = sd + n;
+    const int tid = threadIdx.x;
+    for (long long s = blockIdx.x; s < count; s += gridDim.x) {
+        for (int e = tid; e < n * n; e += NT) sA[e] = Ac[s * n * n + e];
+        for (int e = tid; e < n * m; e += NT) sB[e] = Bc[s * n * m + e];
+        for (int e = tid; e < n; e += NT) sd[e] = dc[s * n + e];
+        cta_sync<NT>();
+        discretize_inplace<NT>(method, dt, sA, sB, sd, n, m, scr);
+        cta_sync<NT>();
+        for (int e = tid; e < n * n; e += NT) Ad[s * n * n + e] = sA[e];
+        for (int e = tid; e < n * m; e += NT) Bd[s * n * m + e] = sB[e];
+        for (int e = tid; e < n; e += NT) dd[s * n + e] = sd[e];
+        cta_sync<NT>();
+    }
+}
+
+int discretize_launch(int n, int m, int method, long long count, double dt, const double* Ac, const double* Bc,
+                      const double* dc, double* Ad, double* Bd, double* dd, cudaStream_t st) {
+    if (count == 0) return 0;
+    const size_t smem = sizeof(double) * (n * n + n * m + n + discretize_scratch_doubles(n, m));
+    if (smem > 227 * 1024) return fail(SRCB200_E_DIM, "discretize: n=%d m=%d needs %zu B of shared memory", n, m, smem);
+    const int grid = (int)(count < 148 * 16 ? count : 148 * 16);
+    if (n <= 12) {
+        SRCB_CUDA(cudaFuncSetAttribute(discretize_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        discretize_kernel<32><<<grid, 32, smem, st>>>(n, m, method, count, dt, Ac, Bc, dc, Ad, Bd, dd);
+    } else {
+        SRCB_CUDA(cudaFuncSetAttribute(discretize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        discretize_kernel<256><<<grid, 256, smem, st>>>(n, m, method, count, dt, Ac, Bc, dc, Ad, Bd, dd);
+    }
+    SRCB_LAUNCH_CHECK("discretize_kernel");
+    return 0;
+}
+
+// ---- affine step x+ = (A x + B u) + d for a batch with per-trajectory matrices (weighting mode) -----------------
+__global__ void __launch_bounds__(128)
+tpwl_step_kernel(int n, int m, long long batch, const double* __restrict__ A, const double* __restrict__ B,
+                 const double* __restrict__ d, const double* __restrict__ x, long long xstride,
+                 const double* __restrict__ u, long long ustride, double* __restrict__ xn, long long xnstride) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        const double* Ab = A + b * (long long)n * n;
+        const double* Bb = B + b * (long long)n * m;
+        const double* xb = x + b * xstride;
+        const double* ub = u + b * ustride;
+        for (int i = warp; i < n; i += nw) {
+            double ax = 0.0, bu = 0.0;
+            for (int k = lane; k < n; k += 32) ax = fma(Ab[i * n + k], xb[k], ax);
+            for (int k = lane; k < m; k += 32) bu = fma(Bb[i * m + k], ub[k], bu);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                ax += __shfl_xor_sync(0xffffffffu, ax, off);
+                bu += __shfl_xor_sync(0xffffffffu, bu, off);
+            }
+            if (lane == 0) xn[b * xnstride + i] = __dadd_rn(__dadd_rn(ax, bu), d[b * n + i]);
+        }
+    }
+}
+
+// z = H x + z_ref for count points (tpwl.py:115-126)
+__global__ void tpwl_output_kernel(TpwlDev M, long long count, const double* __restrict__ x, double* __restrict__ z) {
+    const long long tot = count * M.nz;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+        const long long s = e / M.nz;
+        const int i = (int)(e - s * M.nz);
+        double acc = 0.0;
+        for (int k = 0; k < M.n; ++k) acc = fma(M.H[i * M.n + k], x[s * M.n + k], acc);
+        z[e] = __dadd_rn(acc, M.zref[i]);
+    }
+}
+
+// ---- nn rollout: one CTA walks one trajectory (tpwl.py:193-216 with update_state 226-234) -----------------------
+// PREDISC: the bank is already discrete (or dt < 0): the selected (A, B, d) are used straight from global memory.
+// Otherwise the selected entry is copied to shared memory and discretised (fe/be/bil) every step, like the
+// reference does when pre_discretize() was not called.
+template <bool PREDISC>
+__global__ void __launch_bounds__(kSel)
+tpwl_rollout_nn_kernel(TpwlDev M, long long batch, int N, const double* __restrict__ x0,
+                       const double* __restrict__ u, double dt, double* __restrict__ xo, int* __restrict__ idxo) {
+    extern __shared__ double sm[];
+    __shared__ double red_d[kSel / 32];
+    __shared__ int red_i[kSel / 32];
+    const int n = M.n, m = M.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* sx = sm;
+    double* su = sx + n;
+    double* sxn = su + m;
+    double* sA = sxn + n;                 // only when !PREDISC
+    double* sB = sA + n * n;
+    double* sd = sB + n * m;
+    double* scr = sd + n;
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        double* xb = xo + b * (long long)(N + 1) * n;
+        const double* ub = u + b * (long long)N * m;
+        for (int i = tid; i < n; i += kSel) { sx[i] = x0[b * n + i]; xb[i] = sx[i]; }
+        __syncthreads();
+        for (int t = 0; t < N; ++t) {
+            for (int i = tid; i < m; i += kSel) su[i] = ub[t * m + i];
+            const int p = tpwl_nearest<kSel>(M, sx, nullptr, red_d, red_i, nullptr);
+            if (idxo && tid == 0) idxo[b * (long long)N + t] = p;
+            const double* Ap = M.A + (long long)p * n * n;
+            const double* Bp = M.B + (long long)p * n * m;
+            const double* dp = M.d + (long long)p * n;
+            if (!PREDISC) {
+                for (int e = tid; e < n * n; e += kSel) sA[e] = Ap[e];
+                for (int e = tid; e < n * m; e += kSel) sB[e] = Bp[e];
+                for (int e = tid; e < n; e += kSel) sd[e] = dp[e];
+                __syncthreads();
+                discretize_inplace<kSel>(M.discr, dt, sA, sB, sd, n, m, scr);
+                Ap = sA; Bp = sB; dp = sd;
+            }
+            __syncthreads();
+            for (int i = warp; i < n; i += kSel / 32) {
+                double ax = 0.0, bu = 0.0;
+                for (int k = lane; k < n; k += 32) ax = fma(Ap[i * n + k], sx[k], ax);
+                for (int k = lane; k < m; k += 32) bu = fma(Bp[i * m + k], su[k], bu);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    ax += __shfl_xor_sync(0xffffffffu, ax, off);
+                    bu += __shfl_xor_sync(0xffffffffu, bu, off);
+                }
+                if (lane == 0) sxn[i] = __dadd_rn(__dadd_rn(ax, bu), dp[i]);
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += kSel) { sx[i] = sxn[i]; xb[(t + 1) * n + i] = sxn[i]; }
+            __syncthreads();
+        }
+    }
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline long long bank_width(const TpwlDev& M) { return (long long)M.n * M.n + (long long)M.n * M.m + M.n; }
+
+}  // namespace srcb
+
+using namespace srcb;
+
+extern "C" int srcb200_tpwl_nearest_batch(const srcb200_tpwl_model* mdl, int64_t count, const double* x,
+                                          int32_t* idx, double* dist, void* stream) {
+    if (int e = check_tpwl_model(mdl)) return e;
+    if (count < 0) return fail(SRCB200_E_DIM, "count < 0");
+    if (count == 0) return 0;
+    if (!x || !idx) return fail(SRCB200_E_NULL, "x/idx is NULL");
+    TpwlDev M = to_dev(*mdl);
+    const int grid = (int)(count < 148 * 16 ? count : 148 * 16);
+    tpwl_nearest_kernel<<<grid, kSel, sizeof(double) * M.n, (cudaStream_t)stream>>>(M, count, x, idx, dist);
+    SRCB_LAUNCH_CHECK("tpwl_nearest_kernel");
+    return 0;
+}
+
+extern "C" int srcb200_tpwl_weights_batch(const srcb200_tpwl_model* mdl, int64_t count, const double* x, double* w,
+                                          void* stream) {
+    if (int e = check_tpwl_model(mdl)) return e;
+    if (count < 0) return fail(SRCB200_E_DIM, "count < 0");
+    if (count == 0) return 0;
+    if (!x || !w) return fail(SRCB200_E_NULL, "x/w is NULL");
+    TpwlDev M = to_dev(*mdl);
+    const size_t smem = sizeof(double) * (M.n + M.P);
+    if (smem > 227 * 1024) return fail(SRCB200_E_DIM, "weights: P=%d too large for shared memory", M.P);
+    SRCB_CUDA(cudaFuncSetAttribute(tpwl_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)(count < 148 * 16 ? count : 148 * 16);
+    tpwl_weights_kernel<<<grid, kSel, smem, (cudaStream_t)stream>>>(M, count, x, M.n, w);
+    SRCB_LAUNCH_CHECK("tpwl_weights_kernel");
+    return 0;
+}
+
+extern "C" int srcb200_tpwl_output_batch(const srcb200_tpwl_model* mdl, int64_t count, const double* x, double* z,
+                                         void* stream) {
+    if (int e = check_tpwl_model(mdl)) return e;
+    if (mdl->nz == 0) return fail(SRCB200_E_NULL, "Need to set output or meas. model");   // tpwl.py:126
+    if (count < 0) return fail(SRCB200_E_DIM, "count < 0");
+    if (count == 0) return 0;
+    if (!x || !z) return fail(SRCB200_E_NULL, "x/z is NULL");
+    TpwlDev M = to_dev(*mdl);
+    const long long blocks = (count * M.nz + 255) / 256;
+    tpwl_output_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)stream>>>(M, count, x, z);
+    SRCB_LAUNCH_CHECK("tpwl_output_kernel");
+    return 0;
+}
+
+extern "C" int srcb200_discretize_batch(int32_t n, int32_t m, int32_t discr_method, int64_t count, double dt,
+                                        const double* A_c, const double* B_c, const double* d_c, double* A_d,
+                                        double* B_d, double* d_d, void* stream) {
+    if (n < 1 || m < 1 || n > 128 || m > 32 || count < 0) return fail(SRCB200_E_DIM, "discretize: bad dims n=%d m=%d", n, m);
+    if (discr_method != SRCB200_DISCR_FE && discr_method != SRCB200_DISCR_BE && discr_method != SRCB200_DISCR_BIL)
+        return fail(SRCB200_E_METHOD, "self.discr_method must be in [fe, be, bil, zoh]");
+    if (count == 0) return 0;
+    if (!A_c || !B_c || !d_c || !A_d || !B_d || !d_d) return fail(SRCB200_E_NULL, "discretize: NULL operand");
+    return discretize_launch(n, m, discr_method, count, dt, A_c, B_c, d_c, A_d, B_d, d_d, (cudaStream_t)stream);
+}
+
+// workspace layout for linearize (weighting): [ W (count x P) | blend (count x width) ] ; nn: [ idx (count) ]
+extern "C" size_t srcb200_tpwl_linearize_workspace(const srcb200_tpwl_model* mdl, int64_t count) {
+    if (!mdl || count <= 0) return 0;
+    TpwlDev M = to_dev(*mdl);
+    if (M.method == SRCB200_TPWL_NN) return align_up(sizeof(int32_t) * (size_t)count, 256);
+    return align_up(sizeof(double) * (size_t)count * M.P, 256) + align_up(sizeof(double) * (size_t)count * bank_width(M), 256);
+}
+
+extern "C" int srcb200_tpwl_linearize_batch(const srcb200_tpwl_model* mdl, int64_t count, const double* x, double dt,
+                                            double* A, double* B, double* d, int32_t* idx, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+    if (int e = check_tpwl_model(mdl)) return e;
+    if (count < 0) return fail(SRCB200_E_DIM, "count < 0");
+    if (count == 0) return 0;
+    if (!x || !A || !B || !d) return fail(SRCB200_E_NULL, "linearize: x/A/B/d is NULL");
+    if (!workspace || workspace_bytes < srcb200_tpwl_linearize_workspace(mdl, count))
+        return fail(SRCB200_E_WORKSPACE, "linearize: workspace too small");
+    TpwlDev M = to_dev(*mdl);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = M.n, m = M.m;
+    const bool disc = (dt >= 0.0 && M.discr != SRCB200_DISCR_NONE);
+    const int grid = (int)(count < 148 * 16 ? count : 148 * 16);
+    if (M.method == SRCB200_TPWL_NN) {
+        int32_t* widx = idx ? idx : (int32_t*)workspace;
+        tpwl_nearest_kernel<<<grid, kSel, sizeof(double) * n, st>>>(M, count, x, widx, nullptr);
+        SRCB_LAUNCH_CHECK("tpwl_nearest_kernel");
+        tpwl_gather_kernel<<<grid, 256, 0, st>>>(M, count, widx, A, B, d);
+        SRCB_LAUNCH_CHECK("tpwl_gather_kernel");
+    } else {
+        // the bank is three arrays (A, B, d) -> three GEMMs against the same weight matrix
+        double* W = (double*)workspace;
+        if (int e = srcb200_tpwl_weights_batch(mdl, count, x, W, stream)) return e;
+        if (int e = dgemm_device(0, count, (long long)n * n, M.P, 1.0, W, M.P, M.A, (long long)n * n, A, (long long)n * n, st)) return e;
+        if (int e = dgemm_device(0, count, (long long)n * m, M.P, 1.0, W, M.P, M.B, (long long)n * m, B, (long long)n * m, st)) return e;
+        if (int e = dgemm_device(0, count, n, M.P, 1.0, W, M.P, M.d, n, d, n, st)) return e;
+    }
+    if (disc) return discretize_launch(n, m, M.discr, count, dt, A, B, d, A, B, d, st);
+    return 0;
+}
+
+// rollout workspace (weighting only): [ W (batch x P) | A (batch x n x n) | B (batch x n x m) | d (batch x n) ]
+extern "C" size_t srcb200_tpwl_rollout_workspace(const srcb200_tpwl_model* mdl, int64_t batch) {
+    if (!mdl || batch <= 0) return 0;
+    TpwlDev M = to_dev(*mdl);
+    if (M.method == SRCB200_TPWL_NN) return 256;
+    return align_up(sizeof(double) * (size_t)batch * M.P, 256) + align_up(sizeof(double) * (size_t)batch * M.n * M.n, 256) +
+           align_up(sizeof(double) * (size_t)batch * M.n * M.m, 256) + align_up(sizeof(double) * (size_t)batch * M.n, 256);
+}
+
+extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t batch, int32_t N, const double* x0,
+                                          const double* u, double dt, double* x, double* z, int32_t* idx,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+    if (int e = check_tpwl_model(mdl)) return e;
+    if (batch < 0 || N < 0) return fail(SRCB200_E_DIM, "batch/N < 0");
+    if (batch == 0) return 0;
+    if (!x0 || !x || (N > 0 && !u)) return fail(SRCB200_E_NULL, "rollout: x0/u/x is NULL");
+    if (z && mdl->nz == 0) return fail(SRCB200_E_NULL, "Need to set output or meas. model");
+    TpwlDev M = to_dev(*mdl);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = M.n, m = M.m;
+    const bool disc = (dt >= 0.0 && M.discr != SRCB200_DISCR_NONE);
+    if (M.method == SRCB200_TPWL_NN) {
+        const int grid = (int)(batch < 148 * 16 ? batch : 148 * 16);
+        if (!disc) {
+            const size_t smem = sizeof(double) * (2 * n + m);
+            tpwl_rollout_nn_kernel<true><<<grid, kSel, smem, st>>>(M, batch, N, x0, u, dt, x, idx);
+        } else {
+            const size_t smem = sizeof(double) * (2 * n + m + n * n + n * m + n + discretize_scratch_doubles(n, m));
+            if (smem > 227 * 1024) return fail(SRCB200_E_DIM, "rollout: n=%d needs %zu B of shared memory", n, smem);
+            SRCB_CUDA(cudaFuncSetAttribute(tpwl_rollout_nn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tpwl_rollout_nn_kernel<false><<<grid, kSel, smem, st>>>(M, batch, N, x0, u, dt, x, idx);
+        }
+        SRCB_LAUNCH_CHECK("tpwl_rollout_nn_kernel");
+    } else {
+        // weighting: the whole batch advances in lock step; per time step
+        //   weights (batch x P)  ->  DMMA blend W * bank  ->  discretise  ->  affine step
+        if (!workspace || workspace_bytes < srcb200_tpwl_rollout_workspace(mdl, batch))
+            return fail(SRCB200_E_WORKSPACE, "rollout: workspace too small");
+        char* wp = (char*)workspace;
+        double* W = (double*)wp;   wp += align_up(sizeof(double) * (size_t)batch * M.P, 256);
+        double* Ab = (double*)wp;  wp += align_up(sizeof(double) * (size_t)batch * n * n, 256);
+        double* Bb = (double*)wp;  wp += align_up(sizeof(double) * (size_t)batch * n * m, 256);
+        double* db = (double*)wp;
+        const long long xs = (long long)(N + 1) * n, us = (long long)N * m;
+        SRCB_CUDA(cudaMemcpy2DAsync(x, sizeof(double) * xs, x0, sizeof(double) * n, sizeof(double) * n, batch,
+                                    cudaMemcpyDeviceToDevice, st));
+        const int grid = (int)(batch < 148 * 16 ? batch : 148 * 16);
+        const size_t wsmem = sizeof(double) * (n + M.P);
+        SRCB_CUDA(cudaFuncSetAttribute(tpwl_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+        for (int t = 0; t < N; ++t) {
+            // the states of step t live strided inside x: x[b, t, :]
+            tpwl_weights_kernel<<<grid, kSel, wsmem, st>>>(M, batch, x + (long long)t * n, xs, W);
+            SRCB_LAUNCH_CHECK("tpwl_weights_kernel");
+            if (int e = dgemm_device(0, batch, (long long)n * n, M.P, 1.0, W, M.P, M.A, (long long)n * n, Ab, (long long)n * n, st)) return e;
+            if (int e = dgemm_device(0, batch, (long long)n * m, M.P, 1.0, W, M.P, M.B, (long long)n * m, Bb, (long long)n * m, st)) return e;
+            if (int e = dgemm_device(0, batch, n, M.P, 1.0, W, M.P, M.d, n, db, n, st)) return e;
+            if (disc) if (int e = discretize_launch(n, m, M.discr, batch, dt, Ab, Bb, db, Ab, Bb, db, st)) return e;
+            tpwl_step_kernel<<<grid, 128, 0, st>>>(n, m, batch, Ab, Bb, db, x + (long long)t * n, xs, u + (long long)t * m, us,
+                                                   x + (long long)(t + 1) * n, xs);
+            SRCB_LAUNCH_CHECK("tpwl_step_kernel");
+        }
+    }
+    if (z) {
+        const long long cnt = batch * (long long)(N + 1);
+        tpwl_output_kernel<<<(int)((cnt * M.nz + 255) / 256 < 148 * 8 ? (cnt * M.nz + 255) / 256 : 148 * 8), 256, 0, st>>>(M, cnt, x, z);
+        SRCB_LAUNCH_CHECK("tpwl_output_kernel");
+    }
+    return 0;
+}

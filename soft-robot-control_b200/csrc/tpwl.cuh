@@ -1,0 +1,128 @@
+// tpwl.cuh -- device-side TPWL point selection (nearest neighbour / exponential weights).
+// Reference math: sofacontrol/tpwl/tpwl.py:160-191.
+#pragma once
+#include "common.cuh"
+
+namespace srcb {
+
+struct TpwlDev {
+    int n, m, nz, P, r, method, discr;
+    double wq, wv, beta;
+    const double* qT;
+    const double* vT;
+    const double* A;
+    const double* B;
+    const double* d;
+    const double* H;
+    const double* zref;
+};
+
+inline TpwlDev to_dev(const srcb200_tpwl_model& s) {
+    TpwlDev t;
+    t.n = s.n; t.m = s.m; t.nz = s.nz; t.P = s.P; t.r = s.n / 2; t.method = s.method; t.discr = s.discr_method;
+    t.wq = s.wq; t.wv = s.wv; t.beta = s.beta;
+    t.qT = s.qT; t.vT = s.vT; t.A = s.A; t.B = s.B; t.d = s.d; t.H = s.H; t.zref = s.z_ref;
+    return t;
+}
+
+int check_tpwl_model(const srcb200_tpwl_model* mdl);
+
+// sum_j (bankT[j*P + p] - c[j])^2 over j in [lo, hi) in EXACTLY the order numpy's pairwise summation uses for
+// np.add.reduce(s, axis=1) on a contiguous row (what np.linalg.norm(axis=1) runs; tpwl.py:166-167): squares and
+// differences are rounded separately (no FMA), 8 strided accumulators for 8 <= n <= 128, sequential tail, rows
+// longer than 128 split recursively at n/2 rounded down to a multiple of 8 (the model is
+// checked against numpy's bits in tests/test_oracle_pairwise.py).
+__device__ __forceinline__ double sq_diff(const double* __restrict__ bankT, int P, int p, const double* __restrict__ c, int j) {
+    const double t = __dsub_rn(bankT[(size_t)j * P + p], c[j]);
+    return __dmul_rn(t, t);
+}
+
+__device__ inline double np_pairwise_sumsq(const double* __restrict__ bankT, int P, int p,
+                                           const double* __restrict__ c, int lo, int hi) {
+    const int n = hi - lo;
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = lo; i < hi; ++i) res = __dadd_rn(res, sq_diff(bankT, P, p, c, i));
+        return res;
+    }
+    if (n <= 128) {
+        double r0 = sq_diff(bankT, P, p, c, lo + 0), r1 = sq_diff(bankT, P, p, c, lo + 1);
+        double r2 = sq_diff(bankT, P, p, c, lo + 2), r3 = sq_diff(bankT, P, p, c, lo + 3);
+        double r4 = sq_diff(bankT, P, p, c, lo + 4), r5 = sq_diff(bankT, P, p, c, lo + 5);
+        double r6 = sq_diff(bankT, P, p, c, lo + 6), r7 = sq_diff(bankT, P, p, c, lo + 7);
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+            r0 = __dadd_rn(r0, sq_diff(bankT, P, p, c, lo + i + 0));
+            r1 = __dadd_rn(r1, sq_diff(bankT, P, p, c, lo + i + 1));
+            r2 = __dadd_rn(r2, sq_diff(bankT, P, p, c, lo + i + 2));
+            r3 = __dadd_rn(r3, sq_diff(bankT, P, p, c, lo + i + 3));
+            r4 = __dadd_rn(r4, sq_diff(bankT, P, p, c, lo + i + 4));
+            r5 = __dadd_rn(r5, sq_diff(bankT, P, p, c, lo + i + 5));
+            r6 = __dadd_rn(r6, sq_diff(bankT, P, p, c, lo + i + 6));
+            r7 = __dadd_rn(r7, sq_diff(bankT, P, p, c, lo + i + 7));
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                               __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+        for (; i < n; ++i) res = __dadd_rn(res, sq_diff(bankT, P, p, c, lo + i));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(np_pairwise_sumsq(bankT, P, p, c, lo, lo + n2), np_pairwise_sumsq(bankT, P, p, c, lo + n2, hi));
+}
+
+// d_p = wq * ||Q_p - q|| + wv * ||V_p - v||  with x = [v; q]  (utils.py:133-142, tpwl.py:165-168)
+// A zero weight contributes +0.0 (numpy computes 0 * norm; identical unless the norm is inf/nan).
+__device__ __forceinline__ double tpwl_distance(const TpwlDev& M, const double* __restrict__ x, int p) {
+    const int r = M.r;
+    double dq = 0.0, dv = 0.0;
+    if (M.wq != 0.0) dq = __dmul_rn(M.wq, sqrt(np_pairwise_sumsq(M.qT, M.P, p, x + r, 0, r)));
+    if (M.wv != 0.0) dv = __dmul_rn(M.wv, sqrt(np_pairwise_sumsq(M.vT, M.P, p, x, 0, r)));
+    return __dadd_rn(dq, dv);
+}
+
+// CTA-wide first-occurrence argmin of (d, p) pairs held one per thread.  red_d/red_i: NT/32 entries of shared
+// scratch.  Every thread returns the winning pair.
+template <int NT>
+__device__ __forceinline__ void cta_argmin(double& d, int& p, double* red_d, int* red_i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, d, off);
+        const int op = __shfl_xor_sync(0xffffffffu, p, off);
+        if (od < d || (od == d && op < p)) { d = od; p = op; }
+    }
+    if (NT > 32) {
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        __syncthreads();
+        if (l == 0) { red_d[w] = d; red_i[w] = p; }
+        __syncthreads();
+        d = red_d[0]; p = red_i[0];
+#pragma unroll
+        for (int k = 1; k < NT / 32; ++k) {
+            const double od = red_d[k];
+            const int op = red_i[k];
+            if (od < d || (od == d && op < p)) { d = od; p = op; }
+        }
+        __syncthreads();
+    }
+}
+
+// Nearest stored point to the state x (shared memory, n doubles).  Optionally writes all P distances to `dist`
+// (shared or global).  Returns (index, distance) to every thread.
+template <int NT>
+__device__ __forceinline__ int tpwl_nearest(const TpwlDev& M, const double* __restrict__ x, double* __restrict__ dist,
+                                            double* red_d, int* red_i, double* dmin_out) {
+    double best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int p = threadIdx.x; p < M.P; p += NT) {
+        const double dd = tpwl_distance(M, x, p);
+        if (dist) dist[p] = dd;
+        if (dd < best) { best = dd; bi = p; }
+    }
+    cta_argmin<NT>(best, bi, red_d, red_i);
+    if (bi == 0x7fffffff) bi = 0;   // all distances NaN/inf: np.argmin returns 0 for an all-inf row
+    if (dmin_out) *dmin_out = best;
+    return bi;
+}
+
+}  // namespace srcb

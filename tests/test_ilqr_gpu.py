@@ -1,0 +1,173 @@
+"""GPU parity: batched iLQR kernel (csrc/ilqr.cu) vs golden vectors produced by the UNMODIFIED reference iLQR class
+and vs the numpy oracle (oracle/ilqr_np.py) including its branch trace.  Tolerance: relative 1e-9 on states, inputs,
+gains and costs."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _ssm(m, **kw):
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.SSM.ssm import SSMDynamics
+    s = synth.trunk_ssm(m)
+    return s, SSMDynamics(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
+
+
+def _oracle_ssm(m):
+    import sofacontrol_b200.synth as synth
+    from oracle.ssm_np import SSMDynamicsNP, GaussNewtonSSM
+    s = synth.trunk_ssm(m)
+    return GaussNewtonSSM(SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params']))
+
+
+def _solver(model, m, zt, **kw):
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost
+    Q, R, Qf = synth.trunk_ilqr_costs(6, m)
+    s = iLQR(0.02, model, QuadraticCost(Q, R, Qf), zt.shape[-2] - 1, **kw)
+    s.set_target(zt)
+    return s
+
+
+@pytest.mark.parametrize("tag,m", [("diamond", 4), ("trunk", 8)])
+def test_forward_and_backward_pass_units(golden, tag, m):
+    """One forward pass and one backward pass on the reference's converged trajectory: no branch sensitivity."""
+    gi = golden("ssm_ilqr.npz")
+    _, model = _ssm(m)
+    s = _solver(model, m, gi[tag + '_zt'])
+    x, u, cost, A, B, d = s.forward_pass(gi[tag + '_x'], gi[tag + '_u'])
+    assert relerr(x, gi[tag + '_x']) < TOL and np.array_equal(u, gi[tag + '_u'])
+    assert abs(cost - float(gi[tag + '_fp_cost'])) < TOL * abs(float(gi[tag + '_fp_cost']))
+    assert relerr(A, gi[tag + '_fp_A']) < TOL and relerr(B, gi[tag + '_fp_B']) < TOL and relerr(d, gi[tag + '_fp_d']) < TOL
+    s.rho, s.drho = 0.0, 0.0
+    K, k, Qu, Quu = s.dlqr_recursion(gi[tag + '_x'], gi[tag + '_u'], gi[tag + '_fp_A'], gi[tag + '_fp_B'], gi[tag + '_fp_d'])
+    assert relerr(K, gi[tag + '_bp_K']) < TOL and relerr(k, gi[tag + '_bp_k']) < 1e-7   # k ~ 0 at the optimum: abs scale
+    assert relerr(Qu, gi[tag + '_bp_Qu']) < 1e-7 and relerr(Quu, gi[tag + '_bp_Quu']) < TOL
+    assert abs(float(s.rho) - float(gi[tag + '_bp_rho'])) < 1e-15
+
+
+@pytest.mark.parametrize("tag,m", [("diamond", 4), ("trunk", 8)])
+def test_solve_matches_reference_golden(golden, tag, m):
+    """Full solve from x0 = 0 on the figure-8 target: x, u, K vs the unmodified reference class (golden)."""
+    gi = golden("ssm_ilqr.npz")
+    _, model = _ssm(m)
+    s = _solver(model, m, gi[tag + '_zt'], trace=True)
+    x, u, K = s.ilqr_computation(np.zeros(6))
+    assert x.shape == (101, 6) and u.shape == (100, m) and K.shape == (100, m, 6)
+    assert relerr(x, gi[tag + '_x']) < TOL
+    assert relerr(u, gi[tag + '_u']) < TOL
+    assert relerr(K, gi[tag + '_K']) < TOL
+    assert abs(float(s.info['rho']) - float(gi[tag + '_rho'])) <= 1e-12 * max(1.0, abs(float(gi[tag + '_rho'])))
+    assert s.info['status'] & 1                                            # converged
+
+
+def test_branch_trace_matches_oracle():
+    """Iteration by iteration: accepted step size, cost, rho after the backward pass and PD restarts vs the oracle."""
+    import sofacontrol_b200.synth as synth
+    from oracle.ilqr_np import ILQRNP
+    from oracle.utils_np import QuadraticCost
+    m = 8
+    s_, model = _ssm(m)
+    rng = np.random.default_rng(7)
+    zt = synth.figure8_targets(s_['z_ref'], 60, [4.0, 11.0, 14.5], [0.3, 2.0, 4.4])
+    x0 = rng.uniform(-0.5, 0.5, size=(3, 6)) * np.array([1, 1, 1, 0, 0, 0])
+    s = _solver(model, m, zt, trace=True)
+    x, u, K = s.ilqr_computation(x0)
+    Q, R, Qf = synth.trunk_ilqr_costs(6, m)
+    for b in range(3):
+        o = ILQRNP(0.02, _oracle_ssm(m), QuadraticCost(Q, R, Qf), 60)
+        o.set_target(zt[b])
+        xo, uo, Ko = o.ilqr_computation(x0[b])
+        assert s.info['iterations'][b] == o.iterations
+        tr = s.info['trace'][b]
+        for ev in o.trace:
+            i = ev['it']
+            assert tr[i, 3] == ev['pd_restarts']
+            assert abs(tr[i, 2] - ev['rho_after_bwd']) <= 1e-12 * max(1.0, ev['rho_after_bwd'])
+            assert (tr[i, 1] > 0) == ev['accepted']
+            if ev['accepted']:
+                assert tr[i, 1] == 0.5 ** (len(ev['trials']) - 1)
+            assert abs(tr[i, 0] - ev['cost']) <= 1e-9 * abs(ev['cost'])
+        assert relerr(x[b], xo) < TOL and relerr(u[b], uo) < TOL and relerr(K[b], Ko) < TOL
+        assert abs(s.info['cost'][b] - o.final_cost) < TOL * abs(o.final_cost)
+        assert abs(s.info['cost0'][b] - o.initial_cost) < TOL * abs(o.initial_cost)
+
+
+def test_literal_constant_H_mode_is_degenerate_like_reference():
+    """With the literal SSM.H = zeros (ssm.py:72-73) the reference returns u = 0 after one iteration."""
+    import sofacontrol_b200.synth as synth
+    s_, model = _ssm(4)
+    zt = synth.figure8_targets(s_['z_ref'], 30, 5.0)[0]
+    s = _solver(model, 4, zt, gauss_newton=False)
+    x, u, K = s.ilqr_computation(np.zeros(6))
+    assert not u.any() and s.info['iterations'] == 1 and not K.any()
+
+
+def test_warm_start_u_last_and_config_switches():
+    import sofacontrol_b200.synth as synth
+    from oracle.ilqr_np import ILQRNP
+    from oracle.utils_np import QuadraticCost
+    m = 4
+    s_, model = _ssm(m)
+    rng = np.random.default_rng(9)
+    N = 25
+    zt = synth.figure8_targets(s_['z_ref'], N, 6.0, 1.0)[0]
+    uw = rng.uniform(0, 300, size=(N, m))
+    ul = rng.uniform(0, 300, size=m)
+    Q, R, Qf = synth.trunk_ilqr_costs(6, m)
+    Qf = 10.0 * Q
+    for variant in range(3):
+        from sofacontrol_b200.lqr.ilqr import iLQR
+        from sofacontrol_b200.utils import QuadraticCost as QC
+        s = iLQR(0.02, model, QC(Q, R, Qf), N)
+        o = ILQRNP(0.02, _oracle_ssm(m), QuadraticCost(Q, R, Qf), N)
+        for obj in (s, o):
+            obj.set_target(zt)
+            obj.set_u_last(ul)
+            if variant == 1:
+                obj.params.state_regularization = False
+                obj.params.rho0 = 0.5
+                obj.params.drho0 = 1.0
+            if variant == 2:
+                obj.params.include_input_var_constraint = False
+                obj.params.max_iter = 3
+        x, u, K = s.ilqr_computation(0.1 * np.ones(6), u_warmstart=uw)
+        xo, uo, Ko = o.ilqr_computation(0.1 * np.ones(6), u_warmstart=uw)
+        assert s.info['iterations'] == o.iterations
+        assert relerr(x, xo) < TOL and relerr(u, uo) < TOL and relerr(K, Ko) < TOL
+
+
+def test_tpwl_solve_matches_reference_golden(golden):
+    """TPWL (constant H, nn on the pre-discretised zoh bank of the reference) vs the unmodified reference class."""
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.tpwl.tpwl import TPWLATV
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost
+    gt = golden("tpwl_small.npz")
+    data, Hf = synth.tpwl_bank(seed=11, r=5, m=3, P=40, num_nodes=20, tip_node=7, spread=1.0)
+    g = TPWLATV(data, params={'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}, Hf=Hf, discr_method='zoh')
+    g.set_pre_discretized(gt['zoh_A_d'], gt['zoh_B_d'], gt['zoh_d_d'], 0.01)
+    s = iLQR(0.01, g, QuadraticCost(gt['ilqr_Q'], gt['ilqr_R'], np.zeros((6, 6))), 40)
+    s.set_target(gt['ilqr_zt'])
+    x, u, K = s.ilqr_computation(gt['xs'][0])
+    assert relerr(x, gt['ilqr_x']) < TOL and relerr(u, gt['ilqr_u']) < TOL and relerr(K, gt['ilqr_K']) < TOL
+
+
+def test_batch_is_consistent_and_statuses_reported():
+    """4096-problem shape at a reduced batch (257): every member equals its own single solve bit for bit."""
+    import sofacontrol_b200.synth as synth
+    w = synth.trunk_ilqr_batch(257, N=40, seed=3, m=8)
+    _, model = _ssm(8)
+    s = _solver(model, 8, w['z_target'])
+    x, u, K = s.ilqr_computation(w['x0'])
+    assert x.shape == (257, 41, 6) and np.all(np.isfinite(x)) and np.all(np.isfinite(K))
+    assert np.all(s.info['iterations'] >= 1) and np.all(s.info['cost'] <= s.info['cost0'])
+    for b in (0, 100, 256):
+        s1 = _solver(model, 8, w['z_target'][b])
+        x1, u1, K1 = s1.ilqr_computation(w['x0'][b])
+        assert np.array_equal(x1, x[b]) and np.array_equal(u1, u[b]) and np.array_equal(K1, K[b])

@@ -1,0 +1,96 @@
+"""GPU parity: POD Gram / DMMA GEMM kernels (csrc/gemm.cu) and compute_POD vs the reference's np.linalg.svd route.
+Parity metric: same mode count, singular values of the kept modes to 1e-9 relative, subspace angle < 1e-8."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (7, 5, 3), (130, 129, 17), (257, 300, 64), (512, 256, 1000), (200, 131, 0)])
+@pytest.mark.parametrize("transA", [False, True])
+def test_dgemm_vs_numpy(shape, transA):
+    from sofacontrol_b200.mor import pod
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    A = rng.normal(size=(K, M) if transA else (M, K))
+    B = rng.normal(size=(K, N))
+    C = pod.dgemm_device(_dev(A), _dev(B), transA=transA, alpha=0.5).cpu().numpy()
+    ref = 0.5 * ((A.T if transA else A) @ B)
+    assert C.shape == (M, N)
+    assert np.max(np.abs(C - ref)) <= 1e-12 * max(1.0, np.abs(ref).max()) * max(K, 1)
+
+
+@pytest.mark.parametrize("nf,ns", [(100, 3), (333, 129), (4884, 306), (1000, 257)])
+def test_gram_vs_numpy(nf, ns):
+    from sofacontrol_b200.mor import pod
+    rng = np.random.default_rng(nf)
+    X = rng.normal(size=(nf, ns))
+    G = pod.gram_device(_dev(X)).cpu().numpy()
+    ref = X.T @ X
+    assert np.max(np.abs(G - ref)) <= 1e-12 * np.abs(ref).max() * nf ** 0.5
+    assert np.array_equal(G, G.T)                                   # both triangles written from the same tile
+    G2 = pod.gram_device(_dev(X), G=_dev(ref), accumulate=True).cpu().numpy()
+    assert relerr(G2, 2 * ref) < 1e-12
+
+
+def test_compute_pod_small_golden(golden):
+    from sofacontrol_b200.mor import pod
+    import sofacontrol_b200.synth as synth
+    from oracle.pod_np import subspace_angle
+    gk = golden("pod_known.npz")
+    X, _, _ = synth.pod_snapshots(600, 150, seed=5)
+    U_full, U, nb, S = pod.compute_POD(X, 5e-5)
+    assert nb == int(gk['small_modes']) and U.shape == gk['small_U'].shape
+    assert relerr(S[:nb], gk['small_S'][:nb]) < 1e-9
+    ang, _ = subspace_angle(gk['small_U'], U)
+    assert ang < 1e-8
+    assert np.abs(U.T @ U - np.eye(nb)).max() < 1e-9
+
+
+def test_energy_rule_on_fixture_sigma(golden):
+    """Known answer: pod_model.pkl's Sigma with pod_tolerance 5e-5 keeps exactly 36 modes (pod.py:193-199)."""
+    from sofacontrol_b200.mor import pod
+    gk = golden("pod_known.npz")
+    assert pod.energy_mode_count_device(_dev(gk['Sigma'] ** 2), float(gk['tol'])) == int(gk['modes']) == 36
+
+
+def test_compute_pod_fixture_scale_vs_svd():
+    """Fixture-scale twin (4884 x 612, Diamond-like spectrum): same modes and subspace as np.linalg.svd."""
+    from sofacontrol_b200.mor import pod
+    import sofacontrol_b200.synth as synth
+    from oracle import pod_np
+    X, _, _ = synth.pod_snapshots(4884, 612, seed=5)
+    _, Uo, nbo, So = pod_np.compute_POD(X, 5e-5)
+    _, U, nb, S = pod.compute_POD(X, 5e-5)
+    assert nb == nbo
+    assert relerr(S[:nb], So[:nb]) < 1e-9
+    assert pod_np.subspace_angle(Uo, U)[0] < 1e-8
+
+
+def test_pod_projections_vs_oracle():
+    from sofacontrol_b200.mor import pod
+    from oracle.pod_np import PODNP
+    rng = np.random.default_rng(0)
+    nf, r = 300, 12
+    U, _ = np.linalg.qr(rng.normal(size=(nf, r)))
+    info = {'U': U, 'q_ref': rng.normal(size=nf), 'v_ref': rng.normal(size=nf), 'type': 'POD'}
+    g, o = pod.POD(info), PODNP(info)
+    qf, q = rng.normal(size=nf), rng.normal(size=r)
+    xf, x = rng.normal(size=2 * nf), rng.normal(size=2 * r)
+    M = rng.normal(size=(nf, nf))
+    assert relerr(g.compute_RO_state(qf=qf), o.compute_RO_state(qf=qf)) < 1e-12
+    assert relerr(g.compute_RO_state(vf=qf), o.compute_RO_state(vf=qf)) < 1e-12
+    assert relerr(g.compute_RO_state(xf=xf), o.compute_RO_state(xf=xf)) < 1e-12
+    assert relerr(g.compute_FO_state(q=q), o.compute_FO_state(q=q)) < 1e-12
+    assert relerr(g.compute_FO_state(x=x), o.compute_FO_state(x=x)) < 1e-12
+    assert relerr(g.compute_RO_matrix(M), o.compute_RO_matrix(M)) < 1e-12
+    assert relerr(g.compute_RO_matrix(M, left=True), o.compute_RO_matrix(M, left=True)) < 1e-12
+    assert relerr(g.compute_RO_matrix(M, right=True), o.compute_RO_matrix(M, right=True)) < 1e-12
+    assert np.array_equal(g.V, o.V) and g.rom_dim == r

@@ -1,0 +1,120 @@
+"""GPU parity: SSM kernels (csrc/ssm.cu) vs the FP64 numpy oracle (oracle/ssm_np.py) and the committed golden
+vectors of the reference's module_test fixture.  Tolerance: relative 1e-9 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _models(m=4, **kw):
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.SSM.ssm import SSMDynamics
+    from oracle.ssm_np import SSMDynamicsNP
+    s = synth.trunk_ssm(m)
+    g = SSMDynamics(s['z_ref'], model=s['model'], params=s['params'], **kw)
+    o = SSMDynamicsNP(s['z_ref'], model=s['model'], params=s['params'], **kw)
+    return g, o
+
+
+@pytest.mark.parametrize("m", [4, 8])
+@pytest.mark.parametrize("method", ["fe", "be", "bil"])
+def test_jacobians_single_and_batch(m, method):
+    g, o = _models(m, discrete=False, discr_method=method)
+    rng = np.random.default_rng(0)
+    X = rng.normal(0, 1.5, size=(33, 6))
+    U = rng.uniform(0, 800, size=(33, m))
+    A, B, d = g.get_jacobians(X, U, 0.02)
+    for i in range(X.shape[0]):
+        Ao, Bo, do = o.get_jacobians(X[i], U[i], 0.02)
+        assert relerr(A[i], Ao) < TOL and relerr(B[i], Bo) < TOL and relerr(d[i], do) < TOL
+    A1, B1, d1 = g.get_jacobians(X[5], U[5], 0.02)          # 1-D call keeps the reference's shapes
+    assert A1.shape == (6, 6) and B1.shape == (6, m) and d1.shape == (6,)
+    assert np.array_equal(A1, A[5]) and np.array_equal(d1, d[5])
+
+
+def test_continuous_discrete_and_observer_jacobians():
+    g, o = _models(4, discrete=False, discr_method='be')
+    gd, od = _models(4, discrete=True, discr_method='be')
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        x = rng.normal(0, 1.0, size=6)
+        u = rng.uniform(0, 800, size=4)
+        for a, b in zip(g.get_continuous_jacobians(x, u), o.get_continuous_jacobians(x, u)):
+            assert relerr(a, b) < TOL
+        for a, b in zip(gd.get_discrete_jacobians(x, u), od.get_discrete_jacobians(x, u)):
+            assert relerr(a, b) < TOL
+        for a, b in zip(gd.get_jacobians(x, u, 0.01), od.get_jacobians(x, u, 0.01)):
+            assert relerr(a, b) < TOL
+        H, c = g.get_observer_jacobians(x)
+        Ho, co = o.get_observer_jacobians(x)
+        assert relerr(H, Ho) < TOL and relerr(c, co) < TOL
+        assert relerr(g.update_observer_state(x), o.update_observer_state(x)) < TOL
+        assert relerr(g.update_state(x, u, 0.02), o.update_state(x, u, 0.02)) < TOL
+        assert relerr(g.reduced_dynamics(x, u), o.reduced_dynamics(x, u)) < TOL
+        assert relerr(gd.reduced_dynamics_discrete(x, u), od.reduced_dynamics_discrete(x, u)) < TOL
+
+
+def test_maps_and_shapes():
+    g, o = _models(4)
+    rng = np.random.default_rng(2)
+    X = rng.normal(0, 1.0, size=(17, 6))
+    assert relerr(g.x_to_zfyf(X), o.x_to_zfyf(X)) < TOL
+    assert relerr(g.x_to_zfyf(X[0]), o.x_to_zfyf(X[0])) < TOL
+    assert relerr(g.C_map(X.T), o.C_map(X.T)) < TOL                   # (n, N) column convention
+    assert relerr(g.x_to_zy(X[3]), o.x_to_zy(X[3])) < TOL
+    Z = o.x_to_zfyf(X)
+    assert relerr(g.compute_RO_state(Z[4]), o.compute_RO_state(Z[4])) < TOL
+    assert relerr(g.W_map(X.T), o.W_map(X.T)) < TOL
+    assert np.array_equal(g.zfyf_to_zy(Z), o.zfyf_to_zy(Z)) and np.array_equal(g.zy_to_zfyf(Z), o.zy_to_zfyf(Z))
+    assert g.get_state_dim() == 6 and g.get_input_dim() == 4 and g.get_output_dim() == 6
+    assert g.H.shape == (6, 6) and not g.H.any() and g.nonlinear_observer
+
+
+def test_bad_discretisation_raises_like_reference():
+    g, _ = _models(4, discrete=False, discr_method='zoh')
+    with pytest.raises(RuntimeError):
+        g.get_jacobians(np.zeros(6), np.zeros(4), 0.01)
+
+
+@pytest.mark.parametrize("name,kw", [("be", dict(discrete=False, discr_method='be')),
+                                     ("fe", dict(discrete=False, discr_method='fe')),
+                                     ("bil", dict(discrete=False, discr_method='bil')),
+                                     ("disc", dict(discrete=True, discr_method='be'))])
+def test_module_test_rollout_golden(golden, name, kw):
+    """The reference's module_test (examples/hardware/diamond_SSM.py:83-140): 1001-step open-loop rollout on the
+    recorded inputs; states/outputs vs the golden restatement vectors and the MSE vs the recorded SOFA outputs."""
+    gm = golden("ssm_module_test.npz")
+    g, _ = _models(4, **kw)
+    x, z = g.rollout(np.zeros(6), gm['u'], float(gm['dt']))
+    assert x.shape == gm['x_' + name].shape and z.shape == gm['z_' + name].shape
+    assert relerr(x, gm['x_' + name]) < TOL
+    assert relerr(z, gm['z_' + name]) < TOL
+    err = gm['z_true_qv'] - z[:-1]
+    mse = np.linalg.norm(np.linalg.norm(err, axis=1)) ** 2 / err.shape[0]
+    assert abs(mse - float(gm['mse_' + name])) < 1e-9 * float(gm['mse_' + name])
+
+
+def test_batched_rollout_matches_oracle_and_is_batch_invariant():
+    g, o = _models(8, discrete=False, discr_method='be')
+    rng = np.random.default_rng(3)
+    Bt, N = 37, 50
+    x0 = rng.normal(0, 0.3, size=(Bt, 6))
+    u = rng.uniform(0, 800, size=(Bt, N, 8))
+    x, z = g.rollout(x0, u, 0.02)
+    assert x.shape == (Bt, N + 1, 6) and z.shape == (Bt, N + 1, 6)
+    for b in (0, 7, 36):
+        xo, zo = o.rollout(x0[b], u[b], 0.02)
+        assert relerr(x[b], xo) < TOL and relerr(z[b], zo) < TOL
+    x1, z1 = g.rollout(x0[7], u[7], 0.02)                              # same bits alone or inside a batch
+    assert np.array_equal(x1, x[7]) and np.array_equal(z1, z[7])
+
+
+def test_empty_batch_and_zero_horizon():
+    g, _ = _models(4)
+    A, B, d = g.get_jacobians(np.zeros((0, 6)), np.zeros((0, 4)), 0.01)
+    assert A.shape == (0, 6, 6) and B.shape == (0, 6, 4) and d.shape == (0, 6)
+    x, z = g.rollout(np.ones((3, 6)) * 0.1, np.zeros((3, 0, 4)), 0.01)
+    assert x.shape == (3, 1, 6) and z.shape == (3, 1, 6)

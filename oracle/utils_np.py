@@ -1,7 +1,7 @@
 """numpy restatement of the state-layout helpers and ZOH discretisation of sofacontrol/utils.py.
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py)."""
 import numpy as np
-from scipy.linalg import expm as _dense_expm
+from scipy.sparse.linalg import expm as _ref_expm   # the routine the reference calls (utils.py:4,313)
 
 
 class QuadraticCost:
@@ -28,12 +28,12 @@ def x2qv(x):
 
 def zoh_affine(A, B, d, dt):
     """utils.py:302-335 -- exact ZOH of xdot = A x + B u + d via expm of the (n+m+1) augmented matrix.
-    The reference calls scipy.sparse.linalg.expm on a dense ndarray, which dispatches to the same dense
-    Pade-13 scaling-and-squaring routine as scipy.linalg.expm."""
+    The reference calls scipy.sparse.linalg.expm on the dense augmented matrix (Al-Mohy & Higham scaling and
+    squaring); the same routine is called here so the restatement is bit-identical."""
     n, m = A.shape[0], B.shape[1]
     M = np.zeros((n + m + 1, n + m + 1))
     M[:n, :n] = A
     M[:n, n:n + m] = B
     M[:n, n + m] = d
-    E = _dense_expm(M * dt)
+    E = _ref_expm(M * dt)
     return E[:n, :n], E[:n, n:n + m], E[:n, n + m]

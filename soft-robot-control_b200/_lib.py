@@ -163,15 +163,20 @@ def torch_mod():
 
 def to_dev(a, dtype=None):
     """numpy / list / torch tensor -> contiguous CUDA tensor (float64 unless dtype given)."""
+    require_gpu()
     torch = torch_mod()
     dtype = dtype or torch.float64
     if isinstance(a, torch.Tensor):
         return a.to(device="cuda", dtype=dtype).contiguous()
     np_dtype = {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8}[dtype]
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np_dtype)).cuda()
+    arr = np.ascontiguousarray(np.asarray(a), dtype=np_dtype)
+    if not arr.flags.writeable:
+        arr = arr.copy()
+    return torch.from_numpy(arr).cuda()
 
 
 def empty(shape, dtype=None):
+    require_gpu()
     torch = torch_mod()
     return torch.empty(shape, device="cuda", dtype=dtype or torch.float64)
 

@@ -1,0 +1,161 @@
+"""Pins the numpy oracle (oracle/*.py) bit-for-bit against the UNMODIFIED reference modules imported from
+/root/reference (available only in the build container; skipped elsewhere -- the committed golden vectors that the
+same reference produced are checked in tests/test_oracle_golden.py on every box)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import refimport
+
+pytestmark = pytest.mark.skipif(not refimport.available(), reason="reference tree not present on this box")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return refimport.load()
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def _small_bank():
+    import sofacontrol_b200.synth as synth
+    return synth.tpwl_bank(seed=11, r=5, m=3, P=40, num_nodes=20, tip_node=7, spread=1.0)
+
+
+@pytest.mark.parametrize("method", ["nn", "weighting"])
+@pytest.mark.parametrize("discr", ["fe", "be", "bil", "zoh"])
+def test_tpwl_restatement_bitwise(ref, method, discr):
+    from oracle.tpwl_np import TPWLATVNP
+    data, Hf = _small_bank()
+    params = {'tpwl_method': method, 'dist_weights': {'q': 0.7, 'v': 0.05}, 'beta_weighting': 25.0}
+    r = ref.tpwl.TPWLATV(data, params=params, Hf=Hf, discr_method=discr)
+    o = TPWLATVNP(data, params=params, Hf=Hf, discr_method=discr)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        x = rng.normal(size=10)
+        assert r.calc_nearest_point(x) == o.calc_nearest_point(x)
+        assert np.array_equal(r.calc_weighting_factors(x), o.calc_weighting_factors(x))
+        for a, b in zip(r.get_jacobians(x, dt=0.01), o.get_jacobians(x, dt=0.01)):
+            assert np.array_equal(a, b)
+        for a, b in zip(r.get_jacobians(x), o.get_jacobians(x)):
+            assert np.array_equal(a, b)
+    u = rng.uniform(0, 1500, size=(20, 3))
+    xr, zr = r.rollout(rng.normal(size=10), u, 0.01)
+    xo, zo = o.rollout(np.asarray(xr[0]), u, 0.01)
+    assert np.array_equal(xr, xo) and np.array_equal(zr, zo)
+    if method == 'nn':
+        _quiet(r.pre_discretize, 0.01)
+        o.pre_discretize(0.01)
+        assert np.array_equal(np.array(r.A_d), np.array(o.A_d)) and np.array_equal(np.array(r.d_d), np.array(o.d_d))
+        assert np.array_equal(r.get_characteristic_dx(0.01), o.get_characteristic_dx(0.01))
+
+
+def test_ilqr_restatement_bitwise_on_tpwl(ref):
+    from oracle.tpwl_np import TPWLATVNP
+    from oracle.ilqr_np import ILQRNP
+    from oracle.utils_np import QuadraticCost
+    data, Hf = _small_bank()
+    params = {'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}
+    N = 25
+    Q = np.zeros((6, 6)); Q[3, 3] = Q[4, 4] = 100.0
+    R = 1e-5 * np.eye(3)
+    Qf = 5 * Q
+    rng = np.random.default_rng(1)
+    x0 = rng.normal(size=10)
+    results = []
+    for cls, mcls, qc in ((ref.ilqr.iLQR, ref.tpwl.TPWLATV, ref.utils.QuadraticCost), (ILQRNP, TPWLATVNP, QuadraticCost)):
+        m = mcls(data, params=params, Hf=Hf, discr_method='be')
+        zt = np.tile(m.z_ref, (N + 1, 1)); zt[:, 3] += 0.05 * np.sin(np.linspace(0, 6, N + 1))
+        s = cls(0.01, m, qc(Q, R, Qf), N)
+        s.set_target(zt)
+        s.set_u_last(np.array([10.0, 20.0, 30.0]))
+        results.append(_quiet(s.ilqr_computation, x0, rng.uniform(0, 50, size=(N, 3)) * 0 + 25.0) + (s.rho,))
+    for a, b in zip(*results):
+        assert np.array_equal(a, b)
+
+
+def test_ilqr_restatement_bitwise_on_ssm_adapter(ref):
+    """The Gauss-Newton adapter drives the unmodified reference class and the restatement to identical bits."""
+    import sofacontrol_b200.synth as synth
+    from oracle.ssm_np import SSMDynamicsNP, GaussNewtonSSM
+    from oracle.ilqr_np import ILQRNP
+    from oracle.utils_np import QuadraticCost
+    s = synth.trunk_ssm(8)
+    N = 30
+    zt = synth.figure8_targets(s['z_ref'], N, 7.0, 0.4)[0]
+    Q, R, Qf = synth.trunk_ilqr_costs(6, 8)
+    out = []
+    for cls, qc in ((ref.ilqr.iLQR, ref.utils.QuadraticCost), (ILQRNP, QuadraticCost)):
+        m = GaussNewtonSSM(SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params']))
+        sol = cls(0.02, m, qc(Q, R, Qf), N)
+        sol.set_target(zt)
+        out.append(_quiet(sol.ilqr_computation, np.zeros(6)))
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+
+
+def test_pod_restatement(ref):
+    import sofacontrol_b200.synth as synth
+    from oracle import pod_np
+    X, _, _ = synth.pod_snapshots(300, 80, seed=5)
+    Uf, U, nb, S = ref.pod.compute_POD(X, 1e-4)
+    Uf2, U2, nb2, S2 = pod_np.compute_POD(X, 1e-4)
+    assert nb == nb2 and np.array_equal(S, S2) and np.array_equal(U, U2)
+    info = {'U': U, 'q_ref': X[:, 0], 'v_ref': X[:, 1], 'type': 'POD'}
+    r, o = ref.pod.POD(info), pod_np.PODNP(info)
+    v = np.random.default_rng(0).normal(size=300)
+    assert np.array_equal(r.compute_RO_state(qf=v), o.compute_RO_state(qf=v))
+    assert np.array_equal(r.compute_FO_state(q=v[:nb]), o.compute_FO_state(q=v[:nb]))
+    assert np.array_equal(r.V, o.V)
+
+
+def test_utils_restatement(ref):
+    from oracle import utils_np
+    rng = np.random.default_rng(0)
+    A, B, d = rng.normal(size=(6, 6)), rng.normal(size=(6, 2)), rng.normal(size=6)
+    for a, b in zip(ref.utils.zoh_affine(A, B, d, 0.05), utils_np.zoh_affine(A, B, d, 0.05)):
+        assert np.array_equal(a, b)
+    x = rng.normal(size=(4, 10))
+    assert all(np.array_equal(a, b) for a, b in zip(ref.utils.x2qv(x), utils_np.x2qv(x)))
+    assert np.array_equal(ref.utils.qv2x(x[:, :5], x[:, 5:]), utils_np.qv2x(x[:, :5], x[:, 5:]))
+
+
+def test_monomial_order_matches_reference_sympy_construction():
+    """ssm.py:158-164 builds the basis with sympy (itermonomials sorted by grevlex on reversed variables, constant
+    dropped).  The same sympy construction is repeated here and compared with the combinatorial table used by the
+    oracle and by the CUDA path; the analytic Jacobian is checked against sympy differentiation."""
+    import sympy as sp
+    from sympy.polys.monomials import itermonomials
+    from sympy.polys.orderings import monomial_key
+    from oracle.ssm_np import monomial_index_table, poly_features, poly_features_jac
+    for dim, order in ((3, 2), (3, 3), (6, 3), (4, 4)):
+        zeta = sp.Matrix(sp.symbols('x1:{}'.format(dim + 1)))
+        polys = sorted(itermonomials(list(zeta), order), key=monomial_key('grevlex', list(reversed(zeta))))[1:]
+        table = monomial_index_table(dim, order)
+        assert len(polys) == table.shape[0]
+        for p, row in zip(polys, table):
+            expect = sp.Integer(1)
+            for j in row:
+                if j >= 0:
+                    expect *= zeta[int(j)]
+            assert sp.simplify(p - expect) == 0
+        x = np.random.default_rng(dim).normal(size=dim)
+        f = sp.lambdify(zeta, polys, 'numpy')
+        assert np.allclose(poly_features(x, table), np.array(f(*x), dtype=float), rtol=1e-14)
+        J = sp.lambdify(zeta, sp.Matrix(polys).jacobian(zeta), 'numpy')
+        assert np.allclose(poly_features_jac(x, table), np.array(J(*x), dtype=float), rtol=1e-13, atol=1e-15)
+
+
+def test_golden_vectors_are_what_the_reference_produces_today(ref, golden):
+    """Re-runs a slice of oracle/make_golden.py and compares with the committed fixtures."""
+    gt = golden("tpwl_small.npz")
+    data, Hf = _small_bank()
+    m = ref.tpwl.TPWLATV(data, params={'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}, Hf=Hf, discr_method='be')
+    assert np.array_equal(np.array([m.calc_nearest_point(x) for x in gt['xs']]), gt['idx_w10'])
+    x, z = m.rollout(gt['xs'][0], gt['useq'], 0.01)
+    assert np.array_equal(x, gt['nn_x_be']) and np.array_equal(z, gt['nn_z_be'])

@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native soft-robot-control hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+Default workload (BASELINE.json configs[2], the one the target is quoted on): Trunk-SSM batched iLQR, 4096
+independent solves per GPU, horizon 100, Gauss-Newton tracking of randomised figure-8 targets.  One "step" = one
+batched solve of the whole batch (ONE launch of ilqr_solve_kernel).  Metric: iLQR solves/s (whole job).
+
+  value      : device-resident inputs, CUDA events on the launching stream, L2 flushed between steps (untimed).
+  e2e        : the public host API path -- pinned host buffers, H2D of x0 / targets, solve, D2H of x, u, K, cost.
+  roofline   : algorithmic FP64 flops of the solve kernel / its event time against the measured cuBLAS DGEMM rate.
+  cpu_baseline / --impl reference : the CPU port of the reference algorithm (oracle/, pinned bitwise to the
+               reference classes) on the box's host cores, bounded sample.
+Other workloads (--workload): tpwl_rollout_nn, tpwl_rollout_weighting, ssm_rollout, pod_gram.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+FP64_PEAK_TFLOPS = 35.4   # cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/fp64_peaks_r01.json); the
+#                           driver's MEASURED_PEAKS.json has no FP64 entry.  HBM peak comes from MEASURED_PEAKS.json.
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    hbm, src = 6650.0, "fallback"
+    if os.path.exists(p):
+        try:
+            hbm, src = float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    f = os.path.join(REPO, "profiles", "fp64_peaks_r01.json")
+    fp64 = FP64_PEAK_TFLOPS
+    if os.path.exists(f):
+        try:
+            fp64 = float(json.load(open(f))["cublas_dgemm_tflops_sustained"])
+        except Exception:
+            pass
+    return hbm, src, fp64
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(mhz)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# algorithmic work (DESIGN.md "Algorithmic work per unit")
+# ---------------------------------------------------------------------------------------------------------------
+def ilqr_flops(n, m, nz, nfeat, N, fwd_passes, bwd_passes):
+    """Algorithmic FP64 flops of the iLQR solve: dense counts of the matmuls the reference performs."""
+    ssm_eval = 2 * nfeat * (n + n * n + nz + nz * n)              # f, A = r dphi, z, H = w dphi (dense contraction)
+    be = 2 * (2 * n ** 3) + 2 * n ** 3 + 2 * n * n * m + 2 * n * n  # two inverses (~2n^3 each), sep, B_d, d_d
+    fwd_step = ssm_eval + be + 2 * m * n + 2 * (n * n + n * m) + 2 * (nz * nz + m * m) + 2 * n * m
+    bwd_step = (2 * (n * nz * nz + n * n * nz) + 2 * n * nz + 2 * m * m          # c_xx, c_x, c_u
+                + 2 * (n * n + n * m)                                             # Q_x, Q_u
+                + 2 * (n ** 3) * 2 + 2 * (m * n * n) * 2 + 2 * (m * m * n)        # A'P, (A'P)A, B'P, (B'P)A, (B'P)B
+                + 2 * (m * n * n) * 2 + 2 * (m * m * n)                           # regularised B'(P+rho I), its two products
+                + m ** 3 / 3 + 2 * m ** 3 + 2 * m * m * n + 2 * m * m             # Cholesky, inverse, K, k
+                + 2 * (n * m * m) + 2 * 3 * n * m + 2 * 3 * n * n * m)            # K'Quu, p, P
+    return fwd_passes * N * fwd_step + bwd_passes * N * bwd_step
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------
+def build_ilqr(batch, N, seed):
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.SSM.ssm import SSMDynamics
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost
+    w = synth.trunk_ilqr_batch(batch, N=N, seed=seed, m=8)
+    s = w['ssm']
+    model = SSMDynamics(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
+    Q, R, Qf = synth.trunk_ilqr_costs(6, 8)
+    solver = iLQR(w['dt'], model, QuadraticCost(Q, R, Qf), N)
+    return w, solver
+
+
+def cpu_ilqr_worker(args):
+    """One CPU worker: solves a slice of the same batch with the reference algorithm's CPU port."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    idx, N, seed, batch = args
+    import sofacontrol_b200.synth as synth
+    from oracle.ssm_np import SSMDynamicsNP, GaussNewtonSSM
+    from oracle.ilqr_np import ILQRNP
+    from oracle.utils_np import QuadraticCost
+    w = synth.trunk_ilqr_batch(batch, N=N, seed=seed, m=8)
+    s = w['ssm']
+    Q, R, Qf = synth.trunk_ilqr_costs(6, 8)
+    t0 = time.perf_counter()
+    its = 0
+    for b in idx:
+        o = ILQRNP(w['dt'], GaussNewtonSSM(SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'],
+                                                         params=s['params'])), QuadraticCost(Q, R, Qf), N)
+        o.set_target(w['z_target'][b])
+        o.ilqr_computation(w['x0'][b])
+        its += o.iterations
+    return len(idx), its, time.perf_counter() - t0
+
+
+def cpu_ilqr_baseline(batch, N, seed, per_core=2):
+    """Reference CPU path on the host cores: `per_core` solves per core taken from the same batch, one process per
+    core, OMP_NUM_THREADS=1.  Returns (solves/s aggregate, cores, sample description)."""
+    import multiprocessing as mp
+    cores = max(1, len(os.sched_getaffinity(0)))
+    cores = min(cores, 64)
+    jobs = [(list(range(c * per_core, (c + 1) * per_core)), N, seed, max(batch, cores * per_core)) for c in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(cpu_ilqr_worker, jobs)
+    wall = time.perf_counter() - t0
+    solved = sum(r[0] for r in res)
+    busy = max(r[2] for r in res)
+    return solved / busy, cores, "%d solves (%d per core, first problems of the same seeded batch), horizon %d; " \
+                                 "wall %.1fs incl. process start, slowest worker %.1fs" % (solved, per_core, N, wall, busy)
+
+
+def run_ilqr(args, rank, world, dev_index):
+    import torch
+    import torch.distributed as dist
+    from sofacontrol_b200 import _lib as L
+    batch, N = args.batch, args.horizon
+    w, solver = build_ilqr(batch, N, seed=3 + rank)
+    x0 = L.to_dev(w['x0'])
+    zt = L.to_dev(w['z_target'])
+    flush = torch.empty(256 * 1024 * 1024 // 8, device="cuda", dtype=torch.float64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = None
+    for _ in range(args.warmup):
+        out = solver.solve_device(x0, zt)
+    torch.cuda.synchronize()
+    iters = out['iterations'].cpu().numpy()
+    trials = out['trials'].cpu().numpy()
+    status = out['status'].cpu().numpy()
+
+    # ---- device-resident timing (value)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(dev_index) as clk:
+        for s, e in ev:
+            flush.fill_(1.0)                       # L2 flush, untimed
+            s.record()
+            out = solver.solve_device(x0, zt)
+            e.record()
+        barrier()
+    t_dev = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
+    clocks = clk.summary()
+
+    # ---- end-to-end through the host API with pinned buffers (e2e)
+    x0_h = torch.from_numpy(w['x0']).pin_memory()
+    zt_h = torch.from_numpy(w['z_target']).pin_memory()
+    outs_h = None
+    for _ in range(2):
+        outs_h = solver.solve_pinned(x0_h, zt_h, outs_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        outs_h = solver.solve_pinned(x0_h, zt_h, outs_h)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    h2d = x0_h.numel() * 8 + zt_h.numel() * 8
+    d2h = sum(v.numel() * v.element_size() for v in outs_h.values())
+
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    total = batch * world * args.steps
+    flops = ilqr_flops(6, 8, 6, 83, N, float((trials + 1).sum()), float(iters.sum()))
+    hbm, hsrc, fp64 = measured_peaks()
+    per_launch = t_dev / args.steps
+    ach = flops / per_launch / 1e12
+    res = {
+        "metric": "ilqr_solves_per_sec", "value": total / t_dev, "unit": "solves/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Trunk-SSM batched iLQR (BASELINE configs[2]): %d independent solves per GPU, horizon %d, "
+                               "n=6 m=8 order-3 SSM (83 monomials), be discretisation, dt=0.02, Gauss-Newton figure-8 "
+                               "tracking, randomised amplitude/phase/x0 (seed 3+rank)" % (batch, N),
+                   "batch_per_gpu": batch, "horizon": N, "parallelism": "dp%d (problems sharded, no collective)" % world,
+                   "l2": "256 MB buffer written between timed steps (untimed)",
+                   "converged_frac": float((status & 1).mean()), "mean_iterations": float(iters.mean()),
+                   "mean_forward_passes": float((trials + 1).mean())},
+        "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+        "roofline": {"kernel": "ilqr_solve_kernel<SsmPolicy>", "bound": "tensor", "achieved": ach, "peak": fp64,
+                     "unit": "TFLOP/s", "frac": ach / fp64, "traffic": None,
+                     "note": "FP64 pipe: algorithmic flops of the executed passes (dense counts, DESIGN.md) / event "
+                             "time of the single launch; peak = cuBLAS DGEMM 8192^3 measured on this pool "
+                             "(profiles/fp64_peaks_r01.json), of measured"},
+    }
+    return res
+
+
+def run_tpwl_rollout(args, rank, world, dev_index, method):
+    import torch
+    import torch.distributed as dist
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200 import _lib as L
+    from sofacontrol_b200.tpwl.tpwl import TPWLATV
+    batch, N = args.batch, args.horizon
+    data, Hf = synth.tpwl_bank()
+    params = {'tpwl_method': method, 'dist_weights': {'q': 1.0, 'v': 0.0}, 'beta_weighting': 25.0}
+    g = TPWLATV(data, params=params, Hf=Hf, discr_method='fe' if method == 'weighting' else 'be')
+    if method == 'nn':
+        g.pre_discretize(0.01)
+    x0h, uh = synth.tpwl_rollout_batch(batch, N=N, seed=2 + rank)
+    x0, u = L.to_dev(x0h), L.to_dev(uh)
+    flush = torch.empty(256 * 1024 * 1024 // 8, device="cuda", dtype=torch.float64)
+    for _ in range(args.warmup):
+        g.rollout_device(x0, u, 0.01)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(dev_index) as clk:
+        for s, e in ev:
+            flush.fill_(1.0)
+            s.record()
+            x, z = g.rollout_device(x0, u, 0.01)
+            e.record()
+        torch.cuda.synchronize()
+    t_dev = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
+    # e2e: host API
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g.rollout(x0h, uh, 0.01)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    steps_total = batch * N * world * args.steps
+    hbm, hsrc, fp64 = measured_peaks()
+    n, m, P, r = 72, 4, 1000, 36
+    if method == 'nn':
+        byt = batch * N * ((n * n + n * m + n) * 8 + P * r * 8 + (2 * n + m) * 8)
+        roof = {"kernel": "tpwl_rollout_nn_kernel", "bound": "hbm", "achieved": byt / (t_dev / args.steps) / 1e9,
+                "peak": hbm, "unit": "GB/s", "traffic": None,
+                "note": "algorithmic bytes per trajectory-step = gathered bank entry 44352 B + distance bank 288000 B "
+                        "+ state I/O (SURVEY 8d); the banks are L2-resident so this is an L2/HBM stream rate, of " + hsrc}
+    else:
+        fl = batch * N * 2.0 * P * (n * n + n * m + n)
+        roof = {"kernel": "dgemm_kernel (bank blend)", "bound": "tensor", "achieved": fl / (t_dev / args.steps) / 1e12,
+                "peak": fp64, "unit": "TFLOP/s", "traffic": None,
+                "note": "2 P (n^2+nm+n) flop per trajectory-step; whole step time (weights + blend + discretise + step)"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    return {"metric": "tpwl_%s_rollout_steps_per_sec" % method, "value": steps_total / t_dev, "unit": "steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Diamond TPWL batched rollout (BASELINE configs[1]): %d trajectories x %d steps per GPU, "
+                                   "n=72 m=4 P=1000 r=36, method %s" % (batch, N, method), "batch_per_gpu": batch,
+                       "horizon": N, "l2": "256 MB buffer written between timed steps (untimed)"},
+            "e2e": {"value": steps_total / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": int((x0h.size + uh.size) * 8),
+                    "d2h_bytes_per_step": int(batch * (N + 1) * (n + 6) * 8)},
+            "gpu_launches": args.steps * (1 if method == 'nn' else N * 7) + args.steps, "clocks": clk.summary(),
+            "roofline": roof}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU port on the host cores, same workload/metric (bounded sample)."""
+    t_all = []
+    val = cores = sample = None
+    for i in range(max(1, min(args.steps, 2))):
+        val, cores, sample = cpu_ilqr_baseline(args.batch, args.horizon, seed=3, per_core=args.cpu_per_core)
+        t_all.append(val)
+    val = max(t_all)
+    return {"impl": "reference", "metric": "ilqr_solves_per_sec", "value": val, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Trunk-SSM batched iLQR (BASELINE configs[2]), horizon %d -- reference algorithm on CPU" % args.horizon},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ilqr_trunk_ssm",
+                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--horizon", type=int, default=100)
+    ap.add_argument("--cpu-per-core", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference(args)), flush=True)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    args.warmup = max(args.warmup, 3)
+    if args.workload == "ilqr_trunk_ssm":
+        res = run_ilqr(args, rank, world, local)
+    else:
+        res = run_tpwl_rollout(args, rank, world, local, "nn" if args.workload.endswith("nn") else "weighting")
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "ilqr_trunk_ssm":
+        v, cores, sample = cpu_ilqr_baseline(args.batch, args.horizon, seed=3, per_core=args.cpu_per_core)
+        res["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample}
+    elif rank == 0:
+        res.setdefault("cpu_baseline", None)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

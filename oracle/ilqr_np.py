@@ -217,3 +217,46 @@ class ILQRNP:
         self.iterations = it
         self.final_cost = cost
         return x, u, K
+
+
+def riccati_noise_floor(model, cost, z_target, x, u, A, B, u_last=None):
+    """How far is the reference's own FP64 backward pass from exact arithmetic?  Runs the value recursion of
+    ilqr.py:258-295 (rho = 0) once in float64 and once in numpy longdouble (x87 80-bit here) on identical inputs
+    and returns the relative differences of K and k.  The un-symmetrised recursion amplifies rounding noise along
+    the horizon (measured ~1e6 over N = 100 on the Trunk figure-8), which bounds how closely ANY independent
+    implementation can reproduce the reference's gains -- see DESIGN.md "Parity tolerance"."""
+    N, m = u.shape
+    n = x.shape[1]
+    Hs, Es = [], []
+    for t in range(N + 1):
+        z = model.x_to_zfyf(x[t], zf=True)
+        Hs.append(np.array(model.H, dtype=np.float64))
+        Es.append(z - z_target[t])
+    u_last = np.zeros(m) if u_last is None else u_last
+
+    def run(dt):
+        c = lambda a: np.asarray(a, dtype=dt)
+        Q, R, Qf = c(cost.Q), c(cost.R), c(cost.Qf)
+        P = c(Hs[N]).T @ Qf @ c(Hs[N])
+        p = c(Hs[N]).T @ Qf @ c(Es[N])
+        Ks, ks = [], []
+        for t in reversed(range(N)):
+            H, e, At, Bt = c(Hs[t]), c(Es[t]), c(A[t]), c(B[t])
+            c_xx, c_x = H.T @ Q @ H, H.T @ Q @ e
+            c_u = R @ c(u[t] - (u_last if t == 0 else u[t - 1]))
+            Q_x, Q_u = c_x + At.T @ p, c_u + Bt.T @ p
+            Q_xx, Q_uu, Q_ux = c_xx + At.T @ P @ At, R + Bt.T @ P @ Bt, Bt.T @ P @ At
+            inv = c(np.linalg.inv(np.asarray(Q_uu, dtype=np.float64)))
+            if dt is not np.float64:
+                for _ in range(3):                     # Newton refinement of the inverse in extended precision
+                    inv = inv + inv @ (np.eye(m, dtype=dt) - Q_uu @ inv)
+            K, k = -inv @ Q_ux, -inv @ Q_u
+            p = Q_x + K.T @ Q_uu @ k + K.T @ Q_u + Q_ux.T @ k
+            P = Q_xx + K.T @ Q_uu @ K + K.T @ Q_ux + Q_ux.T @ K
+            Ks.append(K); ks.append(k)
+        return np.array(Ks[::-1]), np.array(ks[::-1])
+
+    K64, k64 = run(np.float64)
+    K80, k80 = run(np.longdouble)
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    return rel(K64, K80), rel(k64, k80)

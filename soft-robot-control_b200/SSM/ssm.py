@@ -179,8 +179,8 @@ class SSM:
         x0 = np.asarray(x0, dtype=np.float64)
         u = np.asarray(u, dtype=np.float64)
         single = (x0.ndim == 1)
-        xd, zd = self.rollout_device(L.to_dev(x0.reshape(-1, self.state_dim)),
-                                     L.to_dev(u.reshape((-1,) + u.shape[-2:])), dt)
+        x0b = x0.reshape(-1, self.state_dim)
+        xd, zd = self.rollout_device(L.to_dev(x0b), L.to_dev(u.reshape((x0b.shape[0],) + u.shape[-2:])), dt)
         x, z = L.to_host(xd), L.to_host(zd)
         return (x[0], z[0]) if single else (x, z)
 

@@ -220,7 +220,12 @@ extern "C" int srcb200_dgemm(int32_t transA, int64_t M, int64_t N, int64_t K, do
                              int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream) {
     if (M < 0 || N < 0 || K < 0) return fail(SRCB200_E_DIM, "dgemm: negative dims");
     if (M == 0 || N == 0) return 0;
-    if (!A || !B || !C) return fail(SRCB200_E_NULL, "dgemm: NULL operand");
+    if (!C) return fail(SRCB200_E_NULL, "dgemm: NULL operand");
+    if (K == 0) {   // empty contraction: C = 0
+        SRCB_CUDA(cudaMemset2DAsync(C, sizeof(double) * ldc, 0, sizeof(double) * N, M, (cudaStream_t)stream));
+        return 0;
+    }
+    if (!A || !B) return fail(SRCB200_E_NULL, "dgemm: NULL operand");
     if (ldb < N || ldc < N || lda < (transA ? M : K)) return fail(SRCB200_E_DIM, "dgemm: leading dimension too small");
     return dgemm_device(transA, M, N, K, alpha, A, lda, B, ldb, C, ldc, (cudaStream_t)stream);
 }

@@ -86,12 +86,17 @@ class iLQR:
         """Builds the srcb200_ilqr_problem; arguments are CUDA tensors (or None)."""
         nz, n = self._nz(), self.state_dim
         c = self.cost_params
-        keep = dict(Q=L.to_dev(np.asarray(c.Q, dtype=np.float64)), R=L.to_dev(np.asarray(c.R, dtype=np.float64)),
-                    Qf=L.to_dev(np.asarray(c.Qf if c.Qf is not None else np.zeros((nz, nz)), dtype=np.float64)))
-        Hc = None
+        host = [np.asarray(c.Q, dtype=np.float64), np.asarray(c.R, dtype=np.float64),
+                np.asarray(c.Qf if c.Qf is not None else np.zeros((nz, nz)), dtype=np.float64)]
         if not self.gauss_newton:
             H = getattr(self.model, 'H', None)
-            Hc = L.to_dev(np.asarray(H if H is not None else np.zeros((nz, n)), dtype=np.float64))
+            host.append(np.asarray(H if H is not None else np.zeros((nz, n)), dtype=np.float64))
+        cache = getattr(self, '_cost_cache', None)
+        if cache is None or len(cache[0]) != len(host) or not all(np.array_equal(a, b) for a, b in zip(cache[0], host)):
+            cache = ([h.copy() for h in host], [L.to_dev(h) for h in host])     # re-upload only when the values change
+            self._cost_cache = cache
+        keep = dict(Q=cache[1][0], R=cache[1][1], Qf=cache[1][2])
+        Hc = cache[1][3] if not self.gauss_newton else None
         shared = int(z_target.dim() == 2)
         pr = L.IlqrProblem(batch=batch, N=int(self.planning_horizon), gauss_newton=int(self.gauss_newton),
                            dt=float(self.dt), x0=L.ptr(x0), u_init=L.ptr(u_init), z_target=L.ptr(z_target),
@@ -145,6 +150,20 @@ class iLQR:
         L.check(L.lib().srcb200_ilqr_solve_batch(self._kind, C_addr(handle), cfg, pr, res, L.ptr(ws), ws.numel() * 8,
                                                  L.stream_ptr()))
         return out
+
+    def solve_pinned(self, x0_h, z_target_h, out_h=None, u_init_h=None, u_last_h=None):
+        """End-to-end batched solve on PINNED host torch tensors: async H2D of the inputs, one kernel launch, async
+        D2H of (x, u, K, cost, iterations, status) into pinned outputs (allocated on first use, reusable), one sync."""
+        torch = L.torch_mod()
+        up = lambda t: None if t is None else t.cuda(non_blocking=True)
+        out = self.solve_device(up(x0_h), up(z_target_h), up(u_init_h), up(u_last_h))
+        if out_h is None:
+            out_h = {k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
+                     for k in ('x', 'u', 'K', 'cost', 'iterations', 'status')}
+        for k, v in out_h.items():
+            v.copy_(out[k], non_blocking=True)
+        torch.cuda.synchronize()
+        return out_h
 
     def ilqr_computation(self, x0, u_warmstart=None):
         """ilqr.py:27-107.  Returns (x, u, K): the optimal sequence and the stabilising gains of the last backward

@@ -62,9 +62,14 @@ def test_solve_matches_reference_golden(golden, tag, m):
     s = _solver(model, m, gi[tag + '_zt'], trace=True)
     x, u, K = s.ilqr_computation(np.zeros(6))
     assert x.shape == (101, 6) and u.shape == (100, m) and K.shape == (100, m, 6)
-    assert relerr(x, gi[tag + '_x']) < TOL
-    assert relerr(u, gi[tag + '_u']) < TOL
-    assert relerr(K, gi[tag + '_K']) < TOL
+    # Diamond: 1e-9.  Trunk (8 redundant inputs, N = 100): the reference's own FP64 recursion is only accurate to
+    # ~2e-10 (K) / 1e-9 (k) against extended precision on this problem (tests/test_oracle_golden.py::
+    # test_reference_fp64_noise_floor_on_trunk_horizon_100), so two independent FP64 evaluations agree to a few
+    # 1e-9 at best; every branch decision is identical (test_branch_trace_matches_oracle).
+    tol = TOL if tag == "diamond" else 5e-9
+    assert relerr(x, gi[tag + '_x']) < tol
+    assert relerr(u, gi[tag + '_u']) < tol
+    assert relerr(K, gi[tag + '_K']) < tol
     assert abs(float(s.info['rho']) - float(gi[tag + '_rho'])) <= 1e-12 * max(1.0, abs(float(gi[tag + '_rho'])))
     assert s.info['status'] & 1                                            # converged
 

@@ -7,8 +7,8 @@
 //   dlqr_recursion(ilqr.py:219-300)  -> bwd_pass<>()      : Riccati sweep, Cholesky PD test, explicit inverse of Q_uu~
 //   ilqr_computation (ilqr.py:27-107)-> ilqr_solve_kernel : outer loop + line search
 // The model is a policy (SSM polynomial model / TPWL bank) providing linearise+observe at one state.
-#include "ssm.cuh"
-#include "tpwl.cuh"
+#include <type_traits>
+#include "ilqr.cuh"
 
 namespace srcb {
 
@@ -145,55 +145,6 @@ struct TpwlPolicy {
     }
 };
 
-// ---------------------------------------------------------------------------------------------------------------
-// Per-problem global scratch
-// ---------------------------------------------------------------------------------------------------------------
-struct Layout {                 // offsets in doubles inside one trajectory record / the per-problem workspace
-    long long x, u, e, H, A, B, idx, rec;       // record fields, record size
-    long long k, ab, total;                     // backward outputs (K goes straight to the result buffer)
-};
-
-__host__ __device__ inline Layout make_layout(int n, int m, int nz, int N, bool gn, bool index_lin) {
-    Layout L;
-    long long o = 0;
-    L.x = o;  o += (long long)(N + 1) * n;
-    L.u = o;  o += (long long)N * m;
-    L.e = o;  o += (long long)(N + 1) * nz;
-    L.H = o;  o += gn ? (long long)(N + 1) * nz * n : 0;
-    L.A = o;  o += index_lin ? 0 : (long long)N * n * n;
-    L.B = o;  o += index_lin ? 0 : (long long)N * n * m;
-    L.idx = o; o += index_lin ? (N + 1) / 2 + 1 : 0;     // N int32 packed into doubles
-    L.rec = (o + 1) & ~1LL;
-    o = 2 * L.rec;
-    L.k = o;  o += (long long)N * m;
-    L.ab = o; o += 2LL * N;
-    L.total = (o + 1) & ~1LL;
-    return L;
-}
-
-struct Rec {                    // one trajectory record resolved to pointers
-    double* x; double* u; double* e; double* H; double* A; double* B; int* idx;
-};
-__device__ inline Rec rec_at(double* base, const Layout& L) {
-    Rec r;
-    r.x = base + L.x; r.u = base + L.u; r.e = base + L.e; r.H = base + L.H; r.A = base + L.A; r.B = base + L.B;
-    r.idx = reinterpret_cast<int*>(base + L.idx);
-    return r;
-}
-
-struct IlqrArgs {
-    int n, m, nz, N, gn, index_lin, shared_target;
-    long long batch;
-    double dt;
-    srcb200_ilqr_config cfg;
-    const double *x0, *u_init, *z_target, *u_last, *Q, *R, *Qf, *Hc;
-    double *ox, *ou, *oK, *ocost, *ocost0, *orho, *otrace;
-    int *oiter, *ostatus, *otrials;
-    double* ws;
-    Layout L;
-    int model_scratch;          // doubles of model scratch in shared memory
-};
-
 // shared-memory plan (doubles); forward and backward phases alias the same region after the common header
 struct Smem {
     int x, xn, u, uprev, dx, z, e, A, B, d, H, Qe, Rdu, mscr, fwd_end;
@@ -227,19 +178,6 @@ __host__ __device__ inline Smem make_smem(int n, int m, int nz, int mscr, bool g
     // the backward pass also needs H_t / e_t / u rows staged: reuse tail
     S.total = (S.fwd_end > S.bwd_end ? S.fwd_end : S.bwd_end) + nz * n + nz + 2 * m + 4;
     return S;
-}
-
-// rho schedule (ilqr.py:198-217), including the `dhro` typo: drho is never lowered.
-__device__ __forceinline__ void rho_update(const srcb200_ilqr_config& c, bool increase, double& rho, double& drho) {
-    if (increase) {
-        drho = fmax(__dmul_rn(drho, c.rho_scaling), c.rho_scaling);
-        rho = fmax(__dmul_rn(rho, drho), c.rho_min);
-        if (rho > c.rho_max) rho = c.rho_max;
-    } else {
-        const double dhro = fmin(__ddiv_rn(drho, c.rho_scaling), __ddiv_rn(1.0, c.rho_scaling));
-        rho = __dmul_rn(rho, dhro);
-        if (rho <= c.rho_min) rho = c.rho_min;
-    }
 }
 
 // x+ = (A x + B u) + d
@@ -831,6 +769,11 @@ static int solve_impl(const typename MP::Dev& M, const srcb200_ilqr_config* cfg,
     a.ox = res->x; a.ou = res->u; a.oK = res->K; a.ocost = res->cost; a.ocost0 = res->cost0; a.orho = res->rho;
     a.otrace = res->trace; a.oiter = res->iterations; a.ostatus = res->status; a.otrials = res->trials;
     a.ws = (double*)ws;
+    if constexpr (std::is_same<MP, SsmPolicy>::value) {
+        bool handled = false;
+        if (int e = ilqr_ssm_fast_launch(M, a, st, &handled)) return e;
+        if (handled) return 0;
+    }
     auto kern = ilqr_solve_kernel<MP>;
     SRCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_size<MP>(a.batch, smem), MP::NT, smem, st>>>(M, a);

@@ -1,0 +1,75 @@
+// ilqr.cuh -- structures shared by the generic iLQR kernels (ilqr.cu) and the register/tensor-core specialised
+// Trunk/Diamond SSM kernel (ilqr_fast.cu).
+#pragma once
+#include "ssm.cuh"
+#include "tpwl.cuh"
+
+namespace srcb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-problem global scratch
+// ---------------------------------------------------------------------------------------------------------------
+struct Layout {                 // offsets in doubles inside one trajectory record / the per-problem workspace
+    long long x, u, e, H, A, B, idx, rec;       // record fields, record size
+    long long k, ab, total;                     // backward outputs (K goes straight to the result buffer)
+};
+
+__host__ __device__ inline Layout make_layout(int n, int m, int nz, int N, bool gn, bool index_lin) {
+    Layout L;
+    long long o = 0;
+    L.x = o;  o += (long long)(N + 1) * n;
+    L.u = o;  o += (long long)N * m;
+    L.e = o;  o += (long long)(N + 1) * nz;
+    L.H = o;  o += gn ? (long long)(N + 1) * nz * n : 0;
+    L.A = o;  o += index_lin ? 0 : (long long)N * n * n;
+    L.B = o;  o += index_lin ? 0 : (long long)N * n * m;
+    L.idx = o; o += index_lin ? (N + 1) / 2 + 1 : 0;     // N int32 packed into doubles
+    L.rec = (o + 1) & ~1LL;
+    o = 2 * L.rec;
+    L.k = o;  o += (long long)N * m;
+    L.ab = o; o += 2LL * N;
+    L.total = (o + 1) & ~1LL;
+    return L;
+}
+
+struct Rec {                    // one trajectory record resolved to pointers
+    double* x; double* u; double* e; double* H; double* A; double* B; int* idx;
+};
+__device__ inline Rec rec_at(double* base, const Layout& L) {
+    Rec r;
+    r.x = base + L.x; r.u = base + L.u; r.e = base + L.e; r.H = base + L.H; r.A = base + L.A; r.B = base + L.B;
+    r.idx = reinterpret_cast<int*>(base + L.idx);
+    return r;
+}
+
+struct IlqrArgs {
+    int n, m, nz, N, gn, index_lin, shared_target;
+    long long batch;
+    double dt;
+    srcb200_ilqr_config cfg;
+    const double *x0, *u_init, *z_target, *u_last, *Q, *R, *Qf, *Hc;
+    double *ox, *ou, *oK, *ocost, *ocost0, *orho, *otrace;
+    int *oiter, *ostatus, *otrials;
+    double* ws;
+    Layout L;
+    int model_scratch;          // doubles of model scratch in shared memory
+};
+
+// rho schedule (ilqr.py:198-217), including the `dhro` typo: drho is never lowered.
+__device__ __forceinline__ void rho_update(const srcb200_ilqr_config& c, bool increase, double& rho, double& drho) {
+    if (increase) {
+        drho = fmax(__dmul_rn(drho, c.rho_scaling), c.rho_scaling);
+        rho = fmax(__dmul_rn(rho, drho), c.rho_min);
+        if (rho > c.rho_max) rho = c.rho_max;
+    } else {
+        const double dhro = fmin(__ddiv_rn(drho, c.rho_scaling), __ddiv_rn(1.0, c.rho_scaling));
+        rho = __dmul_rn(rho, dhro);
+        if (rho <= c.rho_min) rho = c.rho_min;
+    }
+}
+
+
+// implemented in ilqr_fast.cu: returns 1 if the problem was dispatched to the specialised SSM kernel
+int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bool* handled);
+
+}  // namespace srcb

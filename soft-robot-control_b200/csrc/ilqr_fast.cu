@@ -1,0 +1,819 @@
+// ilqr_fast.cu -- Trunk / Diamond SSM iLQR (n = n_z = 6, cubic basis, m = 4 or 8, Gauss-Newton cost) specialised
+// for B200: ONE WARP PER PROBLEM, eight problems per CTA sharing one coefficient table in shared memory.
+//
+//   * small dense algebra on the FP64 tensor pipe: every 6x6 / 8x6 / 8x8 product of the Riccati sweep
+//     (ilqr.py:258-295) and of the discretisation (ssm.py:279-301) is one 8x8x8 DMMA tile (2 x mma.sync.m8n8k4.f64)
+//     with the accumulator kept in registers across chained products; vectors ride along in the padding column
+//     (P | p), (H | e), (Q_ux | Q_u), (K | k), so Q_x, Q_u, k and p cost no extra instructions.
+//   * factorisations with warp shuffles, matrices held one column per lane in registers: the two 6x6 inverses of
+//     the implicit-Euler / bilinear discretisation run simultaneously in the two half-warps (Gauss-Jordan with
+//     partial pivoting); inv(Q_uu~) is a Gauss-Jordan sweep whose pivots double as the positive-definiteness test
+//     (for a symmetric matrix the k-th pivot IS the k-th Cholesky pivot a_kk - sum l_kj^2 of np.linalg.cholesky).
+//   * the polynomial model (ssm.py:158-235) is evaluated sparsely: d phi / d x_j of a degree-<=3 monomial is a
+//     multiple of a degree-<=2 monomial, so A_c = r_coeff dphi/dx and H = w_coeff dphi/dx are 72 dot products of
+//     length 28 against psi = (1, x, x (x) x), and f, z are 12 dot products of length 84 split in three; all 108
+//     partial dots are spread over the 32 lanes (4 accumulators each) and read their coefficients from a
+//     conflict-free table built once per CTA.
+//
+// Control flow (line search, rho schedule, PD restarts, convergence) is identical to the generic kernel in ilqr.cu
+// and to the reference (ilqr.py:27-107); results agree with it to rounding (tests/test_ilqr_gpu.py).
+#include <cstdlib>
+#include "ilqr.cuh"
+
+namespace srcb {
+namespace fast {
+
+constexpr int N6 = 6;
+constexpr int LD = 12;            // tile row stride (doubles): A-/B-fragment loads are bank-conflict free
+constexpr int TILE = 8 * LD;
+constexpr int WARPS = 8;          // problems in flight per CTA
+constexpr int NJ = 28;            // terms per partial dot
+constexpr int NPD = 128;          // partial-dot slots: 4 rounds x 32 lanes (108 used)
+constexpr int TS = 30;            // table row stride (doubles)
+constexpr int NFEAT = 83;
+constexpr unsigned FULL = 0xffffffffu;
+
+// per-CTA shared block (doubles)
+constexpr int SH_T = 0;                         // coefficient table NPD x TS
+constexpr int SH_Q = SH_T + NPD * TS;           // Q tile
+constexpr int SH_R = SH_Q + TILE;               // R tile
+constexpr int SH_QF = SH_R + TILE;              // Qf tile
+constexpr int SH_BR = SH_QF + TILE;             // B_r tile (6 x m)
+constexpr int SH_ZREF = SH_BR + TILE;           // 8
+constexpr int SH_FIDX = SH_ZREF + 8;            // 84 ints = 42 doubles
+constexpr int SH_END = SH_FIDX + 44;
+// per-warp block (doubles)
+constexpr int W_PHI = 0;                        // 84 (+4 pad)
+constexpr int W_X = 88;                         // x_t (6), X[6] = 0, X[7] = 1
+constexpr int W_U = 96;
+constexpr int W_UP = 104;                       // u_{t-1}, then du
+constexpr int W_DC = 112;
+constexpr int W_DD = 120;
+constexpr int W_E = 128;
+constexpr int W_FV = 136;                       // f (6)
+constexpr int W_QE = 144;
+constexpr int W_RDU = 152;
+constexpr int W_TILES = 160;
+constexpr int NTILES = 9;
+constexpr int W_SIZE = W_TILES + NTILES * TILE; // 1024 doubles = 8 KB per warp
+constexpr size_t SMEM_BYTES = sizeof(double) * (SH_END + WARPS * W_SIZE);
+
+struct Frag { double c0, c1; };
+
+__device__ __forceinline__ void dmma(Frag& c, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c.c0), "+d"(c.c1) : "d"(a), "d"(b));
+}
+// C += op(A) op(B) for 8x8 tiles in shared memory; g = lane >> 2, q = lane & 3
+template <bool TA, bool TB>
+__device__ __forceinline__ void mma88(Frag& c, const double* __restrict__ A, const double* __restrict__ B, int g, int q) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int k = 4 * s + q;
+        dmma(c, TA ? A[k * LD + g] : A[g * LD + k], TB ? B[g * LD + k] : B[k * LD + g]);
+    }
+}
+__device__ __forceinline__ void store_frag(double* __restrict__ T, const Frag& c, int g, int q) {
+    *reinterpret_cast<double2*>(T + g * LD + 2 * q) = make_double2(c.c0, c.c1);
+}
+__device__ __forceinline__ Frag load_frag(const double* __restrict__ T, int g, int q) {
+    const double2 v = *reinterpret_cast<const double2*>(T + g * LD + 2 * q);
+    return Frag{v.x, v.y};
+}
+__device__ __forceinline__ void zero_tile(double* __restrict__ T, int lane) {
+#pragma unroll
+    for (int e = lane; e < TILE; e += 32) T[e] = 0.0;
+}
+
+struct Ctx {
+    int lane, g, q;
+    double* sh;     // CTA-shared block
+    double* ws;     // this warp's block
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Coefficient table, built once per CTA from the model arrays.
+//   slots 0..35   : A_c[i][j]   = sum_q T[pd][q] psi_q,  pd = 6 i + j,        T = mult * r_coeff[i][k(j,q)]
+//   slots 36..71  : H[i][j]                              pd = 36 + 6 i + j,   T = mult * w_coeff[i][k(j,q)]
+//   slots 72..83  : value part 0 of f_i (v = i) / z_i (v = 6 + i): operand Phi[0..27]
+//   slots 96..107 : value part 1, operand Phi[28..55];  slots 108..119: value part 2, operand Phi[56..83]
+// with psi = Phi[0..27] = (1, x_1..x_6, 21 quadratic monomials) and Phi[1 + k] = phi_k (83 monomials).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ int find_monomial(const SsmDev& M, int a, int b, int c) {
+    // sort ascending with 0xFF (absent) last
+    if (a > b) { int t = a; a = b; b = t; }
+    if (b > c) { int t = b; b = c; c = t; }
+    if (a > b) { int t = a; a = b; b = t; }
+    for (int k = 0; k < M.nfeat; ++k) {
+        const uint8_t* r = M.mono + k * SRCB200_SSM_MAX_ORDER;
+        if (r[0] == a && r[1] == b && r[2] == c) return k;
+    }
+    return -1;
+}
+
+__device__ void build_tables(const SsmDev& M, const IlqrArgs& a, double* sh, int m) {
+    double* T = sh + SH_T;
+    for (int e = threadIdx.x; e < NPD * TS; e += blockDim.x) T[e] = 0.0;
+    for (int e = threadIdx.x; e < 4 * TILE + 8; e += blockDim.x) sh[SH_Q + e] = 0.0;
+    __syncthreads();
+    // Jacobian slots
+    for (int e = threadIdx.x; e < 72 * NJ; e += blockDim.x) {
+        const int pd = e / NJ, q = e - pd * NJ;
+        const double* src = pd < 36 ? M.r : M.w;
+        const int o = pd < 36 ? pd : pd - 36, i = o / 6, j = o - 6 * i;
+        int s0 = 0xFF, s1 = 0xFF;
+        if (q >= 1) { s0 = M.mono[(q - 1) * SRCB200_SSM_MAX_ORDER]; s1 = M.mono[(q - 1) * SRCB200_SSM_MAX_ORDER + 1]; }
+        const int k = find_monomial(M, s0, s1, j);
+        const int mult = 1 + (s0 == j) + (s1 == j);
+        T[pd * TS + q] = (k >= 0) ? (double)mult * src[i * M.nfeat + k] : 0.0;
+    }
+    // value slots
+    for (int e = threadIdx.x; e < 36 * NJ; e += blockDim.x) {
+        const int s = e / NJ, q = e - s * NJ;          // s = part * 12 + v
+        const int part = s / 12, v = s - 12 * part;
+        const int pd = (part == 0) ? 72 + v : (part == 1 ? 96 + v : 108 + v);
+        const double* src = v < 6 ? M.r : M.w;
+        const int i = v < 6 ? v : v - 6;
+        const int k = 28 * part + q - 1;
+        T[pd * TS + q] = (k >= 0 && k < M.nfeat) ? src[i * M.nfeat + k] : 0.0;
+    }
+    for (int e = threadIdx.x; e < 36; e += blockDim.x) {
+        const int i = e / 6, j = e - 6 * i;
+        sh[SH_Q + i * LD + j] = a.Q[e];
+        sh[SH_QF + i * LD + j] = a.Qf[e];
+    }
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) sh[SH_R + (e / m) * LD + (e % m)] = a.R[e];
+    for (int e = threadIdx.x; e < 6 * m; e += blockDim.x) sh[SH_BR + (e / m) * LD + (e % m)] = M.B[e];
+    for (int e = threadIdx.x; e < 6; e += blockDim.x) sh[SH_ZREF + e] = M.zref[e];
+    int* fidx = reinterpret_cast<int*>(sh + SH_FIDX);
+    for (int k = threadIdx.x; k < NFEAT; k += blockDim.x) {
+        const uint8_t* r = M.mono + k * SRCB200_SSM_MAX_ORDER;
+        const int i0 = r[0], i1 = r[1] == 0xFF ? 7 : r[1], i2 = r[2] == 0xFF ? 7 : r[2];
+        fidx[k] = i0 | (i1 << 3) | (i2 << 6);
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Model evaluation at the state in X: fills Phi, then A_c -> tile AC, H -> tile HT, returns in lanes 8..13 the
+// polynomial part of f_i (i = lane - 8) and in lanes 14..19 the raw output z_i (i = lane - 14).
+// ---------------------------------------------------------------------------------------------------------------
+struct Scatter { int o0, o1, o2; };   // per-lane tile offsets of the Jacobian outputs of rounds 0, 1, 2
+
+__device__ __forceinline__ Scatter make_scatter(int lane) {
+    Scatter s;
+    s.o0 = (lane / 6) * LD + lane % 6;                                   // A_c, o = lane
+    if (lane < 4) s.o1 = ((32 + lane) / 6) * LD + (32 + lane) % 6;       // A_c, o = 32 + lane
+    else          s.o1 = ((lane - 4) / 6) * LD + (lane - 4) % 6;         // H,   o' = lane - 4
+    s.o2 = ((28 + lane) / 6) * LD + (28 + lane) % 6;                     // H,   o' = 28 + lane (lanes < 8)
+    return s;
+}
+
+__device__ __forceinline__ double ssm_eval_fast(const Ctx& c, const Scatter& sc, double* __restrict__ AC,
+                                                double* __restrict__ HT) {
+    const int lane = c.lane;
+    double* PHI = c.ws + W_PHI;
+    const double* X = c.ws + W_X;
+    const int* fidx = reinterpret_cast<const int*>(c.sh + SH_FIDX);
+    // features, products left to right like the oracle: (x_a x_b) x_c with absent factors = 1
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int k = lane + 32 * r;
+        if (k < NFEAT) {
+            const int pk = fidx[k];
+            double p = X[pk & 7];
+            p = __dmul_rn(p, X[(pk >> 3) & 7]);
+            p = __dmul_rn(p, X[(pk >> 6) & 7]);
+            PHI[1 + k] = p;
+        }
+    }
+    __syncwarp();
+    const double* T = c.sh + SH_T;
+    const double* t0 = T + lane * TS;
+    const double* t1 = T + (32 + lane) * TS;
+    const double* t2 = T + (64 + lane) * TS;
+    const double* t3 = T + (96 + lane) * TS;
+    const double* op3 = PHI + (lane < 12 ? 28 : 56);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int q = 0; q < NJ; q += 2) {
+        const double2 ps = *reinterpret_cast<const double2*>(PHI + q);
+        const double2 p3 = *reinterpret_cast<const double2*>(op3 + q);
+        const double2 c0 = *reinterpret_cast<const double2*>(t0 + q);
+        const double2 c1 = *reinterpret_cast<const double2*>(t1 + q);
+        const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
+        const double2 c3 = *reinterpret_cast<const double2*>(t3 + q);
+        a0 = fma(c0.x, ps.x, a0); a0 = fma(c0.y, ps.y, a0);
+        a1 = fma(c1.x, ps.x, a1); a1 = fma(c1.y, ps.y, a1);
+        a2 = fma(c2.x, ps.x, a2); a2 = fma(c2.y, ps.y, a2);
+        a3 = fma(c3.x, p3.x, a3); a3 = fma(c3.y, p3.y, a3);
+    }
+    // scatter the Jacobians into their tiles
+    AC[sc.o0] = a0;
+    if (lane < 4) AC[sc.o1] = a1; else HT[sc.o1] = a1;
+    if (lane < 8) HT[sc.o2] = a2;
+    // combine the three parts of the 12 value outputs in lanes 8..19
+    const int v = lane - 8;
+    const double p1 = __shfl_sync(FULL, a3, v & 31);
+    const double p2 = __shfl_sync(FULL, a3, (12 + v) & 31);
+    return __dadd_rn(__dadd_rn(a2, p1), p2);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two 6x6 inverses at once (half-warp h handles matrix h): Gauss-Jordan on [M | I] with partial pivoting, one
+// column per lane (j = lane & 15 < 12), rows in registers, implicit row exchange.  The inverse lands in `dst`
+// (tile, LD) for each half.  Zero pivots produce inf/nan exactly like the singular case would.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gj6_pair(double (&col)[6], int lane, double* __restrict__ dst) {
+    const int j = lane & 15;
+    unsigned used = 0, cmap = 0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const int src = (lane & 16) | c;
+        double cc[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) cc[r] = __shfl_sync(FULL, col[r], src);
+        double best = -1.0;
+        int p = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const double av = fabs(cc[r]);
+            const bool take = !((used >> r) & 1u) && (av > best);
+            best = take ? av : best;
+            p = take ? r : p;
+        }
+        used |= 1u << p;
+        cmap |= (unsigned)c << (4 * p);
+        double piv = cc[0], pv = col[0];
+#pragma unroll
+        for (int r = 1; r < 6; ++r) { piv = (p == r) ? cc[r] : piv; pv = (p == r) ? col[r] : pv; }
+        const double pc = __ddiv_rn(pv, piv);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) col[r] = (p == r) ? pc : fma(-cc[r], pc, col[r]);
+    }
+    if (j >= 6 && j < 12) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) dst[((cmap >> (4 * r)) & 7u) * LD + (j - 6)] = col[r];
+    }
+}
+
+// inv(Q_uu~) (M x M, no pivoting) + PD test from the pivots.  Reads the matrix from `tile`, writes the inverse back.
+template <int M>
+__device__ __forceinline__ bool gj_spd(double* __restrict__ tile, int lane) {
+    double col[M];
+    const int j = lane;
+#pragma unroll
+    for (int r = 0; r < M; ++r) col[r] = (j < M) ? tile[r * LD + j] : ((j - M == r) ? 1.0 : 0.0);
+    bool pd = true;
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+        double cc[M];
+#pragma unroll
+        for (int r = 0; r < M; ++r) cc[r] = __shfl_sync(FULL, col[r], c);
+        const double piv = cc[c];
+        pd = pd && (piv > 0.0) && !isinf(piv);
+        const double pc = __ddiv_rn(col[c], piv);
+#pragma unroll
+        for (int r = 0; r < M; ++r) col[r] = (r == c) ? pc : fma(-cc[r], pc, col[r]);
+    }
+    __syncwarp();
+    if (j >= M && j < 2 * M) {
+#pragma unroll
+        for (int r = 0; r < M; ++r) tile[r * LD + (j - M)] = col[r];
+    }
+    __syncwarp();
+    return pd;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward pass (ilqr.py:117-162)
+// ---------------------------------------------------------------------------------------------------------------
+template <int M>
+__device__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int discr, const double* __restrict__ nx,
+                           const double* __restrict__ nu, double alpha, const double* __restrict__ K,
+                           const double* __restrict__ k, const Rec& tr, const double* __restrict__ ztar,
+                           const double* __restrict__ ulast) {
+    const int lane = c.lane, g = c.g, q = c.q, N = a.N;
+    double* ws = c.ws;
+    double* X = ws + W_X;   double* U = ws + W_U;   double* UP = ws + W_UP;  double* DC = ws + W_DC;
+    double* DD = ws + W_DD; double* E = ws + W_E;   double* FV = ws + W_FV;  double* QE = ws + W_QE;
+    double* RDU = ws + W_RDU;
+    double* AC = ws + W_TILES + 0 * TILE;   // A_c
+    double* AD = ws + W_TILES + 1 * TILE;   // A_d
+    double* IA = ws + W_TILES + 2 * TILE;   // inv(A_c)
+    double* SP = ws + W_TILES + 3 * TILE;   // sep = inv(A_c) (A_d - I)
+    double* BD = ws + W_TILES + 4 * TILE;   // B_d
+    double* HT = ws + W_TILES + 5 * TILE;   // H_t
+    double* W0 = ws + W_TILES + 6 * TILE;   // inv(I - h A_c) for bil
+    const double* Qt = c.sh + SH_Q;  const double* Rt = c.sh + SH_R;  const double* Qft = c.sh + SH_QF;
+    const double* Brt = c.sh + SH_BR; const double* zref = c.sh + SH_ZREF;
+    const Scatter sc = make_scatter(lane);
+    const double dt = a.dt;
+    const bool inc = a.cfg.include_input_var_constraint != 0;
+    double cost = 0.0;
+
+    for (int t = 0; t < 7; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
+    if (lane < 8) X[lane] = lane < 6 ? nx[lane] : (lane == 7 ? 1.0 : 0.0);
+    if (lane < 6) tr.x[lane] = nx[lane];
+    if (lane < 8) UP[lane] = (lane < M && ulast) ? ulast[lane] : 0.0;
+    if (lane == 0) ws[W_PHI] = 1.0;
+    if (lane < 8) { U[lane] = 0.0; DC[lane] = 0.0; }
+    __syncwarp();
+
+    for (int t = 0; t <= N; ++t) {
+        const bool last = (t == N);
+        if (!last) {
+            // u_t = (u_prev[t] + alpha k[t]) + K[t] (x[t] - x_prev[t])          (ilqr.py:140)
+            if (lane < M) {
+                double v = nu[t * M + lane];
+                if (k) v = __dadd_rn(v, __dmul_rn(alpha, k[t * M + lane]));
+                if (K) {
+                    const double* row = K + ((long long)t * M + lane) * 6;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < 6; ++jj) acc = fma(row[jj], __dsub_rn(X[jj], nx[t * 6 + jj]), acc);
+                    v = __dadd_rn(v, acc);
+                }
+                U[lane] = v;
+                tr.u[t * M + lane] = v;
+            }
+        }
+        // model at x_t: A_c, H_t, f, z
+        const double val = ssm_eval_fast(c, sc, AC, HT);
+        if (lane >= 14 && lane < 20) {
+            const int i = lane - 14;
+            const double e = __dsub_rn(__dadd_rn(val, zref[i]), ztar[t * 6 + i]);
+            E[i] = e;
+            tr.e[t * 6 + i] = e;
+        }
+        __syncwarp();   // U, E, AC, HT visible
+        // H_t to the record
+        for (int e2 = lane; e2 < 36; e2 += 32) tr.H[(long long)t * 36 + e2] = HT[(e2 / 6) * LD + e2 % 6];
+        if (last) {
+            // terminal cost .5 e^T Qf e (ilqr.py:164-166)
+            if (lane < 6) {
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) acc = fma(E[i], Qft[i * LD + lane], acc);
+                QE[lane] = acc;
+            }
+            __syncwarp();
+            double s1 = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < 6; ++jj) s1 = fma(QE[jj], E[jj], s1);
+            cost = __dadd_rn(cost, __dmul_rn(0.5, s1));
+            break;
+        }
+        // f = r phi + B u,  d_c = (f - A_c x) - B u                            (ssm.py:168, 203)
+        if (lane >= 8 && lane < 14) {
+            const int i = lane - 8;
+            double bu = 0.0, ax = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < M; ++jj) bu = fma(Brt[i * LD + jj], U[jj], bu);
+#pragma unroll
+            for (int kk = 0; kk < 6; ++kk) ax = fma(AC[i * LD + kk], X[kk], ax);
+            const double f = __dadd_rn(val, bu);
+            FV[i] = f;
+            DC[i] = __dsub_rn(__dsub_rn(f, ax), bu);
+        }
+        // step-cost pieces: QE = e^T Q, RDU = du^T R                            (ilqr.py:168-175)
+        if (lane >= 14 && lane < 20) {
+            const int jj = lane - 14;
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) acc = fma(E[i], Qt[i * LD + jj], acc);
+            QE[jj] = acc;
+        }
+        if (lane >= 20 && lane < 20 + M) {
+            const int jj = lane - 20;
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const double du = inc ? __dsub_rn(U[i], UP[i]) : U[i];
+                acc = fma(du, Rt[i * LD + jj], acc);
+            }
+            RDU[jj] = acc;
+        }
+        __syncwarp();   // DC, QE, RDU visible
+        // discretisation (ssm.py:279-301)
+        if (discr == SRCB200_DISCR_BE || discr == SRCB200_DISCR_BIL) {
+            const double h = (discr == SRCB200_DISCR_BE) ? dt : 0.5 * dt;
+            const int hm = lane >> 4, j = lane & 15;
+            double col[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                double v = 0.0;
+                if (j < 6) {
+                    const double av = AC[r * LD + j];
+                    v = hm ? av : __dsub_rn(r == j ? 1.0 : 0.0, __dmul_rn(h, av));
+                } else if (j < 12) {
+                    v = (r == j - 6) ? 1.0 : 0.0;
+                }
+                col[r] = v;
+            }
+            gj6_pair(col, lane, hm ? IA : (discr == SRCB200_DISCR_BE ? AD : W0));
+            __syncwarp();
+            if (discr == SRCB200_DISCR_BIL) {
+                // A_d = (I + h A_c) inv(I - h A_c)
+                Frag f{0.0, 0.0};
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int kk = 4 * s + q;
+                    const double av = (g < 6 && kk < 6) ? __dadd_rn(g == kk ? 1.0 : 0.0, __dmul_rn(h, AC[g * LD + kk])) : 0.0;
+                    dmma(f, av, W0[kk * LD + g]);
+                }
+                store_frag(AD, f, g, q);
+                __syncwarp();
+            }
+            // sep = inv(A_c) (A_d - I)
+            Frag s{0.0, 0.0};
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int kk = 4 * s2 + q;
+                const double bv = (kk < 6 && g < 6) ? __dsub_rn(AD[kk * LD + g], kk == g ? 1.0 : 0.0) : 0.0;
+                dmma(s, IA[g * LD + kk], bv);
+            }
+            store_frag(SP, s, g, q);
+            __syncwarp();
+            // B_d = sep B_r ; d_d = sep d_c
+            Frag b{0.0, 0.0};
+            mma88<false, false>(b, SP, Brt, g, q);
+            store_frag(BD, b, g, q);
+            if (lane < 6) {
+                double acc = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 6; ++kk) acc = fma(SP[lane * LD + kk], DC[kk], acc);
+                DD[lane] = acc;
+            }
+        } else if (discr == SRCB200_DISCR_FE) {
+            for (int e2 = lane; e2 < 36; e2 += 32) {
+                const int i = e2 / 6, jj = e2 % 6;
+                const double v = __dmul_rn(dt, AC[i * LD + jj]);
+                AD[i * LD + jj] = (i == jj) ? __dadd_rn(1.0, v) : v;
+            }
+            for (int e2 = lane; e2 < 6 * M; e2 += 32) BD[(e2 / M) * LD + e2 % M] = __dmul_rn(dt, Brt[(e2 / M) * LD + e2 % M]);
+            if (lane < 6) DD[lane] = __dmul_rn(dt, DC[lane]);
+        } else {   // already discrete
+            for (int e2 = lane; e2 < 36; e2 += 32) AD[(e2 / 6) * LD + e2 % 6] = AC[(e2 / 6) * LD + e2 % 6];
+            for (int e2 = lane; e2 < 6 * M; e2 += 32) BD[(e2 / M) * LD + e2 % M] = Brt[(e2 / M) * LD + e2 % M];
+            if (lane < 6) DD[lane] = DC[lane];
+        }
+        __syncwarp();
+        // cost accumulation (identical in every lane)
+        {
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < 6; ++jj) s1 = fma(QE[jj], E[jj], s1);
+#pragma unroll
+            for (int jj = 0; jj < M; ++jj) s2 = fma(RDU[jj], inc ? __dsub_rn(U[jj], UP[jj]) : U[jj], s2);
+            cost = __dadd_rn(cost, __dadd_rn(__dmul_rn(0.5, s1), __dmul_rn(0.5, s2)));
+        }
+        // x_{t+1} = (A_d x + B_d u) + d_d                                        (ssm.py:330-333)
+        double xn = 0.0;
+        if (lane < 6) {
+            double ax = 0.0, bu = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 6; ++kk) ax = fma(AD[lane * LD + kk], X[kk], ax);
+#pragma unroll
+            for (int jj = 0; jj < M; ++jj) bu = fma(BD[lane * LD + jj], U[jj], bu);
+            xn = __dadd_rn(__dadd_rn(ax, bu), DD[lane]);
+        }
+        // record the linearisation
+        for (int e2 = lane; e2 < 36; e2 += 32) tr.A[(long long)t * 36 + e2] = AD[(e2 / 6) * LD + e2 % 6];
+        for (int e2 = lane; e2 < 6 * M; e2 += 32) tr.B[(long long)t * 6 * M + e2] = BD[(e2 / M) * LD + e2 % M];
+        __syncwarp();
+        if (lane < 6) { X[lane] = xn; tr.x[(long long)(t + 1) * 6 + lane] = xn; }
+        if (lane < M) UP[lane] = U[lane];
+        __syncwarp();
+    }
+    return cost;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward pass (ilqr.py:219-300)
+// ---------------------------------------------------------------------------------------------------------------
+template <int M>
+__device__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec& rc, const double* __restrict__ ulast,
+                        double* __restrict__ Kout, double* __restrict__ kout, double* __restrict__ ab, double& rho,
+                        double& drho, bool& give_up) {
+    const int lane = c.lane, g = c.g, q = c.q, N = a.N;
+    double* ws = c.ws;
+    double* P = ws + W_TILES + 0 * TILE;     // (P | p)
+    double* A = ws + W_TILES + 1 * TILE;     // A_t with A[6][6] = 1
+    double* B = ws + W_TILES + 2 * TILE;     // B_t
+    double* H = ws + W_TILES + 3 * TILE;     // (H | e), then B^T P, B^T(P+rho I), K^T Q_uu
+    double* W = ws + W_TILES + 4 * TILE;     // H^T Q, then A^T P, then (Q_ux~ | Q_u)
+    double* QUU = ws + W_TILES + 5 * TILE;
+    double* QUX = ws + W_TILES + 6 * TILE;   // (Q_ux | Q_u)
+    double* INV = ws + W_TILES + 7 * TILE;
+    double* KT = ws + W_TILES + 8 * TILE;    // (K | k)
+    double* CU = ws + W_DC;
+    const double* Qt = c.sh + SH_Q;  const double* Rt = c.sh + SH_R;  const double* Qft = c.sh + SH_QF;
+    const srcb200_ilqr_config& cf = a.cfg;
+    const bool sreg = cf.regularize && cf.state_regularization;
+    int restarts = 0;
+    give_up = false;
+
+    while (true) {
+        for (int t = 0; t < NTILES; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
+        __syncwarp();
+        // terminal: (P | p) = (H^T Qf) (H | e)                                   (ilqr.py:177-182)
+        for (int e2 = lane; e2 < 36; e2 += 32) H[(e2 / 6) * LD + e2 % 6] = rc.H[(long long)N * 36 + e2];
+        if (lane < 6) H[lane * LD + 6] = rc.e[N * 6 + lane];
+        __syncwarp();
+        {
+            Frag f{0.0, 0.0};
+            mma88<true, false>(f, H, Qft, g, q);
+            store_frag(W, f, g, q);
+            __syncwarp();
+            Frag p{0.0, 0.0};
+            mma88<false, false>(p, W, H, g, q);
+            if (g >= 6) { p.c0 = 0.0; p.c1 = 0.0; }
+            if (q == 3) p.c1 = 0.0;
+            store_frag(P, p, g, q);
+        }
+        if (lane == 0) A[6 * LD + 6] = 1.0;
+        __syncwarp();
+
+        bool ok = true;
+        for (int t = N - 1; t >= 0; --t) {
+            // ---- stage A_t, B_t, (H_t | e_t), c_u
+            for (int e2 = lane; e2 < 36; e2 += 32) {
+                const int off = (e2 / 6) * LD + e2 % 6;
+                A[off] = rc.A[(long long)t * 36 + e2];
+                H[off] = rc.H[(long long)t * 36 + e2];
+            }
+            for (int e2 = lane; e2 < 6 * M; e2 += 32) B[(e2 / M) * LD + e2 % M] = rc.B[(long long)t * 6 * M + e2];
+            if (lane < 6) H[lane * LD + 6] = rc.e[t * 6 + lane];   // rows 6,7 / column 7 of this tile never reach rows<6, cols<7
+            if (lane >= 8 && lane < 8 + M) {
+                const int i = lane - 8;
+                double acc = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < M; ++jj) {
+                    const double ut = rc.u[t * M + jj];
+                    double du = ut;
+                    if (cf.include_input_var_constraint)
+                        du = __dsub_rn(ut, t == 0 ? (ulast ? ulast[jj] : 0.0) : rc.u[(t - 1) * M + jj]);
+                    acc = fma(Rt[i * LD + jj], du, acc);
+                }
+                CU[i] = acc;                                                     // c_u = R du
+            }
+            __syncwarp();
+            // ---- cost derivatives: W = (H|e)^T Q ; (c_xx | c_x) = W (H | e)      (ilqr.py:186-190)
+            Frag w{0.0, 0.0};
+            mma88<true, false>(w, H, Qt, g, q);
+            store_frag(W, w, g, q);
+            __syncwarp();
+            Frag qxx{0.0, 0.0};
+            mma88<false, false>(qxx, W, H, g, q);
+            __syncwarp();
+            // ---- A^T (P | p) -> W ;  B^T (P | p) -> H
+            Frag atp{0.0, 0.0}, btp{0.0, 0.0};
+            mma88<true, false>(atp, A, P, g, q);
+            mma88<true, false>(btp, B, P, g, q);
+            store_frag(W, atp, g, q);
+            store_frag(H, btp, g, q);
+            __syncwarp();
+            // ---- (Q_xx | Q_x) = (c_xx | c_x) + (A^T P | A^T p) A'                (ilqr.py:258,260)
+            mma88<false, false>(qxx, W, A, g, q);
+            // ---- Q_uu = R + (B^T P) B ; (Q_ux | Q_u) = (0 | c_u) + (B^T P | B^T p) A'   (ilqr.py:259,261,262)
+            Frag quu = load_frag(Rt, g, q);
+            mma88<false, false>(quu, H, B, g, q);
+            Frag qux{(q == 3) ? CU[g] : 0.0, 0.0};
+            if (g >= M) qux.c0 = 0.0;
+            mma88<false, false>(qux, H, A, g, q);
+            store_frag(QUU, quu, g, q);
+            store_frag(QUX, qux, g, q);
+            __syncwarp();
+            // ---- regularised terms                                               (ilqr.py:264-274)
+            Frag quut, quxt;
+            if (sreg) {
+                Frag btpr{0.0, 0.0};
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int kk = 4 * s + q;
+                    double pv = P[kk * LD + g];
+                    if (kk == g && kk < 6) pv = __dadd_rn(pv, rho);
+                    dmma(btpr, B[kk * LD + g], pv);
+                }
+                store_frag(H, btpr, g, q);
+                __syncwarp();
+                quut = load_frag(Rt, g, q);
+                mma88<false, false>(quut, H, B, g, q);
+                quxt = Frag{0.0, 0.0};
+                mma88<false, false>(quxt, H, A, g, q);
+            } else {
+                quut = quu;
+                quxt = qux;
+                if (cf.regularize) {
+                    if (2 * q == g) quut.c0 = __dadd_rn(quut.c0, rho);
+                    if (2 * q + 1 == g) quut.c1 = __dadd_rn(quut.c1, rho);
+                }
+            }
+            if (g >= M) {   // keep the padding block of Q_uu~ an identity so the sweep below is well defined
+                quut.c0 = (2 * q == g) ? 1.0 : 0.0;
+                quut.c1 = (2 * q + 1 == g) ? 1.0 : 0.0;
+            }
+            store_frag(INV, quut, g, q);
+            // right-hand side (Q_ux~ | Q_u)
+            if (q == 3) { quxt.c0 = qux.c0; quxt.c1 = 0.0; }
+            store_frag(W, quxt, g, q);
+            __syncwarp();
+            // ---- PD test + explicit inverse                                       (ilqr.py:276-289)
+            const bool pd = gj_spd<M>(INV, lane);
+            if (!pd && cf.regularize) {
+                rho_update(cf, true, rho, drho);
+                ok = false;
+                break;
+            }
+            // ---- (K | k) = -inv (Q_ux~ | Q_u)                                     (ilqr.py:291-292)
+            Frag kf{0.0, 0.0};
+            mma88<false, false>(kf, INV, W, g, q);
+            kf.c0 = -kf.c0; kf.c1 = -kf.c1;
+            if (g >= M) { kf.c0 = 0.0; kf.c1 = 0.0; }
+            if (q == 3) kf.c1 = 0.0;
+            store_frag(KT, kf, g, q);
+            if (g < M) {
+                if (q < 3) {
+                    *reinterpret_cast<double2*>(Kout + ((long long)t * M + g) * 6 + 2 * q) = make_double2(kf.c0, kf.c1);
+                } else {
+                    kout[t * M + g] = kf.c0;
+                }
+            }
+            __syncwarp();
+            // ---- K^T Q_uu -> H                                                    (ilqr.py:294-295)
+            Frag kq{0.0, 0.0};
+            mma88<true, false>(kq, KT, QUU, g, q);
+            store_frag(H, kq, g, q);
+            __syncwarp();
+            // ---- (P | p) = (((Q_xx|Q_x) + KQ (K|k)) + K^T (Q_ux|Q_u)) + Q_ux^T (K|k)
+            mma88<false, false>(qxx, H, KT, g, q);
+            mma88<true, false>(qxx, KT, QUX, g, q);
+            mma88<true, false>(qxx, QUX, KT, g, q);
+            // line-search scalars: a_t = k . Q_u, b_t = (k^T Q_uu) . k              (ilqr.py:69-71)
+            double pa = 0.0, pb = 0.0;
+            if (lane < M) {
+                const double kv = KT[lane * LD + 6];
+                pa = __dmul_rn(kv, QUX[lane * LD + 6]);
+                pb = __dmul_rn(H[6 * LD + lane], kv);
+            }
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) {
+                pa = __dadd_rn(pa, __shfl_xor_sync(FULL, pa, off));
+                pb = __dadd_rn(pb, __shfl_xor_sync(FULL, pb, off));
+            }
+            if (lane == 0) { ab[2 * t] = pa; ab[2 * t + 1] = pb; }
+            __syncwarp();
+            if (g >= 6) { qxx.c0 = 0.0; qxx.c1 = 0.0; }
+            if (q == 3) qxx.c1 = 0.0;
+            store_frag(P, qxx, g, q);
+            __syncwarp();
+        }
+        if (ok) {
+            rho_update(cf, false, rho, drho);
+            break;
+        }
+        ++restarts;
+        if (restarts >= cf.max_pd_restarts) { give_up = true; break; }
+    }
+    return restarts;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Solve kernel (ilqr.py:27-107): one warp per problem
+// ---------------------------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+ilqr_ssm_fast_kernel(SsmDev Mdl, IlqrArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    build_tables(Mdl, a, sm, M);
+    Ctx c;
+    c.lane = threadIdx.x & 31;
+    c.g = c.lane >> 2;
+    c.q = c.lane & 3;
+    c.sh = sm;
+    const int warp = threadIdx.x >> 5;
+    c.ws = sm + SH_END + warp * W_SIZE;
+    const int lane = c.lane, N = a.N;
+    const srcb200_ilqr_config& cf = a.cfg;
+    const int discr = Mdl.discr;
+
+    for (long long b = (long long)blockIdx.x * WARPS + warp; b < a.batch; b += (long long)gridDim.x * WARPS) {
+        double* wsb = a.ws + b * a.L.total;
+        Rec rec[2] = {rec_at(wsb, a.L), rec_at(wsb + a.L.rec, a.L)};
+        double* kbuf = wsb + a.L.k;
+        double* ab = wsb + a.L.ab;
+        double* Kbuf = a.oK + b * (long long)N * M * 6;
+        const double* ztar = a.z_target + (a.shared_target ? 0 : b * (long long)(N + 1) * 6);
+        const double* ulast = a.u_last ? a.u_last + b * M : nullptr;
+        double* trace = a.otrace ? a.otrace + b * (long long)(cf.max_iter + 1) * 4 : nullptr;
+
+        double rho = cf.rho0, drho = cf.drho0;
+        int fails = 0, cur = 0, status = 0, trials = 0;
+        {
+            Rec& nom = rec[1];
+            if (lane < 6) nom.x[lane] = a.x0[b * 6 + lane];
+            for (int e = lane; e < N * M; e += 32) nom.u[e] = a.u_init ? a.u_init[b * (long long)N * M + e] : 0.0;
+            __syncwarp();
+        }
+        double cost = fwd_fast<M>(c, a, discr, rec[1].x, rec[1].u, 1.0, nullptr, nullptr, rec[0], ztar, ulast);
+        if (a.ocost0 && lane == 0) a.ocost0[b] = cost;
+
+        bool conv = false;
+        int it = 0;
+        while (!conv && it <= cf.max_iter) {
+            bool give_up = false;
+            const int restarts = bwd_fast<M>(c, a, rec[cur], ulast, Kbuf, kbuf, ab, rho, drho, give_up);
+            const double rho_bwd = rho;
+            if (give_up) { status |= SRCB200_ILQR_ST_PD_GIVEUP; break; }
+            __syncwarp();
+            const double prev_cost = cost;
+            double alpha = cf.alpha0;
+            bool improved = false, failed = false;
+            double cost_t = cost, alpha_acc = 0.0;
+            while (!improved && !failed) {
+                improved = true;
+                cost_t = fwd_fast<M>(c, a, discr, rec[cur].x, rec[cur].u, alpha, Kbuf, kbuf, rec[cur ^ 1], ztar, ulast);
+                ++trials;
+                double dc = 0.0;
+                const double a2 = __dmul_rn(__dmul_rn(alpha, alpha), 0.5);
+                for (int t = 0; t < N; ++t)
+                    dc = __dadd_rn(dc, __dadd_rn(__dmul_rn(alpha, ab[2 * t]), __dmul_rn(a2, ab[2 * t + 1])));
+                alpha_acc = alpha;
+                if (cf.do_linesearch) {
+                    const double ratio = __ddiv_rn(__dsub_rn(cost_t, prev_cost), dc);
+                    if (ratio <= cf.improv_lb || ratio > cf.improv_ub) {
+                        alpha = __dmul_rn(cf.alpha_scaling, alpha);
+                        improved = false;
+                        if (alpha < cf.alpha_min) {
+                            rho_update(cf, true, rho, drho);
+                            rho = __dadd_rn(rho, cf.rho_increase_fp);
+                            failed = true;
+                        }
+                    }
+                }
+            }
+            if (!failed) {
+                cur ^= 1;
+                cost = cost_t;
+                const double dJ = __dsub_rn(prev_cost, cost);
+                conv = (dJ < cf.epsilon) && (dJ >= 0.0);
+                if (conv) status |= SRCB200_ILQR_ST_CONVERGED;
+                fails = 0;
+            } else {
+                ++fails;
+                if (fails >= cf.counter_limit) { conv = true; status |= SRCB200_ILQR_ST_ABANDONED; }
+            }
+            if (trace && lane == 0) {
+                trace[it * 4 + 0] = cost;
+                trace[it * 4 + 1] = failed ? 0.0 : alpha_acc;
+                trace[it * 4 + 2] = rho_bwd;
+                trace[it * 4 + 3] = (double)restarts;
+            }
+            ++it;
+            if (!isfinite(cost)) { status |= SRCB200_ILQR_ST_NONFINITE; break; }
+        }
+        if (!conv && it > cf.max_iter) status |= SRCB200_ILQR_ST_MAXITER;
+
+        __syncwarp();
+        const Rec& fin = rec[cur];
+        for (int e = lane; e < (N + 1) * 6; e += 32) a.ox[b * (long long)(N + 1) * 6 + e] = fin.x[e];
+        for (int e = lane; e < N * M; e += 32) a.ou[b * (long long)N * M + e] = fin.u[e];
+        if (lane == 0) {
+            a.ocost[b] = cost;
+            if (a.orho) a.orho[b] = rho;
+            a.oiter[b] = it;
+            a.ostatus[b] = status;
+            if (a.otrials) a.otrials[b] = trials;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace fast
+
+// Dispatch: Gauss-Newton SSM problems with the Trunk/Diamond shape go to the specialised kernel.
+int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bool* handled) {
+    *handled = false;
+    const char* env = getenv("SRCB200_ILQR_GENERIC");
+    if (env && env[0] == '1') return 0;
+    if (!(M.n == 6 && M.nz == 6 && M.order == 3 && M.nfeat == fast::NFEAT && (M.m == 4 || M.m == 8) && a.gn && !a.index_lin))
+        return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ctas = (a.batch + fast::WARPS - 1) / fast::WARPS;
+    const int grid = (int)(ctas < 2LL * sms ? ctas : 2LL * sms);   // persistent: 2 CTAs (16 warps) per SM
+    if (M.m == 8) {
+        SRCB_CUDA(cudaFuncSetAttribute(fast::ilqr_ssm_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
+        fast::ilqr_ssm_fast_kernel<8><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, a);
+    } else {
+        SRCB_CUDA(cudaFuncSetAttribute(fast::ilqr_ssm_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
+        fast::ilqr_ssm_fast_kernel<4><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, a);
+    }
+    SRCB_LAUNCH_CHECK("ilqr_ssm_fast_kernel");
+    *handled = true;
+    return 0;
+}
+
+}  // namespace srcb

@@ -763,9 +763,10 @@ static int solve_impl(const typename MP::Dev& M, const srcb200_ilqr_config* cfg,
     if (int e = fill_args<MP>(M, cfg, pr, a, smem)) return e;
     if (!res || !res->x || !res->u || !res->K || !res->cost || !res->iterations || !res->status)
         return fail(SRCB200_E_NULL, "ilqr: result x/u/K/cost/iterations/status must be provided");
-    if (!ws || ws_bytes < sizeof(double) * (size_t)a.L.total * (size_t)a.batch)
+    if (!ws || ws_bytes < sizeof(double) * (size_t)a.L.total * (size_t)a.batch + 256)
         return fail(SRCB200_E_WORKSPACE, "ilqr: workspace too small (%zu < %zu)", ws_bytes,
-                    sizeof(double) * (size_t)a.L.total * (size_t)a.batch);
+                    sizeof(double) * (size_t)a.L.total * (size_t)a.batch + 256);
+    a.work_counter = reinterpret_cast<int*>((double*)ws + (size_t)a.L.total * (size_t)a.batch);
     a.ox = res->x; a.ou = res->u; a.oK = res->K; a.ocost = res->cost; a.ocost0 = res->cost0; a.orho = res->rho;
     a.otrace = res->trace; a.oiter = res->iterations; a.ostatus = res->status; a.otrials = res->trials;
     a.ws = (double*)ws;
@@ -849,7 +850,7 @@ extern "C" size_t srcb200_ilqr_workspace_bytes(int32_t model_kind, const void* m
         n = M.n; m = M.m; nz = M.nz; il = TpwlPolicy::index_lin(M, pr->dt);
     }
     const Layout L = make_layout(n, m, nz, pr->N, pr->gauss_newton != 0, il);
-    return sizeof(double) * (size_t)L.total * (size_t)pr->batch;
+    return sizeof(double) * (size_t)L.total * (size_t)pr->batch + 256;   // + the work counter of the fast kernel
 }
 
 extern "C" int srcb200_ilqr_solve_batch(int32_t model_kind, const void* model, const srcb200_ilqr_config* cfg,

@@ -53,6 +53,7 @@ struct IlqrArgs {
     double* ws;
     Layout L;
     int model_scratch;          // doubles of model scratch in shared memory
+    int* work_counter;          // device int (zeroed before launch) handing problems to warps in the fast kernel
 };
 
 // rho schedule (ilqr.py:198-217), including the `dhro` typo: drho is never lowered.

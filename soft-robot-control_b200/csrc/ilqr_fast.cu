@@ -23,7 +23,6 @@
 namespace srcb {
 namespace fast {
 
-constexpr int N6 = 6;
 constexpr int LD = 12;            // tile row stride (doubles): A-/B-fragment loads are bank-conflict free
 constexpr int TILE = 8 * LD;
 constexpr int WARPS = 8;          // problems in flight per CTA
@@ -50,7 +49,7 @@ constexpr int W_UP = 104;                       // u_{t-1}, then du
 constexpr int W_DC = 112;
 constexpr int W_DD = 120;
 constexpr int W_E = 128;
-constexpr int W_FV = 136;                       // f (6)
+constexpr int W_DX = 136;                       // x_t - x_prev_t (6)
 constexpr int W_QE = 144;
 constexpr int W_RDU = 152;
 constexpr int W_TILES = 160;
@@ -87,8 +86,9 @@ __device__ __forceinline__ void zero_tile(double* __restrict__ T, int lane) {
 
 struct Ctx {
     int lane, g, q;
-    double* sh;     // CTA-shared block
-    double* ws;     // this warp's block
+    int off0, off1;  // tile offsets of elements `lane` and `32 + lane` (lane < 4) of a row-major 6 x 6 matrix
+    double* sh;      // CTA-shared block
+    double* ws;      // this warp's block
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -163,14 +163,13 @@ struct Scatter { int o0, o1, o2; };   // per-lane tile offsets of the Jacobian o
 __device__ __forceinline__ Scatter make_scatter(int lane) {
     Scatter s;
     s.o0 = (lane / 6) * LD + lane % 6;                                   // A_c, o = lane
-    if (lane < 4) s.o1 = ((32 + lane) / 6) * LD + (32 + lane) % 6;       // A_c, o = 32 + lane
-    else          s.o1 = ((lane - 4) / 6) * LD + (lane - 4) % 6;         // H,   o' = lane - 4
-    s.o2 = ((28 + lane) / 6) * LD + (28 + lane) % 6;                     // H,   o' = 28 + lane (lanes < 8)
+    s.o1 = ((32 + lane) / 6) * LD + (32 + lane) % 6;                     // A_c, o = 32 + lane (lanes < 4)
+    s.o2 = 0;
     return s;
 }
 
 __device__ __forceinline__ double ssm_eval_fast(const Ctx& c, const Scatter& sc, double* __restrict__ AC,
-                                                double* __restrict__ HT) {
+                                                double* __restrict__ Hg) {
     const int lane = c.lane;
     double* PHI = c.ws + W_PHI;
     const double* X = c.ws + W_X;
@@ -194,7 +193,7 @@ __device__ __forceinline__ double ssm_eval_fast(const Ctx& c, const Scatter& sc,
     const double* t2 = T + (64 + lane) * TS;
     const double* t3 = T + (96 + lane) * TS;
     const double* op3 = PHI + (lane < 12 ? 28 : 56);
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;   // even / odd terms
 #pragma unroll
     for (int q = 0; q < NJ; q += 2) {
         const double2 ps = *reinterpret_cast<const double2*>(PHI + q);
@@ -203,15 +202,16 @@ __device__ __forceinline__ double ssm_eval_fast(const Ctx& c, const Scatter& sc,
         const double2 c1 = *reinterpret_cast<const double2*>(t1 + q);
         const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
         const double2 c3 = *reinterpret_cast<const double2*>(t3 + q);
-        a0 = fma(c0.x, ps.x, a0); a0 = fma(c0.y, ps.y, a0);
-        a1 = fma(c1.x, ps.x, a1); a1 = fma(c1.y, ps.y, a1);
-        a2 = fma(c2.x, ps.x, a2); a2 = fma(c2.y, ps.y, a2);
-        a3 = fma(c3.x, p3.x, a3); a3 = fma(c3.y, p3.y, a3);
+        a0 = fma(c0.x, ps.x, a0); b0 = fma(c0.y, ps.y, b0);
+        a1 = fma(c1.x, ps.x, a1); b1 = fma(c1.y, ps.y, b1);
+        a2 = fma(c2.x, ps.x, a2); b2 = fma(c2.y, ps.y, b2);
+        a3 = fma(c3.x, p3.x, a3); b3 = fma(c3.y, p3.y, b3);
     }
-    // scatter the Jacobians into their tiles
+    a0 = __dadd_rn(a0, b0); a1 = __dadd_rn(a1, b1); a2 = __dadd_rn(a2, b2); a3 = __dadd_rn(a3, b3);
+    // A_c into its tile, H_t straight to the trajectory record
     AC[sc.o0] = a0;
-    if (lane < 4) AC[sc.o1] = a1; else HT[sc.o1] = a1;
-    if (lane < 8) HT[sc.o2] = a2;
+    if (lane < 4) AC[sc.o1] = a1; else Hg[lane - 4] = a1;
+    if (lane < 8) Hg[28 + lane] = a2;
     // combine the three parts of the 12 value outputs in lanes 8..19
     const int v = lane - 8;
     const double p1 = __shfl_sync(FULL, a3, v & 31);
@@ -247,7 +247,7 @@ __device__ __forceinline__ void gj6_pair(double (&col)[6], int lane, double* __r
         double piv = cc[0], pv = col[0];
 #pragma unroll
         for (int r = 1; r < 6; ++r) { piv = (p == r) ? cc[r] : piv; pv = (p == r) ? col[r] : pv; }
-        const double pc = __ddiv_rn(pv, piv);
+        const double pc = __dmul_rn(pv, __drcp_rn(piv));
 #pragma unroll
         for (int r = 0; r < 6; ++r) col[r] = (p == r) ? pc : fma(-cc[r], pc, col[r]);
     }
@@ -272,7 +272,7 @@ __device__ __forceinline__ bool gj_spd(double* __restrict__ tile, int lane) {
         for (int r = 0; r < M; ++r) cc[r] = __shfl_sync(FULL, col[r], c);
         const double piv = cc[c];
         pd = pd && (piv > 0.0) && !isinf(piv);
-        const double pc = __ddiv_rn(col[c], piv);
+        const double pc = __dmul_rn(col[c], __drcp_rn(piv));
 #pragma unroll
         for (int r = 0; r < M; ++r) col[r] = (r == c) ? pc : fma(-cc[r], pc, col[r]);
     }
@@ -286,69 +286,91 @@ __device__ __forceinline__ bool gj_spd(double* __restrict__ tile, int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Forward pass (ilqr.py:117-162)
+// Forward pass (ilqr.py:117-162).  Global inputs of step t+1 (nominal u, k, K row, nominal x, target) are fetched
+// into registers while step t computes.
 // ---------------------------------------------------------------------------------------------------------------
 template <int M>
-__device__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int discr, const double* __restrict__ nx,
-                           const double* __restrict__ nu, double alpha, const double* __restrict__ K,
-                           const double* __restrict__ k, const Rec& tr, const double* __restrict__ ztar,
-                           const double* __restrict__ ulast) {
+__device__ __noinline__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int discr, const double* __restrict__ nx,
+                                        const double* __restrict__ nu, double alpha, const double* __restrict__ K,
+                                        const double* __restrict__ k, const Rec& tr, const double* __restrict__ ztar,
+                                        const double* __restrict__ ulast) {
     const int lane = c.lane, g = c.g, q = c.q, N = a.N;
     double* ws = c.ws;
     double* X = ws + W_X;   double* U = ws + W_U;   double* UP = ws + W_UP;  double* DC = ws + W_DC;
-    double* DD = ws + W_DD; double* E = ws + W_E;   double* FV = ws + W_FV;  double* QE = ws + W_QE;
+    double* DD = ws + W_DD; double* E = ws + W_E;   double* DX = ws + W_DX;  double* QE = ws + W_QE;
     double* RDU = ws + W_RDU;
     double* AC = ws + W_TILES + 0 * TILE;   // A_c
     double* AD = ws + W_TILES + 1 * TILE;   // A_d
     double* IA = ws + W_TILES + 2 * TILE;   // inv(A_c)
     double* SP = ws + W_TILES + 3 * TILE;   // sep = inv(A_c) (A_d - I)
     double* BD = ws + W_TILES + 4 * TILE;   // B_d
-    double* HT = ws + W_TILES + 5 * TILE;   // H_t
-    double* W0 = ws + W_TILES + 6 * TILE;   // inv(I - h A_c) for bil
+    double* W0 = ws + W_TILES + 5 * TILE;   // inv(I - h A_c) for bil
     const double* Qt = c.sh + SH_Q;  const double* Rt = c.sh + SH_R;  const double* Qft = c.sh + SH_QF;
     const double* Brt = c.sh + SH_BR; const double* zref = c.sh + SH_ZREF;
     const Scatter sc = make_scatter(lane);
     const double dt = a.dt;
     const bool inc = a.cfg.include_input_var_constraint != 0;
+    const int bo0 = (lane / M) * LD + lane % M;                    // B element `lane`
+    const int bo1 = ((32 + lane) / M) * LD + (32 + lane) % M;      // B element `32 + lane` (valid while < 6 M)
     double cost = 0.0;
 
-    for (int t = 0; t < 7; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
+    for (int t = 0; t < 6; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
     if (lane < 8) X[lane] = lane < 6 ? nx[lane] : (lane == 7 ? 1.0 : 0.0);
     if (lane < 6) tr.x[lane] = nx[lane];
-    if (lane < 8) UP[lane] = (lane < M && ulast) ? ulast[lane] : 0.0;
+    if (lane < 8) { UP[lane] = (lane < M && ulast) ? ulast[lane] : 0.0; U[lane] = 0.0; DC[lane] = 0.0; DX[lane] = 0.0; }
     if (lane == 0) ws[W_PHI] = 1.0;
-    if (lane < 8) { U[lane] = 0.0; DC[lane] = 0.0; }
+    // prefetch registers for step 0
+    double p_nu = 0.0, p_k = 0.0, p_K[6] = {0, 0, 0, 0, 0, 0}, p_nx = 0.0, p_zt = 0.0;
+    if (lane < M) {
+        p_nu = nu[lane];
+        if (k) p_k = k[lane];
+        if (K) {
+#pragma unroll
+            for (int jj = 0; jj < 6; ++jj) p_K[jj] = K[lane * 6 + jj];
+        }
+    }
+    if (lane >= 14 && lane < 20) p_zt = ztar[lane - 14];
     __syncwarp();
 
     for (int t = 0; t <= N; ++t) {
         const bool last = (t == N);
-        if (!last) {
+        if (!last && lane < M) {
             // u_t = (u_prev[t] + alpha k[t]) + K[t] (x[t] - x_prev[t])          (ilqr.py:140)
-            if (lane < M) {
-                double v = nu[t * M + lane];
-                if (k) v = __dadd_rn(v, __dmul_rn(alpha, k[t * M + lane]));
-                if (K) {
-                    const double* row = K + ((long long)t * M + lane) * 6;
-                    double acc = 0.0;
+            double v = p_nu;
+            if (k) v = __dadd_rn(v, __dmul_rn(alpha, p_k));
+            if (K) {
+                double acc = 0.0;
 #pragma unroll
-                    for (int jj = 0; jj < 6; ++jj) acc = fma(row[jj], __dsub_rn(X[jj], nx[t * 6 + jj]), acc);
-                    v = __dadd_rn(v, acc);
-                }
-                U[lane] = v;
-                tr.u[t * M + lane] = v;
+                for (int jj = 0; jj < 6; ++jj) acc = fma(p_K[jj], DX[jj], acc);
+                v = __dadd_rn(v, acc);
             }
+            U[lane] = v;
+            tr.u[t * M + lane] = v;
         }
-        // model at x_t: A_c, H_t, f, z
-        const double val = ssm_eval_fast(c, sc, AC, HT);
+        const double zt_now = p_zt;
+        // issue the loads of step t+1
+        if (t + 1 <= N) {
+            if (t + 1 < N && lane < M) {
+                p_nu = nu[(t + 1) * M + lane];
+                if (k) p_k = k[(t + 1) * M + lane];
+                if (K) {
+                    const double* row = K + ((long long)(t + 1) * M + lane) * 6;
+#pragma unroll
+                    for (int jj = 0; jj < 6; ++jj) p_K[jj] = row[jj];
+                }
+            }
+            if (K && lane < 6) p_nx = nx[(t + 1) * 6 + lane];
+            if (lane >= 14 && lane < 20) p_zt = ztar[(t + 1) * 6 + lane - 14];
+        }
+        // model at x_t: A_c (tile), H_t (record), f, z
+        const double val = ssm_eval_fast(c, sc, AC, tr.H + (long long)t * 36);
         if (lane >= 14 && lane < 20) {
             const int i = lane - 14;
-            const double e = __dsub_rn(__dadd_rn(val, zref[i]), ztar[t * 6 + i]);
+            const double e = __dsub_rn(__dadd_rn(val, zref[i]), zt_now);
             E[i] = e;
             tr.e[t * 6 + i] = e;
         }
-        __syncwarp();   // U, E, AC, HT visible
-        // H_t to the record
-        for (int e2 = lane; e2 < 36; e2 += 32) tr.H[(long long)t * 36 + e2] = HT[(e2 / 6) * LD + e2 % 6];
+        __syncwarp();   // U, E, AC visible
         if (last) {
             // terminal cost .5 e^T Qf e (ilqr.py:164-166)
             if (lane < 6) {
@@ -372,9 +394,7 @@ __device__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int discr, const dou
             for (int jj = 0; jj < M; ++jj) bu = fma(Brt[i * LD + jj], U[jj], bu);
 #pragma unroll
             for (int kk = 0; kk < 6; ++kk) ax = fma(AC[i * LD + kk], X[kk], ax);
-            const double f = __dadd_rn(val, bu);
-            FV[i] = f;
-            DC[i] = __dsub_rn(__dsub_rn(f, ax), bu);
+            DC[i] = __dsub_rn(__dsub_rn(__dadd_rn(val, bu), ax), bu);
         }
         // step-cost pieces: QE = e^T Q, RDU = du^T R                            (ilqr.py:168-175)
         if (lane >= 14 && lane < 20) {
@@ -394,7 +414,6 @@ __device__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int discr, const dou
             }
             RDU[jj] = acc;
         }
-        __syncwarp();   // DC, QE, RDU visible
         // discretisation (ssm.py:279-301)
         if (discr == SRCB200_DISCR_BE || discr == SRCB200_DISCR_BIL) {
             const double h = (discr == SRCB200_DISCR_BE) ? dt : 0.5 * dt;
@@ -434,7 +453,7 @@ __device__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int discr, const dou
                 dmma(s, IA[g * LD + kk], bv);
             }
             store_frag(SP, s, g, q);
-            __syncwarp();
+            __syncwarp();   // also orders DC / QE / RDU
             // B_d = sep B_r ; d_d = sep d_c
             Frag b{0.0, 0.0};
             mma88<false, false>(b, SP, Brt, g, q);
@@ -445,18 +464,25 @@ __device__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int discr, const dou
                 for (int kk = 0; kk < 6; ++kk) acc = fma(SP[lane * LD + kk], DC[kk], acc);
                 DD[lane] = acc;
             }
-        } else if (discr == SRCB200_DISCR_FE) {
-            for (int e2 = lane; e2 < 36; e2 += 32) {
-                const int i = e2 / 6, jj = e2 % 6;
-                const double v = __dmul_rn(dt, AC[i * LD + jj]);
-                AD[i * LD + jj] = (i == jj) ? __dadd_rn(1.0, v) : v;
+        } else {
+            __syncwarp();   // DC visible
+            if (discr == SRCB200_DISCR_FE) {
+                const double v0 = __dmul_rn(dt, AC[c.off0]);
+                AD[c.off0] = (lane / 6 == lane % 6) ? __dadd_rn(1.0, v0) : v0;
+                if (lane < 4) {
+                    const double v1 = __dmul_rn(dt, AC[c.off1]);
+                    AD[c.off1] = (lane == 3) ? __dadd_rn(1.0, v1) : v1;   // element 35 is the (5,5) diagonal
+                }
+                if (lane < 6 * M) BD[bo0] = __dmul_rn(dt, Brt[bo0]);
+                if (32 + lane < 6 * M) BD[bo1] = __dmul_rn(dt, Brt[bo1]);
+                if (lane < 6) DD[lane] = __dmul_rn(dt, DC[lane]);
+            } else {   // already discrete
+                AD[c.off0] = AC[c.off0];
+                if (lane < 4) AD[c.off1] = AC[c.off1];
+                if (lane < 6 * M) BD[bo0] = Brt[bo0];
+                if (32 + lane < 6 * M) BD[bo1] = Brt[bo1];
+                if (lane < 6) DD[lane] = DC[lane];
             }
-            for (int e2 = lane; e2 < 6 * M; e2 += 32) BD[(e2 / M) * LD + e2 % M] = __dmul_rn(dt, Brt[(e2 / M) * LD + e2 % M]);
-            if (lane < 6) DD[lane] = __dmul_rn(dt, DC[lane]);
-        } else {   // already discrete
-            for (int e2 = lane; e2 < 36; e2 += 32) AD[(e2 / 6) * LD + e2 % 6] = AC[(e2 / 6) * LD + e2 % 6];
-            for (int e2 = lane; e2 < 6 * M; e2 += 32) BD[(e2 / M) * LD + e2 % M] = Brt[(e2 / M) * LD + e2 % M];
-            if (lane < 6) DD[lane] = DC[lane];
         }
         __syncwarp();
         // cost accumulation (identical in every lane)
@@ -479,10 +505,16 @@ __device__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int discr, const dou
             xn = __dadd_rn(__dadd_rn(ax, bu), DD[lane]);
         }
         // record the linearisation
-        for (int e2 = lane; e2 < 36; e2 += 32) tr.A[(long long)t * 36 + e2] = AD[(e2 / 6) * LD + e2 % 6];
-        for (int e2 = lane; e2 < 6 * M; e2 += 32) tr.B[(long long)t * 6 * M + e2] = BD[(e2 / M) * LD + e2 % M];
+        tr.A[(long long)t * 36 + lane] = AD[c.off0];
+        if (lane < 4) tr.A[(long long)t * 36 + 32 + lane] = AD[c.off1];
+        if (lane < 6 * M) tr.B[(long long)t * 6 * M + lane] = BD[bo0];
+        if (32 + lane < 6 * M) tr.B[(long long)t * 6 * M + 32 + lane] = BD[bo1];
         __syncwarp();
-        if (lane < 6) { X[lane] = xn; tr.x[(long long)(t + 1) * 6 + lane] = xn; }
+        if (lane < 6) {
+            X[lane] = xn;
+            DX[lane] = K ? __dsub_rn(xn, p_nx) : 0.0;
+            tr.x[(long long)(t + 1) * 6 + lane] = xn;
+        }
         if (lane < M) UP[lane] = U[lane];
         __syncwarp();
     }
@@ -490,12 +522,29 @@ __device__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int discr, const dou
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Backward pass (ilqr.py:219-300)
+// Backward pass (ilqr.py:219-300).  The record of step t-1 is fetched into registers while step t computes.
 // ---------------------------------------------------------------------------------------------------------------
 template <int M>
-__device__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec& rc, const double* __restrict__ ulast,
-                        double* __restrict__ Kout, double* __restrict__ kout, double* __restrict__ ab, double& rho,
-                        double& drho, bool& give_up) {
+struct StepRegs { double a0, a1, h0, h1, b0, b1, e, u, up; };
+
+template <int M>
+__device__ __forceinline__ void load_step(StepRegs<M>& r, const Rec& rc, int t, int lane, const double* __restrict__ ulast) {
+    r.a0 = rc.A[(long long)t * 36 + lane];
+    r.h0 = rc.H[(long long)t * 36 + lane];
+    if (lane < 4) { r.a1 = rc.A[(long long)t * 36 + 32 + lane]; r.h1 = rc.H[(long long)t * 36 + 32 + lane]; }
+    if (lane < 6 * M) r.b0 = rc.B[(long long)t * 6 * M + lane];
+    if (32 + lane < 6 * M) r.b1 = rc.B[(long long)t * 6 * M + 32 + lane];
+    if (lane < 6) r.e = rc.e[t * 6 + lane];
+    if (lane < M) {
+        r.u = rc.u[t * M + lane];
+        r.up = (t == 0) ? (ulast ? ulast[lane] : 0.0) : rc.u[(t - 1) * M + lane];
+    }
+}
+
+template <int M>
+__device__ __noinline__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec& rc, const double* __restrict__ ulast,
+                                     double* __restrict__ Kout, double* __restrict__ kout, double* __restrict__ ab,
+                                     double& rho, double& drho, bool& give_up) {
     const int lane = c.lane, g = c.g, q = c.q, N = a.N;
     double* ws = c.ws;
     double* P = ws + W_TILES + 0 * TILE;     // (P | p)
@@ -508,9 +557,13 @@ __device__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec& rc, const do
     double* INV = ws + W_TILES + 7 * TILE;
     double* KT = ws + W_TILES + 8 * TILE;    // (K | k)
     double* CU = ws + W_DC;
+    double* DU = ws + W_DD;
     const double* Qt = c.sh + SH_Q;  const double* Rt = c.sh + SH_R;  const double* Qft = c.sh + SH_QF;
     const srcb200_ilqr_config& cf = a.cfg;
     const bool sreg = cf.regularize && cf.state_regularization;
+    const bool inc = cf.include_input_var_constraint != 0;
+    const int bo0 = (lane / M) * LD + lane % M;
+    const int bo1 = ((32 + lane) / M) * LD + (32 + lane) % M;
     int restarts = 0;
     give_up = false;
 
@@ -518,8 +571,11 @@ __device__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec& rc, const do
         for (int t = 0; t < NTILES; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
         __syncwarp();
         // terminal: (P | p) = (H^T Qf) (H | e)                                   (ilqr.py:177-182)
-        for (int e2 = lane; e2 < 36; e2 += 32) H[(e2 / 6) * LD + e2 % 6] = rc.H[(long long)N * 36 + e2];
+        H[c.off0] = rc.H[(long long)N * 36 + lane];
+        if (lane < 4) H[c.off1] = rc.H[(long long)N * 36 + 32 + lane];
         if (lane < 6) H[lane * LD + 6] = rc.e[N * 6 + lane];
+        StepRegs<M> pre;
+        load_step<M>(pre, rc, N - 1, lane, ulast);
         __syncwarp();
         {
             Frag f{0.0, 0.0};
@@ -537,28 +593,23 @@ __device__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec& rc, const do
 
         bool ok = true;
         for (int t = N - 1; t >= 0; --t) {
-            // ---- stage A_t, B_t, (H_t | e_t), c_u
-            for (int e2 = lane; e2 < 36; e2 += 32) {
-                const int off = (e2 / 6) * LD + e2 % 6;
-                A[off] = rc.A[(long long)t * 36 + e2];
-                H[off] = rc.H[(long long)t * 36 + e2];
-            }
-            for (int e2 = lane; e2 < 6 * M; e2 += 32) B[(e2 / M) * LD + e2 % M] = rc.B[(long long)t * 6 * M + e2];
-            if (lane < 6) H[lane * LD + 6] = rc.e[t * 6 + lane];   // rows 6,7 / column 7 of this tile never reach rows<6, cols<7
+            // ---- stage A_t, B_t, (H_t | e_t), du from the prefetched registers; fetch step t-1
+            A[c.off0] = pre.a0;
+            H[c.off0] = pre.h0;
+            if (lane < 4) { A[c.off1] = pre.a1; H[c.off1] = pre.h1; }
+            if (lane < 6 * M) B[bo0] = pre.b0;
+            if (32 + lane < 6 * M) B[bo1] = pre.b1;
+            if (lane < 6) H[lane * LD + 6] = pre.e;   // rows 6,7 / column 7 of this tile never reach rows<6, cols<7
+            if (lane < M) DU[lane] = inc ? __dsub_rn(pre.u, pre.up) : pre.u;
+            if (t > 0) load_step<M>(pre, rc, t - 1, lane, ulast);
+            __syncwarp();
             if (lane >= 8 && lane < 8 + M) {
                 const int i = lane - 8;
                 double acc = 0.0;
 #pragma unroll
-                for (int jj = 0; jj < M; ++jj) {
-                    const double ut = rc.u[t * M + jj];
-                    double du = ut;
-                    if (cf.include_input_var_constraint)
-                        du = __dsub_rn(ut, t == 0 ? (ulast ? ulast[jj] : 0.0) : rc.u[(t - 1) * M + jj]);
-                    acc = fma(Rt[i * LD + jj], du, acc);
-                }
+                for (int jj = 0; jj < M; ++jj) acc = fma(Rt[i * LD + jj], DU[jj], acc);
                 CU[i] = acc;                                                     // c_u = R du
             }
-            __syncwarp();
             // ---- cost derivatives: W = (H|e)^T Q ; (c_xx | c_x) = W (H | e)      (ilqr.py:186-190)
             Frag w{0.0, 0.0};
             mma88<true, false>(w, H, Qt, g, q);
@@ -579,8 +630,7 @@ __device__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec& rc, const do
             // ---- Q_uu = R + (B^T P) B ; (Q_ux | Q_u) = (0 | c_u) + (B^T P | B^T p) A'   (ilqr.py:259,261,262)
             Frag quu = load_frag(Rt, g, q);
             mma88<false, false>(quu, H, B, g, q);
-            Frag qux{(q == 3) ? CU[g] : 0.0, 0.0};
-            if (g >= M) qux.c0 = 0.0;
+            Frag qux{(q == 3 && g < M) ? CU[g] : 0.0, 0.0};
             mma88<false, false>(qux, H, A, g, q);
             store_frag(QUU, quu, g, q);
             store_frag(QUX, qux, g, q);
@@ -680,17 +730,19 @@ __device__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec& rc, const do
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Solve kernel (ilqr.py:27-107): one warp per problem
+// Solve kernel (ilqr.py:27-107): one warp per problem, problems handed out through an atomic work counter
 // ---------------------------------------------------------------------------------------------------------------
 template <int M>
 __global__ void __launch_bounds__(WARPS * 32, 2)
-ilqr_ssm_fast_kernel(SsmDev Mdl, IlqrArgs a) {
+ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__ IlqrArgs a) {
     extern __shared__ __align__(16) double sm[];
     build_tables(Mdl, a, sm, M);
     Ctx c;
     c.lane = threadIdx.x & 31;
     c.g = c.lane >> 2;
     c.q = c.lane & 3;
+    c.off0 = (c.lane / 6) * LD + c.lane % 6;
+    c.off1 = ((32 + c.lane) / 6) * LD + (32 + c.lane) % 6;
     c.sh = sm;
     const int warp = threadIdx.x >> 5;
     c.ws = sm + SH_END + warp * W_SIZE;
@@ -698,9 +750,12 @@ ilqr_ssm_fast_kernel(SsmDev Mdl, IlqrArgs a) {
     const srcb200_ilqr_config& cf = a.cfg;
     const int discr = Mdl.discr;
 
-    for (long long b = (long long)blockIdx.x * WARPS + warp; b < a.batch; b += (long long)gridDim.x * WARPS) {
+    while (true) {
+        long long b = 0;
+        if (lane == 0) b = (long long)atomicAdd(a.work_counter, 1);
+        b = __shfl_sync(FULL, b, 0);
+        if (b >= a.batch) break;
         double* wsb = a.ws + b * a.L.total;
-        Rec rec[2] = {rec_at(wsb, a.L), rec_at(wsb + a.L.rec, a.L)};
         double* kbuf = wsb + a.L.k;
         double* ab = wsb + a.L.ab;
         double* Kbuf = a.oK + b * (long long)N * M * 6;
@@ -711,19 +766,25 @@ ilqr_ssm_fast_kernel(SsmDev Mdl, IlqrArgs a) {
         double rho = cf.rho0, drho = cf.drho0;
         int fails = 0, cur = 0, status = 0, trials = 0;
         {
-            Rec& nom = rec[1];
+            const Rec nom = rec_at(wsb + a.L.rec, a.L);
             if (lane < 6) nom.x[lane] = a.x0[b * 6 + lane];
             for (int e = lane; e < N * M; e += 32) nom.u[e] = a.u_init ? a.u_init[b * (long long)N * M + e] : 0.0;
             __syncwarp();
+            __threadfence_block();
         }
-        double cost = fwd_fast<M>(c, a, discr, rec[1].x, rec[1].u, 1.0, nullptr, nullptr, rec[0], ztar, ulast);
+        double cost;
+        {
+            const Rec nom = rec_at(wsb + a.L.rec, a.L), tr0 = rec_at(wsb, a.L);
+            cost = fwd_fast<M>(c, a, discr, nom.x, nom.u, 1.0, nullptr, nullptr, tr0, ztar, ulast);
+        }
         if (a.ocost0 && lane == 0) a.ocost0[b] = cost;
 
         bool conv = false;
         int it = 0;
         while (!conv && it <= cf.max_iter) {
             bool give_up = false;
-            const int restarts = bwd_fast<M>(c, a, rec[cur], ulast, Kbuf, kbuf, ab, rho, drho, give_up);
+            const Rec rcur = rec_at(wsb + (cur ? a.L.rec : 0), a.L), rtrial = rec_at(wsb + (cur ? 0 : a.L.rec), a.L);
+            const int restarts = bwd_fast<M>(c, a, rcur, ulast, Kbuf, kbuf, ab, rho, drho, give_up);
             const double rho_bwd = rho;
             if (give_up) { status |= SRCB200_ILQR_ST_PD_GIVEUP; break; }
             __syncwarp();
@@ -733,7 +794,7 @@ ilqr_ssm_fast_kernel(SsmDev Mdl, IlqrArgs a) {
             double cost_t = cost, alpha_acc = 0.0;
             while (!improved && !failed) {
                 improved = true;
-                cost_t = fwd_fast<M>(c, a, discr, rec[cur].x, rec[cur].u, alpha, Kbuf, kbuf, rec[cur ^ 1], ztar, ulast);
+                cost_t = fwd_fast<M>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
                 ++trials;
                 double dc = 0.0;
                 const double a2 = __dmul_rn(__dmul_rn(alpha, alpha), 0.5);
@@ -776,7 +837,7 @@ ilqr_ssm_fast_kernel(SsmDev Mdl, IlqrArgs a) {
         if (!conv && it > cf.max_iter) status |= SRCB200_ILQR_ST_MAXITER;
 
         __syncwarp();
-        const Rec& fin = rec[cur];
+        const Rec fin = rec_at(wsb + (cur ? a.L.rec : 0), a.L);
         for (int e = lane; e < (N + 1) * 6; e += 32) a.ox[b * (long long)(N + 1) * 6 + e] = fin.x[e];
         for (int e = lane; e < N * M; e += 32) a.ou[b * (long long)N * M + e] = fin.u[e];
         if (lane == 0) {
@@ -804,6 +865,7 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ctas = (a.batch + fast::WARPS - 1) / fast::WARPS;
     const int grid = (int)(ctas < 2LL * sms ? ctas : 2LL * sms);   // persistent: 2 CTAs (16 warps) per SM
+    SRCB_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
     if (M.m == 8) {
         SRCB_CUDA(cudaFuncSetAttribute(fast::ilqr_ssm_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
         fast::ilqr_ssm_fast_kernel<8><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, a);

@@ -84,12 +84,15 @@ __device__ __forceinline__ void zero_tile(double* __restrict__ T, int lane) {
     for (int e = lane; e < TILE; e += 32) T[e] = 0.0;
 }
 
+extern __shared__ __align__(16) double g_sm[];   // [ CTA-shared block | WARPS per-warp blocks ]
+
 struct Ctx {
     int lane, g, q;
     int off0, off1;  // tile offsets of elements `lane` and `32 + lane` (lane < 4) of a row-major 6 x 6 matrix
-    double* sh;      // CTA-shared block
-    double* ws;      // this warp's block
+    int ws_off;      // this warp's block inside g_sm (offsets, not pointers: accesses stay LDS/STS across calls)
 };
+#define CTX_SH (g_sm)
+#define CTX_WS(c) (g_sm + (c).ws_off)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Coefficient table, built once per CTA from the model arrays.
@@ -168,12 +171,12 @@ __device__ __forceinline__ Scatter make_scatter(int lane) {
     return s;
 }
 
-__device__ __forceinline__ double ssm_eval_fast(const Ctx& c, const Scatter& sc, double* __restrict__ AC,
+__device__ __forceinline__ double ssm_eval_fast(const Ctx c, const Scatter sc, double* __restrict__ AC,
                                                 double* __restrict__ Hg) {
     const int lane = c.lane;
-    double* PHI = c.ws + W_PHI;
-    const double* X = c.ws + W_X;
-    const int* fidx = reinterpret_cast<const int*>(c.sh + SH_FIDX);
+    double* PHI = CTX_WS(c) + W_PHI;
+    const double* X = CTX_WS(c) + W_X;
+    const int* fidx = reinterpret_cast<const int*>(CTX_SH + SH_FIDX);
     // features, products left to right like the oracle: (x_a x_b) x_c with absent factors = 1
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -187,7 +190,7 @@ __device__ __forceinline__ double ssm_eval_fast(const Ctx& c, const Scatter& sc,
         }
     }
     __syncwarp();
-    const double* T = c.sh + SH_T;
+    const double* T = CTX_SH + SH_T;
     const double* t0 = T + lane * TS;
     const double* t1 = T + (32 + lane) * TS;
     const double* t2 = T + (64 + lane) * TS;
@@ -290,12 +293,12 @@ __device__ __forceinline__ bool gj_spd(double* __restrict__ tile, int lane) {
 // into registers while step t computes.
 // ---------------------------------------------------------------------------------------------------------------
 template <int M>
-__device__ __noinline__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int discr, const double* __restrict__ nx,
+__device__ __noinline__ double fwd_fast(const Ctx c, const IlqrArgs& a, int discr, const double* __restrict__ nx,
                                         const double* __restrict__ nu, double alpha, const double* __restrict__ K,
-                                        const double* __restrict__ k, const Rec& tr, const double* __restrict__ ztar,
+                                        const double* __restrict__ k, const Rec tr, const double* __restrict__ ztar,
                                         const double* __restrict__ ulast) {
     const int lane = c.lane, g = c.g, q = c.q, N = a.N;
-    double* ws = c.ws;
+    double* ws = CTX_WS(c);
     double* X = ws + W_X;   double* U = ws + W_U;   double* UP = ws + W_UP;  double* DC = ws + W_DC;
     double* DD = ws + W_DD; double* E = ws + W_E;   double* DX = ws + W_DX;  double* QE = ws + W_QE;
     double* RDU = ws + W_RDU;
@@ -305,8 +308,8 @@ __device__ __noinline__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int dis
     double* SP = ws + W_TILES + 3 * TILE;   // sep = inv(A_c) (A_d - I)
     double* BD = ws + W_TILES + 4 * TILE;   // B_d
     double* W0 = ws + W_TILES + 5 * TILE;   // inv(I - h A_c) for bil
-    const double* Qt = c.sh + SH_Q;  const double* Rt = c.sh + SH_R;  const double* Qft = c.sh + SH_QF;
-    const double* Brt = c.sh + SH_BR; const double* zref = c.sh + SH_ZREF;
+    const double* Qt = CTX_SH + SH_Q;  const double* Rt = CTX_SH + SH_R;  const double* Qft = CTX_SH + SH_QF;
+    const double* Brt = CTX_SH + SH_BR; const double* zref = CTX_SH + SH_ZREF;
     const Scatter sc = make_scatter(lane);
     const double dt = a.dt;
     const bool inc = a.cfg.include_input_var_constraint != 0;
@@ -524,29 +527,28 @@ __device__ __noinline__ double fwd_fast(const Ctx& c, const IlqrArgs& a, int dis
 // ---------------------------------------------------------------------------------------------------------------
 // Backward pass (ilqr.py:219-300).  The record of step t-1 is fetched into registers while step t computes.
 // ---------------------------------------------------------------------------------------------------------------
-template <int M>
-struct StepRegs { double a0, a1, h0, h1, b0, b1, e, u, up; };
+struct BwdResult { double rho, drho; int restarts; int give_up; };
+
+#define LOAD_STEP(tt)                                                                                        \
+    do {                                                                                                     \
+        const long long t36 = (long long)(tt) * 36, tB = (long long)(tt) * 6 * M;                            \
+        pa0 = rc.A[t36 + lane];                                                                              \
+        ph0 = rc.H[t36 + lane];                                                                              \
+        pa1 = rc.A[t36 + 32 + (lane & 3)];                                                                   \
+        ph1 = rc.H[t36 + 32 + (lane & 3)];                                                                   \
+        pb0 = rc.B[tB + (lane < 6 * M ? lane : 0)];                                                          \
+        pb1 = rc.B[tB + (32 + lane < 6 * M ? 32 + lane : 0)];                                                \
+        pe = rc.e[(tt) * 6 + (lane < 6 ? lane : 0)];                                                         \
+        pu = rc.u[(tt) * M + (lane & (M - 1))];                                                              \
+        pup = ((tt) == 0) ? (ulast ? ulast[lane & (M - 1)] : 0.0) : rc.u[((tt) - 1) * M + (lane & (M - 1))]; \
+    } while (0)
 
 template <int M>
-__device__ __forceinline__ void load_step(StepRegs<M>& r, const Rec& rc, int t, int lane, const double* __restrict__ ulast) {
-    r.a0 = rc.A[(long long)t * 36 + lane];
-    r.h0 = rc.H[(long long)t * 36 + lane];
-    if (lane < 4) { r.a1 = rc.A[(long long)t * 36 + 32 + lane]; r.h1 = rc.H[(long long)t * 36 + 32 + lane]; }
-    if (lane < 6 * M) r.b0 = rc.B[(long long)t * 6 * M + lane];
-    if (32 + lane < 6 * M) r.b1 = rc.B[(long long)t * 6 * M + 32 + lane];
-    if (lane < 6) r.e = rc.e[t * 6 + lane];
-    if (lane < M) {
-        r.u = rc.u[t * M + lane];
-        r.up = (t == 0) ? (ulast ? ulast[lane] : 0.0) : rc.u[(t - 1) * M + lane];
-    }
-}
-
-template <int M>
-__device__ __noinline__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec& rc, const double* __restrict__ ulast,
-                                     double* __restrict__ Kout, double* __restrict__ kout, double* __restrict__ ab,
-                                     double& rho, double& drho, bool& give_up) {
+__device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const Rec rc, const double* __restrict__ ulast,
+                                           double* __restrict__ Kout, double* __restrict__ kout, double* __restrict__ ab,
+                                           double rho, double drho) {
     const int lane = c.lane, g = c.g, q = c.q, N = a.N;
-    double* ws = c.ws;
+    double* ws = CTX_WS(c);
     double* P = ws + W_TILES + 0 * TILE;     // (P | p)
     double* A = ws + W_TILES + 1 * TILE;     // A_t with A[6][6] = 1
     double* B = ws + W_TILES + 2 * TILE;     // B_t
@@ -558,14 +560,15 @@ __device__ __noinline__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec&
     double* KT = ws + W_TILES + 8 * TILE;    // (K | k)
     double* CU = ws + W_DC;
     double* DU = ws + W_DD;
-    const double* Qt = c.sh + SH_Q;  const double* Rt = c.sh + SH_R;  const double* Qft = c.sh + SH_QF;
+    const double* Qt = CTX_SH + SH_Q;  const double* Rt = CTX_SH + SH_R;  const double* Qft = CTX_SH + SH_QF;
     const srcb200_ilqr_config& cf = a.cfg;
     const bool sreg = cf.regularize && cf.state_regularization;
     const bool inc = cf.include_input_var_constraint != 0;
     const int bo0 = (lane / M) * LD + lane % M;
     const int bo1 = ((32 + lane) / M) * LD + (32 + lane) % M;
     int restarts = 0;
-    give_up = false;
+    int give_up = 0;
+    double pa0, pa1, ph0, ph1, pb0, pb1, pe, pu, pup;   // record of the next step to process, in registers
 
     while (true) {
         for (int t = 0; t < NTILES; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
@@ -574,8 +577,7 @@ __device__ __noinline__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec&
         H[c.off0] = rc.H[(long long)N * 36 + lane];
         if (lane < 4) H[c.off1] = rc.H[(long long)N * 36 + 32 + lane];
         if (lane < 6) H[lane * LD + 6] = rc.e[N * 6 + lane];
-        StepRegs<M> pre;
-        load_step<M>(pre, rc, N - 1, lane, ulast);
+        LOAD_STEP(N - 1);
         __syncwarp();
         {
             Frag f{0.0, 0.0};
@@ -594,14 +596,14 @@ __device__ __noinline__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec&
         bool ok = true;
         for (int t = N - 1; t >= 0; --t) {
             // ---- stage A_t, B_t, (H_t | e_t), du from the prefetched registers; fetch step t-1
-            A[c.off0] = pre.a0;
-            H[c.off0] = pre.h0;
-            if (lane < 4) { A[c.off1] = pre.a1; H[c.off1] = pre.h1; }
-            if (lane < 6 * M) B[bo0] = pre.b0;
-            if (32 + lane < 6 * M) B[bo1] = pre.b1;
-            if (lane < 6) H[lane * LD + 6] = pre.e;   // rows 6,7 / column 7 of this tile never reach rows<6, cols<7
-            if (lane < M) DU[lane] = inc ? __dsub_rn(pre.u, pre.up) : pre.u;
-            if (t > 0) load_step<M>(pre, rc, t - 1, lane, ulast);
+            A[c.off0] = pa0;
+            H[c.off0] = ph0;
+            if (lane < 4) { A[c.off1] = pa1; H[c.off1] = ph1; }
+            if (lane < 6 * M) B[bo0] = pb0;
+            if (32 + lane < 6 * M) B[bo1] = pb1;
+            if (lane < 6) H[lane * LD + 6] = pe;   // rows 6,7 / column 7 of this tile never reach rows<6, cols<7
+            if (lane < M) DU[lane] = inc ? __dsub_rn(pu, pup) : pu;
+            if (t > 0) LOAD_STEP(t - 1);
             __syncwarp();
             if (lane >= 8 && lane < 8 + M) {
                 const int i = lane - 8;
@@ -724,9 +726,9 @@ __device__ __noinline__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec&
             break;
         }
         ++restarts;
-        if (restarts >= cf.max_pd_restarts) { give_up = true; break; }
+        if (restarts >= cf.max_pd_restarts) { give_up = 1; break; }
     }
-    return restarts;
+    return BwdResult{rho, drho, restarts, give_up};
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -735,17 +737,15 @@ __device__ __noinline__ int bwd_fast(const Ctx& c, const IlqrArgs& a, const Rec&
 template <int M>
 __global__ void __launch_bounds__(WARPS * 32, 2)
 ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__ IlqrArgs a) {
-    extern __shared__ __align__(16) double sm[];
-    build_tables(Mdl, a, sm, M);
+    build_tables(Mdl, a, g_sm, M);
     Ctx c;
     c.lane = threadIdx.x & 31;
     c.g = c.lane >> 2;
     c.q = c.lane & 3;
     c.off0 = (c.lane / 6) * LD + c.lane % 6;
     c.off1 = ((32 + c.lane) / 6) * LD + (32 + c.lane) % 6;
-    c.sh = sm;
     const int warp = threadIdx.x >> 5;
-    c.ws = sm + SH_END + warp * W_SIZE;
+    c.ws_off = SH_END + warp * W_SIZE;
     const int lane = c.lane, N = a.N;
     const srcb200_ilqr_config& cf = a.cfg;
     const int discr = Mdl.discr;
@@ -782,11 +782,12 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
         bool conv = false;
         int it = 0;
         while (!conv && it <= cf.max_iter) {
-            bool give_up = false;
             const Rec rcur = rec_at(wsb + (cur ? a.L.rec : 0), a.L), rtrial = rec_at(wsb + (cur ? 0 : a.L.rec), a.L);
-            const int restarts = bwd_fast<M>(c, a, rcur, ulast, Kbuf, kbuf, ab, rho, drho, give_up);
+            const BwdResult br = bwd_fast<M>(c, a, rcur, ulast, Kbuf, kbuf, ab, rho, drho);
+            rho = br.rho; drho = br.drho;
+            const int restarts = br.restarts;
             const double rho_bwd = rho;
-            if (give_up) { status |= SRCB200_ILQR_ST_PD_GIVEUP; break; }
+            if (br.give_up) { status |= SRCB200_ILQR_ST_PD_GIVEUP; break; }
             __syncwarp();
             const double prev_cost = cost;
             double alpha = cf.alpha0;

@@ -25,7 +25,7 @@ namespace fast {
 
 constexpr int LD = 12;            // tile row stride (doubles): A-/B-fragment loads are bank-conflict free
 constexpr int TILE = 8 * LD;
-constexpr int WARPS = 8;          // problems in flight per CTA
+constexpr int WARPS = 8;          // problems in flight per CTA (2 CTAs per SM; 20-24 warps at 96/80 registers measured slower)
 constexpr int NJ = 28;            // terms per partial dot
 constexpr int NPD = 128;          // partial-dot slots: 4 rounds x 32 lanes (108 used)
 constexpr int TS = 30;            // table row stride (doubles)

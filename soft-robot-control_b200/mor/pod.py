@@ -53,7 +53,7 @@ def energy_mode_count_device(s2, tol):
     return int(idx[0].item()) + 1 if idx.numel() else int(s2.numel())
 
 
-def _finish_pod(Xd, G, tol, full_U):
+def _finish_pod(Xd, G, tol, full_U, gemm=None):
     torch = L.torch_mod()
     lam, V = torch.linalg.eigh(G)                # ascending
     lam = torch.flip(lam, (0,)).clamp_min(0.0)
@@ -62,7 +62,7 @@ def _finish_pod(Xd, G, tol, full_U):
     nb = energy_mode_count_device(lam, tol)
     keep = V.shape[1] if full_U else nb
     Vs = (V[:, :keep] / S[:keep].clamp_min(np.finfo(np.float64).tiny)).contiguous()
-    U = dgemm_device(Xd, Vs)                     # (nf, keep)
+    U = (gemm or dgemm_device)(Xd, Vs)           # (nf, keep)
     return U, nb, S
 
 
@@ -72,15 +72,15 @@ def compute_POD_device(Xd, tol, full_U=False):
     return _finish_pod(Xd, G, tol, full_U)
 
 
-def compute_POD_sharded(X_local, tol, group=None):
+def compute_POD_sharded(X_local, tol, group=None, gram=None, gemm=None):
     """Row-sharded POD: every rank holds a block of DOF rows X_g (nf_g x ns).  G = sum_g X_g^T X_g through ONE
-    NCCL allreduce (torch.distributed), the eigen-solve is replicated, U_g = X_g V S^-1 stays row-sharded.
-    Returns (U_local, nbModes, S)."""
-    import torch.distributed as dist
-    G = gram_device(X_local)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
-    return _finish_pod(X_local, G, tol, False)
+    all-reduce (NCCL over NVLink on GPUs), the small eigen-solve is replicated, U_g = X_g V S^-1 stays row-sharded.
+    Returns (U_local, nbModes, S).  `gram` / `gemm` default to the DMMA kernels; the gloo CPU tests of the
+    multi-process logic inject plain torch stand-ins."""
+    from ..parallel import allreduce_sum_
+    G = (gram or gram_device)(X_local)
+    allreduce_sum_(G, group)
+    return _finish_pod(X_local, G, tol, False, gemm)
 
 
 def compute_POD(snapshots, tol, rom_dim=None):

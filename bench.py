@@ -312,6 +312,62 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
             "roofline": roof}
 
 
+def run_ssm_rollout(args, rank, world, dev_index):
+    import torch
+    import torch.distributed as dist
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200 import _lib as L
+    from sofacontrol_b200.SSM.ssm import SSMDynamics
+    batch, N = args.batch, args.horizon
+    s = synth.trunk_ssm(8)
+    g = SSMDynamics(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
+    rng = np.random.default_rng(1 + rank)
+    x0h = np.zeros((batch, 6)); x0h[:, :3] = rng.uniform(-0.5, 0.5, size=(batch, 3))
+    uh = rng.uniform(0, 800, size=(batch, N, 8))
+    x0, u = L.to_dev(x0h), L.to_dev(uh)
+    flush = torch.empty(256 * 1024 * 1024 // 8, device="cuda", dtype=torch.float64)
+    for _ in range(args.warmup):
+        g.rollout_device(x0, u, 0.02)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(dev_index) as clk:
+        for s_, e_ in ev:
+            flush.fill_(1.0)
+            s_.record()
+            g.rollout_device(x0, u, 0.02)
+            e_.record()
+        torch.cuda.synchronize()
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g.rollout(x0h, uh, 0.02)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    total = batch * N * world * args.steps
+    hbm, hsrc, fp64 = measured_peaks()
+    fl = batch * N * (2.0 * 83 * (6 + 36 + 6) + 2 * (2 * 216) + 2 * 216 + 2 * 36 * 8 + 2 * (36 + 48) * 2)
+    ach = fl / (t_dev / args.steps) / 1e12
+    return {"metric": "ssm_rollout_steps_per_sec", "value": total / t_dev, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Trunk SSM batched open-loop rollout (BASELINE configs[0] batched): %d trajectories x %d steps per "
+                                   "GPU, n=6 m=8 order 3, be discretisation, dt=0.02, u~U(0,800)" % (batch, N),
+                       "batch_per_gpu": batch, "horizon": N, "l2": "256 MB buffer written between timed steps (untimed)"},
+            "e2e": {"value": total / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": int((x0h.size + uh.size) * 8),
+                    "d2h_bytes_per_step": int(batch * (N + 1) * 12 * 8)},
+            "gpu_launches": args.steps, "clocks": clk.summary(),
+            "roofline": {"kernel": "ssm_rollout_fast_kernel<8>", "bound": "tensor", "achieved": ach, "peak": fp64,
+                         "unit": "TFLOP/s", "frac": ach / fp64, "traffic": None,
+                         "note": "dense algorithmic flops (model contraction + discretisation + step) / event time, of measured cuBLAS DGEMM"}}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU port on the host cores, same workload/metric (bounded sample)."""
     t_all = []
@@ -336,7 +392,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ilqr_trunk_ssm",
-                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting"])
+                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting", "ssm_rollout"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--cpu-per-core", type=int, default=2)
@@ -362,6 +418,8 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.workload == "ilqr_trunk_ssm":
         res = run_ilqr(args, rank, world, local)
+    elif args.workload == "ssm_rollout":
+        res = run_ssm_rollout(args, rank, world, local)
     else:
         res = run_tpwl_rollout(args, rank, world, local, "nn" if args.workload.endswith("nn") else "weighting")
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "ilqr_trunk_ssm":

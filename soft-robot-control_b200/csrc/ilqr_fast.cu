@@ -114,7 +114,7 @@ __device__ int find_monomial(const SsmDev& M, int a, int b, int c) {
     return -1;
 }
 
-__device__ void build_tables(const SsmDev& M, const IlqrArgs& a, double* sh, int m) {
+__device__ void build_tables(const SsmDev& M, const double* Qg, const double* Rg, const double* Qfg, double* sh, int m) {
     double* T = sh + SH_T;
     for (int e = threadIdx.x; e < NPD * TS; e += blockDim.x) T[e] = 0.0;
     for (int e = threadIdx.x; e < 4 * TILE + 8; e += blockDim.x) sh[SH_Q + e] = 0.0;
@@ -142,10 +142,10 @@ __device__ void build_tables(const SsmDev& M, const IlqrArgs& a, double* sh, int
     }
     for (int e = threadIdx.x; e < 36; e += blockDim.x) {
         const int i = e / 6, j = e - 6 * i;
-        sh[SH_Q + i * LD + j] = a.Q[e];
-        sh[SH_QF + i * LD + j] = a.Qf[e];
+        if (Qg) sh[SH_Q + i * LD + j] = Qg[e];
+        if (Qfg) sh[SH_QF + i * LD + j] = Qfg[e];
     }
-    for (int e = threadIdx.x; e < m * m; e += blockDim.x) sh[SH_R + (e / m) * LD + (e % m)] = a.R[e];
+    if (Rg) for (int e = threadIdx.x; e < m * m; e += blockDim.x) sh[SH_R + (e / m) * LD + (e % m)] = Rg[e];
     for (int e = threadIdx.x; e < 6 * m; e += blockDim.x) sh[SH_BR + (e / m) * LD + (e % m)] = M.B[e];
     for (int e = threadIdx.x; e < 6; e += blockDim.x) sh[SH_ZREF + e] = M.zref[e];
     int* fidx = reinterpret_cast<int*>(sh + SH_FIDX);
@@ -213,8 +213,8 @@ __device__ __forceinline__ double ssm_eval_fast(const Ctx c, const Scatter sc, d
     a0 = __dadd_rn(a0, b0); a1 = __dadd_rn(a1, b1); a2 = __dadd_rn(a2, b2); a3 = __dadd_rn(a3, b3);
     // A_c into its tile, H_t straight to the trajectory record
     AC[sc.o0] = a0;
-    if (lane < 4) AC[sc.o1] = a1; else Hg[lane - 4] = a1;
-    if (lane < 8) Hg[28 + lane] = a2;
+    if (lane < 4) AC[sc.o1] = a1; else if (Hg) Hg[lane - 4] = a1;
+    if (lane < 8 && Hg) Hg[28 + lane] = a2;
     // combine the three parts of the 12 value outputs in lanes 8..19
     const int v = lane - 8;
     const double p1 = __shfl_sync(FULL, a3, v & 31);
@@ -737,7 +737,7 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
 template <int M>
 __global__ void __launch_bounds__(WARPS * 32, 2)
 ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__ IlqrArgs a) {
-    build_tables(Mdl, a, g_sm, M);
+    build_tables(Mdl, a.Q, a.R, a.Qf, g_sm, M);
     Ctx c;
     c.lane = threadIdx.x & 31;
     c.g = c.lane >> 2;
@@ -852,7 +852,168 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Open-loop rollout (ssm.py:134-156) for the same model shape: one warp per trajectory, re-linearised every step.
+// ---------------------------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+ssm_rollout_fast_kernel(const __grid_constant__ SsmDev Mdl, long long batch, int N, const double* __restrict__ x0,
+                        const double* __restrict__ u, double dt, double* __restrict__ xo, double* __restrict__ zo) {
+    build_tables(Mdl, nullptr, nullptr, nullptr, g_sm, M);
+    Ctx c;
+    c.lane = threadIdx.x & 31;
+    c.g = c.lane >> 2;
+    c.q = c.lane & 3;
+    c.off0 = (c.lane / 6) * LD + c.lane % 6;
+    c.off1 = ((32 + c.lane) / 6) * LD + (32 + c.lane) % 6;
+    c.ws_off = SH_END + (threadIdx.x >> 5) * W_SIZE;
+    const int lane = c.lane, g = c.g, q = c.q, discr = Mdl.discr;
+    double* ws = CTX_WS(c);
+    double* X = ws + W_X;   double* U = ws + W_U;   double* DC = ws + W_DC;  double* DD = ws + W_DD;
+    double* AC = ws + W_TILES + 0 * TILE;  double* AD = ws + W_TILES + 1 * TILE;  double* IA = ws + W_TILES + 2 * TILE;
+    double* SP = ws + W_TILES + 3 * TILE;  double* BD = ws + W_TILES + 4 * TILE;  double* W0 = ws + W_TILES + 5 * TILE;
+    const double* Brt = CTX_SH + SH_BR; const double* zref = CTX_SH + SH_ZREF;
+    const Scatter sc = make_scatter(lane);
+    const int bo0 = (lane / M) * LD + lane % M, bo1 = ((32 + lane) / M) * LD + (32 + lane) % M;
+
+    // every trajectory costs the same: static striding is perfectly balanced, no work counter needed
+    for (long long b = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); b < batch; b += (long long)gridDim.x * WARPS) {
+        const double* ub = u + b * (long long)N * M;
+        double* xb = xo + b * (long long)(N + 1) * 6;
+        double* zb = zo ? zo + b * (long long)(N + 1) * 6 : nullptr;
+        for (int t = 0; t < 6; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
+        if (lane < 8) { X[lane] = lane < 6 ? x0[b * 6 + lane] : (lane == 7 ? 1.0 : 0.0); U[lane] = 0.0; DC[lane] = 0.0; }
+        if (lane < 6) xb[lane] = x0[b * 6 + lane];
+        if (lane == 0) ws[W_PHI] = 1.0;
+        double p_u = (lane < M && N > 0) ? ub[lane] : 0.0;
+        __syncwarp();
+        for (int t = 0; t <= N; ++t) {
+            const bool last = (t == N);
+            if (!last && lane < M) U[lane] = p_u;
+            if (t + 1 < N && lane < M) p_u = ub[(t + 1) * M + lane];
+            const double val = ssm_eval_fast(c, sc, AC, nullptr);
+            if (zb && lane >= 14 && lane < 20) zb[t * 6 + lane - 14] = __dadd_rn(val, zref[lane - 14]);
+            __syncwarp();
+            if (last) break;
+            if (lane >= 8 && lane < 14) {
+                const int i = lane - 8;
+                double bu = 0.0, ax = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < M; ++jj) bu = fma(Brt[i * LD + jj], U[jj], bu);
+#pragma unroll
+                for (int kk = 0; kk < 6; ++kk) ax = fma(AC[i * LD + kk], X[kk], ax);
+                DC[i] = __dsub_rn(__dsub_rn(__dadd_rn(val, bu), ax), bu);
+            }
+            if (discr == SRCB200_DISCR_BE || discr == SRCB200_DISCR_BIL) {
+                const double h = (discr == SRCB200_DISCR_BE) ? dt : 0.5 * dt;
+                const int hm = lane >> 4, j = lane & 15;
+                double col[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    double v = 0.0;
+                    if (j < 6) {
+                        const double av = AC[r * LD + j];
+                        v = hm ? av : __dsub_rn(r == j ? 1.0 : 0.0, __dmul_rn(h, av));
+                    } else if (j < 12) {
+                        v = (r == j - 6) ? 1.0 : 0.0;
+                    }
+                    col[r] = v;
+                }
+                gj6_pair(col, lane, hm ? IA : (discr == SRCB200_DISCR_BE ? AD : W0));
+                __syncwarp();
+                if (discr == SRCB200_DISCR_BIL) {
+                    Frag f{0.0, 0.0};
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const int kk = 4 * s + q;
+                        const double av = (g < 6 && kk < 6) ? __dadd_rn(g == kk ? 1.0 : 0.0, __dmul_rn(h, AC[g * LD + kk])) : 0.0;
+                        dmma(f, av, W0[kk * LD + g]);
+                    }
+                    store_frag(AD, f, g, q);
+                    __syncwarp();
+                }
+                Frag s{0.0, 0.0};
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int kk = 4 * s2 + q;
+                    const double bv = (kk < 6 && g < 6) ? __dsub_rn(AD[kk * LD + g], kk == g ? 1.0 : 0.0) : 0.0;
+                    dmma(s, IA[g * LD + kk], bv);
+                }
+                store_frag(SP, s, g, q);
+                __syncwarp();
+                Frag bf{0.0, 0.0};
+                mma88<false, false>(bf, SP, Brt, g, q);
+                store_frag(BD, bf, g, q);
+                if (lane < 6) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < 6; ++kk) acc = fma(SP[lane * LD + kk], DC[kk], acc);
+                    DD[lane] = acc;
+                }
+            } else {
+                __syncwarp();
+                if (discr == SRCB200_DISCR_FE) {
+                    const double v0 = __dmul_rn(dt, AC[c.off0]);
+                    AD[c.off0] = (lane / 6 == lane % 6) ? __dadd_rn(1.0, v0) : v0;
+                    if (lane < 4) {
+                        const double v1 = __dmul_rn(dt, AC[c.off1]);
+                        AD[c.off1] = (lane == 3) ? __dadd_rn(1.0, v1) : v1;
+                    }
+                    if (lane < 6 * M) BD[bo0] = __dmul_rn(dt, Brt[bo0]);
+                    if (32 + lane < 6 * M) BD[bo1] = __dmul_rn(dt, Brt[bo1]);
+                    if (lane < 6) DD[lane] = __dmul_rn(dt, DC[lane]);
+                } else {
+                    AD[c.off0] = AC[c.off0];
+                    if (lane < 4) AD[c.off1] = AC[c.off1];
+                    if (lane < 6 * M) BD[bo0] = Brt[bo0];
+                    if (32 + lane < 6 * M) BD[bo1] = Brt[bo1];
+                    if (lane < 6) DD[lane] = DC[lane];
+                }
+            }
+            __syncwarp();
+            double xn = 0.0;
+            if (lane < 6) {
+                double ax = 0.0, bu = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 6; ++kk) ax = fma(AD[lane * LD + kk], X[kk], ax);
+#pragma unroll
+                for (int jj = 0; jj < M; ++jj) bu = fma(BD[lane * LD + jj], U[jj], bu);
+                xn = __dadd_rn(__dadd_rn(ax, bu), DD[lane]);
+            }
+            __syncwarp();
+            if (lane < 6) { X[lane] = xn; xb[(long long)(t + 1) * 6 + lane] = xn; }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace fast
+
+// Rollout dispatch (called from ssm.cu): returns handled = true when the specialised kernel ran.
+int ssm_rollout_fast_launch(const SsmDev& M, long long batch, int N, const double* x0, const double* u, double dt,
+                            double* x, double* z, cudaStream_t st, bool* handled) {
+    *handled = false;
+    const char* env = getenv("SRCB200_ILQR_GENERIC");
+    if (env && env[0] == '1') return 0;
+    if (!(M.n == 6 && M.nz == 6 && M.order == 3 && M.nfeat == fast::NFEAT && (M.m == 4 || M.m == 8))) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ctas = (batch + fast::WARPS - 1) / fast::WARPS;
+    const int grid = (int)(ctas < 2LL * sms ? ctas : 2LL * sms);
+    if (M.m == 8) {
+        SRCB_CUDA(cudaFuncSetAttribute(fast::ssm_rollout_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
+        fast::ssm_rollout_fast_kernel<8><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, batch, N, x0, u, dt, x, z);
+    } else {
+        SRCB_CUDA(cudaFuncSetAttribute(fast::ssm_rollout_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
+        fast::ssm_rollout_fast_kernel<4><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, batch, N, x0, u, dt, x, z);
+    }
+    SRCB_LAUNCH_CHECK("ssm_rollout_fast_kernel");
+    *handled = true;
+    return 0;
+}
+
 
 // Dispatch: Gauss-Newton SSM problems with the Trunk/Diamond shape go to the specialised kernel.
 int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bool* handled) {

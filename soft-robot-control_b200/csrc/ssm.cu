@@ -4,6 +4,9 @@
 
 namespace srcb {
 
+int ssm_rollout_fast_launch(const SsmDev& M, long long batch, int N, const double* x0, const double* u, double dt,
+                            double* x, double* z, cudaStream_t st, bool* handled);   // ilqr_fast.cu
+
 int check_ssm_model(const srcb200_ssm_model* s) {
     if (!s) return fail(SRCB200_E_NULL, "ssm model is NULL");
     if (s->n < 1 || s->n > SRCB200_SSM_MAX_N || s->m < 1 || s->m > SRCB200_SSM_MAX_M ||
@@ -185,6 +188,11 @@ extern "C" int srcb200_ssm_rollout_batch(const srcb200_ssm_model* mdl, int64_t b
     if (batch == 0) return 0;
     if (!x0 || !x || (N > 0 && !u)) return fail(SRCB200_E_NULL, "x0/u/x is NULL");
     SsmDev M = to_dev(*mdl);
+    {   // Trunk / Diamond shape: warp-per-trajectory kernel sharing the specialised iLQR device code
+        bool handled = false;
+        if (int e = ssm_rollout_fast_launch(M, batch, N, x0, u, dt, x, z, (cudaStream_t)stream, &handled)) return e;
+        if (handled) return 0;
+    }
     const int n = M.n, m = M.m, nz = M.nz;
     const size_t smem = sizeof(double) * (n + m + n * n + n * m + n + nz + n + ssm_eval_scratch_doubles(n, m, M.nfeat));
     SRCB_CUDA(cudaFuncSetAttribute(ssm_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

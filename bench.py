@@ -289,11 +289,15 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
     hbm, hsrc, fp64 = measured_peaks()
     n, m, P, r = 72, 4, 1000, 36
     if method == 'nn':
-        byt = batch * N * ((n * n + n * m + n) * 8 + P * r * 8 + (2 * n + m) * 8)
-        roof = {"kernel": "tpwl_rollout_nn_kernel", "bound": "hbm", "achieved": byt / (t_dev / args.steps) / 1e9,
+        byt = batch * N * ((n * n + n * m + n) * 8 + (2 * n + m) * 8) + N * P * r * 8
+        ops = batch * N * 3.0 * P * r
+        roof = {"kernel": "tpwl_rollout_nn_multi_kernel<36>", "bound": "hbm", "achieved": byt / (t_dev / args.steps) / 1e9,
                 "peak": hbm, "unit": "GB/s", "traffic": None,
-                "note": "algorithmic bytes per trajectory-step = gathered bank entry 44352 B + distance bank 288000 B "
-                        "+ state I/O (SURVEY 8d); the banks are L2-resident so this is an L2/HBM stream rate, of " + hsrc}
+                "fp64_ops_tops": ops / (t_dev / args.steps) / 1e12,
+                "note": "algorithmic bytes per trajectory-step = gathered bank entry 44352 B + state I/O, distance bank "
+                        "288000 B once per time step for the whole batch (SURVEY 8d), of " + hsrc + "; the distance search "
+                        "(3 P r un-fused FP64 ops per step, numpy rounding order) is the actual limiter: fp64_ops_tops "
+                        "against %.1f T pipe slots/s (half the measured DGEMM flop rate)" % (fp64 / 2)}
     else:
         fl = batch * N * 2.0 * P * (n * n + n * m + n)
         roof = {"kernel": "dgemm_kernel (bank blend)", "bound": "tensor", "achieved": fl / (t_dev / args.steps) / 1e12,

@@ -245,6 +245,178 @@ tpwl_rollout_nn_kernel(TpwlDev M, long long batch, int N, const double* __restri
     }
 }
 
+// ---- nn rollout on a pre-discretised bank, T trajectories per CTA ----------------------------------------------
+// The distance bank (r x P, L2 resident) is read ONCE per CTA-step and applied to kMT trajectories, which divides
+// the L2 traffic of the selection by kMT; sums follow numpy's pairwise order (8 strided accumulators per row,
+// r <= 128), so indices stay bit-exact.  RT > 0 fixes r at compile time (Diamond: 36) so the whole distance loop
+// unrolls with immediate offsets.  The affine step is one thread per row against the gathered A_i (L2).
+constexpr int kMT = 4;        // trajectories per CTA
+constexpr int kMThreads = 256;
+
+// sum_j (bank[j][p] - x[tr][j])^2 in numpy's pairwise order for the kMT trajectories; xs = transposed states
+// xs[j * kMT + tr].  Adds w * sqrt(sum) to out[tr].
+template <int RT>
+__device__ __forceinline__ void multi_distances(int r_runtime, int P, const double* __restrict__ bank_p,
+                                                const double* __restrict__ xs, double w, double (&out)[kMT]) {
+    const int r = RT > 0 ? RT : r_runtime;
+    double res[kMT];
+    if (r < 8) {
+#pragma unroll
+        for (int tr = 0; tr < kMT; ++tr) res[tr] = 0.0;
+        for (int j = 0; j < r; ++j) {
+            const double qv = bank_p[(size_t)j * P];
+#pragma unroll
+            for (int tr = 0; tr < kMT; ++tr) {
+                const double t = __dsub_rn(qv, xs[j * kMT + tr]);
+                res[tr] = __dadd_rn(res[tr], __dmul_rn(t, t));
+            }
+        }
+    } else {
+        double acc[kMT][8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double qv = bank_p[(size_t)k * P];
+#pragma unroll
+            for (int tr = 0; tr < kMT; ++tr) {
+                const double t = __dsub_rn(qv, xs[k * kMT + tr]);
+                acc[tr][k] = __dmul_rn(t, t);
+            }
+        }
+        const int rfull = r - (r % 8);
+#pragma unroll
+        for (int j = 8; j < rfull; j += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double qv = bank_p[(size_t)(j + k) * P];
+#pragma unroll
+                for (int tr = 0; tr < kMT; ++tr) {
+                    const double t = __dsub_rn(qv, xs[(j + k) * kMT + tr]);
+                    acc[tr][k] = __dadd_rn(acc[tr][k], __dmul_rn(t, t));
+                }
+            }
+        }
+#pragma unroll
+        for (int tr = 0; tr < kMT; ++tr)
+            res[tr] = __dadd_rn(__dadd_rn(__dadd_rn(acc[tr][0], acc[tr][1]), __dadd_rn(acc[tr][2], acc[tr][3])),
+                                __dadd_rn(__dadd_rn(acc[tr][4], acc[tr][5]), __dadd_rn(acc[tr][6], acc[tr][7])));
+#pragma unroll
+        for (int j = rfull; j < r; ++j) {
+            const double qv = bank_p[(size_t)j * P];
+#pragma unroll
+            for (int tr = 0; tr < kMT; ++tr) {
+                const double t = __dsub_rn(qv, xs[j * kMT + tr]);
+                res[tr] = __dadd_rn(res[tr], __dmul_rn(t, t));
+            }
+        }
+    }
+#pragma unroll
+    for (int tr = 0; tr < kMT; ++tr) out[tr] = __dadd_rn(out[tr], __dmul_rn(w, sqrt(res[tr])));
+}
+
+template <int RT>
+__global__ void __launch_bounds__(kMThreads, 2)
+tpwl_rollout_nn_multi_kernel(TpwlDev M, long long batch, int N, const double* __restrict__ x0,
+                             const double* __restrict__ u, double* __restrict__ xo, int* __restrict__ idxo) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red_d[kMT][kMThreads / 32];
+    __shared__ int red_i[kMT][kMThreads / 32];
+    __shared__ int sel[kMT];
+    const int n = M.n, m = M.m, r = RT > 0 ? RT : M.r, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* sxT = sm;                 // n x kMT  (transposed: the kMT states of one coordinate are contiguous)
+    double* su = sxT + kMT * n;       // kMT x m
+    double* sxn = su + kMT * m;       // kMT x n
+    const long long groups = (batch + kMT - 1) / kMT;
+    for (long long gidx = blockIdx.x; gidx < groups; gidx += gridDim.x) {
+        const long long b0 = gidx * kMT;
+        const int nt = (int)((batch - b0) < kMT ? (batch - b0) : kMT);
+        for (int e = tid; e < kMT * n; e += kMThreads) {
+            const int tr = e / n, i = e - tr * n;
+            const double v = (tr < nt) ? x0[(b0 + tr) * n + i] : 0.0;
+            sxT[i * kMT + tr] = v;
+            if (tr < nt) xo[(b0 + tr) * (long long)(N + 1) * n + i] = v;
+        }
+        __syncthreads();
+        for (int t = 0; t < N; ++t) {
+            for (int e = tid; e < kMT * m; e += kMThreads) {
+                const int tr = e / m, i = e - tr * m;
+                su[e] = (tr < nt) ? u[((b0 + tr) * (long long)N + t) * m + i] : 0.0;
+            }
+            // ---- nearest stored point for the kMT states (x = [v; q]: q at offset r, v at offset 0)
+            double best[kMT];
+            int bi[kMT];
+#pragma unroll
+            for (int tr = 0; tr < kMT; ++tr) { best[tr] = INFINITY; bi[tr] = 0x7fffffff; }
+            for (int p = tid; p < M.P; p += kMThreads) {
+                double dd[kMT];
+#pragma unroll
+                for (int tr = 0; tr < kMT; ++tr) dd[tr] = 0.0;
+                if (M.wq != 0.0) multi_distances<RT>(r, M.P, M.qT + p, sxT + r * kMT, M.wq, dd);
+                if (M.wv != 0.0) {
+                    double dv[kMT];
+#pragma unroll
+                    for (int tr = 0; tr < kMT; ++tr) dv[tr] = 0.0;
+                    multi_distances<RT>(r, M.P, M.vT + p, sxT, M.wv, dv);
+#pragma unroll
+                    for (int tr = 0; tr < kMT; ++tr) dd[tr] = __dadd_rn(dd[tr], dv[tr]);
+                }
+#pragma unroll
+                for (int tr = 0; tr < kMT; ++tr)
+                    if (dd[tr] < best[tr]) { best[tr] = dd[tr]; bi[tr] = p; }
+            }
+#pragma unroll
+            for (int tr = 0; tr < kMT; ++tr) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double od = __shfl_xor_sync(0xffffffffu, best[tr], off);
+                    const int op = __shfl_xor_sync(0xffffffffu, bi[tr], off);
+                    if (od < best[tr] || (od == best[tr] && op < bi[tr])) { best[tr] = od; bi[tr] = op; }
+                }
+                if (lane == 0) { red_d[tr][warp] = best[tr]; red_i[tr][warp] = bi[tr]; }
+            }
+            __syncthreads();
+            if (tid < kMT) {
+                double d = red_d[tid][0];
+                int p = red_i[tid][0];
+                for (int k = 1; k < kMThreads / 32; ++k) {
+                    const double od = red_d[tid][k];
+                    const int op = red_i[tid][k];
+                    if (od < d || (od == d && op < p)) { d = od; p = op; }
+                }
+                if (p == 0x7fffffff) p = 0;
+                sel[tid] = p;
+                if (idxo && tid < nt) idxo[(b0 + tid) * (long long)N + t] = p;
+            }
+            __syncthreads();
+            // ---- x+ = (A_i x + B_i u) + d_i : one thread per (trajectory, row), sequential dot in ascending k
+            for (int row = tid; row < kMT * n; row += kMThreads) {
+                const int tr = row / n, i = row - tr * n;
+                const long long p = sel[tr];
+                const double* Ap = M.A + (p * n + i) * n;
+                const double* Bp = M.B + (p * n + i) * m;
+                double ax = 0.0, bu = 0.0;
+                if ((n & 1) == 0) {
+                    for (int k = 0; k < n; k += 2) {
+                        const double2 a2 = *reinterpret_cast<const double2*>(Ap + k);
+                        ax = fma(a2.x, sxT[k * kMT + tr], ax);
+                        ax = fma(a2.y, sxT[(k + 1) * kMT + tr], ax);
+                    }
+                } else {
+                    for (int k = 0; k < n; ++k) ax = fma(Ap[k], sxT[k * kMT + tr], ax);
+                }
+                for (int k = 0; k < m; ++k) bu = fma(Bp[k], su[tr * m + k], bu);
+                sxn[row] = __dadd_rn(__dadd_rn(ax, bu), M.d[p * n + i]);
+            }
+            __syncthreads();
+            for (int e = tid; e < kMT * n; e += kMThreads) {
+                const int tr = e / n, i = e - tr * n;
+                sxT[i * kMT + tr] = sxn[e];
+                if (tr < nt) xo[((b0 + tr) * (long long)(N + 1) + t + 1) * n + i] = sxn[e];
+            }
+            __syncthreads();
+        }
+    }
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline long long bank_width(const TpwlDev& M) { return (long long)M.n * M.n + (long long)M.n * M.m + M.n; }
 
@@ -369,7 +541,13 @@ extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t
     const bool disc = (dt >= 0.0 && M.discr != SRCB200_DISCR_NONE);
     if (M.method == SRCB200_TPWL_NN) {
         const int grid = (int)(batch < 148 * 16 ? batch : 148 * 16);
-        if (!disc) {
+        if (!disc && M.r <= 128) {
+            const long long groups = (batch + kMT - 1) / kMT;
+            const int g2 = (int)(groups < 148 * 8 ? groups : 148 * 8);
+            const size_t smem = sizeof(double) * kMT * (2 * n + m);
+            if (M.r == 36) tpwl_rollout_nn_multi_kernel<36><<<g2, kMThreads, smem, st>>>(M, batch, N, x0, u, x, idx);
+            else           tpwl_rollout_nn_multi_kernel<0><<<g2, kMThreads, smem, st>>>(M, batch, N, x0, u, x, idx);
+        } else if (!disc) {
             const size_t smem = sizeof(double) * (2 * n + m);
             tpwl_rollout_nn_kernel<true><<<grid, kSel, smem, st>>>(M, batch, N, x0, u, dt, x, idx);
         } else {

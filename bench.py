@@ -254,7 +254,7 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
     batch, N = args.batch, args.horizon
     data, Hf = synth.tpwl_bank()
     params = {'tpwl_method': method, 'dist_weights': {'q': 1.0, 'v': 0.0}, 'beta_weighting': 25.0}
-    g = TPWLATV(data, params=params, Hf=Hf, discr_method='fe' if method == 'weighting' else 'be')
+    g = TPWLATV(data, params=params, Hf=Hf, discr_method='fe' if method == 'weighting' else 'zoh')
     if method == 'nn':
         g.pre_discretize(0.01)
     x0h, uh = synth.tpwl_rollout_batch(batch, N=N, seed=2 + rank)
@@ -308,7 +308,7 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "Diamond TPWL batched rollout (BASELINE configs[1]): %d trajectories x %d steps per GPU, "
-                                   "n=72 m=4 P=1000 r=36, method %s" % (batch, N, method), "batch_per_gpu": batch,
+                                   "n=72 m=4 P=1000 r=36, method %s (%s)" % (batch, N, method, "pre-discretised zoh bank" if method == "nn" else "fe per step"), "batch_per_gpu": batch,
                        "horizon": N, "l2": "256 MB buffer written between timed steps (untimed)"},
             "e2e": {"value": steps_total / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": int((x0h.size + uh.size) * 8),
                     "d2h_bytes_per_step": int(batch * (N + 1) * (n + 6) * 8)},

@@ -40,7 +40,7 @@ extern "C" {
 #define SRCB200_DISCR_FE   0
 #define SRCB200_DISCR_BE   1
 #define SRCB200_DISCR_BIL  2
-#define SRCB200_DISCR_ZOH  3   /* TPWL only, bank must be pre-discretised (srcb200_tpwl_prediscretize_zoh) */
+#define SRCB200_DISCR_ZOH  3   /* TPWL only: srcb200_zoh_batch on the bank (pre_discretize) or per evaluation */
 #define SRCB200_DISCR_NONE 4   /* model is already discrete: SSM discrete=True, TPWL pre-discretised bank */
 
 int         srcb200_abi_version(void);
@@ -152,6 +152,13 @@ int srcb200_tpwl_output_batch(const srcb200_tpwl_model* mdl, int64_t count, cons
 int srcb200_discretize_batch(int32_t n, int32_t m, int32_t discr_method, int64_t count, double dt,
                              const double* A_c, const double* B_c, const double* d_c, double* A_d, double* B_d,
                              double* d_d, void* stream);
+
+/* Zero-order-hold discretisation of a batch (sofacontrol/utils.py:302-335 zoh_affine: expm of the (n+m+1)^2 augmented
+ * matrix; TPWLATV.discretize_dynamics('zoh') / pre_discretize, tpwl.py:291-322).  Pade-13 scaling and squaring. */
+size_t srcb200_zoh_workspace(int32_t n, int32_t m, int64_t count);
+int srcb200_zoh_batch(int32_t n, int32_t m, int64_t count, double dt, const double* A_c, const double* B_c,
+                      const double* d_c, double* A_d, double* B_d, double* d_d, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * iLQR  (sofacontrol/lqr/ilqr.py:6-300, sofacontrol/lqr/config.py:1-31)

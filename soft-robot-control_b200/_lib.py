@@ -81,6 +81,9 @@ _SIGS = {
     "srcb200_tpwl_output_batch": (C.c_int, [C.POINTER(TpwlModel), C.c_int64, c_dp, c_dp, c_dp]),
     "srcb200_discretize_batch": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_double, c_dp, c_dp,
                                            c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "srcb200_zoh_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
+    "srcb200_zoh_batch": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                    c_dp, C.c_size_t, c_dp]),
     "srcb200_ilqr_workspace_bytes": (C.c_size_t, [C.c_int32, c_dp, C.POINTER(IlqrProblem)]),
     "srcb200_ilqr_solve_batch": (C.c_int, [C.c_int32, c_dp, C.POINTER(IlqrConfig), C.POINTER(IlqrProblem),
                                            C.POINTER(IlqrResult), c_dp, C.c_size_t, c_dp]),

@@ -2,6 +2,11 @@
 // blend + discretisation) and batched rollout.  Reference: sofacontrol/tpwl/tpwl.py (see include/srcb200.h).
 #include "tpwl.cuh"
 
+extern "C" size_t srcb200_zoh_workspace(int32_t n, int32_t m, int64_t count);
+extern "C" int srcb200_zoh_batch(int32_t n, int32_t m, int64_t count, double dt, const double* A_c, const double* B_c,
+                                 const double* d_c, double* A_d, double* B_d, double* d_d, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
 namespace srcb {
 
 int dgemm_device(int transA, long long M, long long N, long long K, double alpha, const double* A, long long lda,
@@ -19,8 +24,6 @@ int check_tpwl_model(const srcb200_tpwl_model* s) {
         return fail(SRCB200_E_METHOD, "tpwl method should be nn or weighting");               // tpwl.py:268
     if (s->discr_method < SRCB200_DISCR_FE || s->discr_method > SRCB200_DISCR_NONE)
         return fail(SRCB200_E_METHOD, "self.discr_method must be in [fe, be, bil, zoh]");     // tpwl.py:295
-    if (s->discr_method == SRCB200_DISCR_ZOH)
-        return fail(SRCB200_E_METHOD, "zoh is only available through a pre-discretised bank (discr_method NONE)");
     return 0;
 }
 
@@ -148,6 +151,14 @@ int discretize_launch(int n, int m, int method, long long count, double dt, cons
     }
     SRCB_LAUNCH_CHECK("discretize_kernel");
     return 0;
+}
+
+// fe / be / bil through discretize_kernel, zoh through the expm kernel (expm.cu) with caller workspace
+static int discretize_any(int n, int m, int method, long long count, double dt, double* A, double* B, double* d,
+                          void* zoh_ws, size_t zoh_ws_bytes, cudaStream_t st) {
+    if (method == SRCB200_DISCR_ZOH)
+        return srcb200_zoh_batch(n, m, count, dt, A, B, d, A, B, d, zoh_ws, zoh_ws_bytes, (void*)st);
+    return discretize_launch(n, m, method, count, dt, A, B, d, A, B, d, st);
 }
 
 // ---- affine step x+ = (A x + B u) + d for a batch with per-trajectory matrices (weighting mode) -----------------
@@ -418,7 +429,6 @@ tpwl_rollout_nn_multi_kernel(TpwlDev M, long long batch, int N, const double* __
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static inline long long bank_width(const TpwlDev& M) { return (long long)M.n * M.n + (long long)M.n * M.m + M.n; }
 
 }  // namespace srcb
 
@@ -482,8 +492,9 @@ extern "C" int srcb200_discretize_batch(int32_t n, int32_t m, int32_t discr_meth
 extern "C" size_t srcb200_tpwl_linearize_workspace(const srcb200_tpwl_model* mdl, int64_t count) {
     if (!mdl || count <= 0) return 0;
     TpwlDev M = to_dev(*mdl);
-    if (M.method == SRCB200_TPWL_NN) return align_up(sizeof(int32_t) * (size_t)count, 256);
-    return align_up(sizeof(double) * (size_t)count * M.P, 256) + align_up(sizeof(double) * (size_t)count * bank_width(M), 256);
+    const size_t z = (M.discr == SRCB200_DISCR_ZOH) ? align_up(srcb200_zoh_workspace(M.n, M.m, count), 256) : 0;
+    if (M.method == SRCB200_TPWL_NN) return align_up(sizeof(int32_t) * (size_t)count, 256) + z;
+    return align_up(sizeof(double) * (size_t)count * M.P, 256) + z;
 }
 
 extern "C" int srcb200_tpwl_linearize_batch(const srcb200_tpwl_model* mdl, int64_t count, const double* x, double dt,
@@ -514,7 +525,11 @@ extern "C" int srcb200_tpwl_linearize_batch(const srcb200_tpwl_model* mdl, int64
         if (int e = dgemm_device(0, count, (long long)n * m, M.P, 1.0, W, M.P, M.B, (long long)n * m, B, (long long)n * m, st)) return e;
         if (int e = dgemm_device(0, count, n, M.P, 1.0, W, M.P, M.d, n, d, n, st)) return e;
     }
-    if (disc) return discretize_launch(n, m, M.discr, count, dt, A, B, d, A, B, d, st);
+    if (disc) {
+        const size_t first = (M.method == SRCB200_TPWL_NN) ? align_up(sizeof(int32_t) * (size_t)count, 256)
+                                                           : align_up(sizeof(double) * (size_t)count * M.P, 256);
+        return discretize_any(n, m, M.discr, count, dt, A, B, d, (char*)workspace + first, workspace_bytes - first, st);
+    }
     return 0;
 }
 
@@ -523,8 +538,9 @@ extern "C" size_t srcb200_tpwl_rollout_workspace(const srcb200_tpwl_model* mdl, 
     if (!mdl || batch <= 0) return 0;
     TpwlDev M = to_dev(*mdl);
     if (M.method == SRCB200_TPWL_NN) return 256;
+    const size_t z = (M.discr == SRCB200_DISCR_ZOH) ? align_up(srcb200_zoh_workspace(M.n, M.m, batch), 256) : 0;
     return align_up(sizeof(double) * (size_t)batch * M.P, 256) + align_up(sizeof(double) * (size_t)batch * M.n * M.n, 256) +
-           align_up(sizeof(double) * (size_t)batch * M.n * M.m, 256) + align_up(sizeof(double) * (size_t)batch * M.n, 256);
+           align_up(sizeof(double) * (size_t)batch * M.n * M.m, 256) + align_up(sizeof(double) * (size_t)batch * M.n, 256) + z;
 }
 
 extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t batch, int32_t N, const double* x0,
@@ -541,6 +557,9 @@ extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t
     const bool disc = (dt >= 0.0 && M.discr != SRCB200_DISCR_NONE);
     if (M.method == SRCB200_TPWL_NN) {
         const int grid = (int)(batch < 148 * 16 ? batch : 148 * 16);
+        if (disc && M.discr == SRCB200_DISCR_ZOH)
+            return fail(SRCB200_E_METHOD, "nn rollout with zoh needs a pre-discretised bank: discretise the bank once "
+                                          "(srcb200_zoh_batch) and pass it with discr_method NONE");
         if (!disc && M.r <= 128) {
             const long long groups = (batch + kMT - 1) / kMT;
             const int g2 = (int)(groups < 148 * 8 ? groups : 148 * 8);
@@ -566,7 +585,9 @@ extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t
         double* W = (double*)wp;   wp += align_up(sizeof(double) * (size_t)batch * M.P, 256);
         double* Ab = (double*)wp;  wp += align_up(sizeof(double) * (size_t)batch * n * n, 256);
         double* Bb = (double*)wp;  wp += align_up(sizeof(double) * (size_t)batch * n * m, 256);
-        double* db = (double*)wp;
+        double* db = (double*)wp;  wp += align_up(sizeof(double) * (size_t)batch * n, 256);
+        void* zws = wp;
+        const size_t zws_bytes = workspace_bytes - (size_t)(wp - (char*)workspace);
         const long long xs = (long long)(N + 1) * n, us = (long long)N * m;
         SRCB_CUDA(cudaMemcpy2DAsync(x, sizeof(double) * xs, x0, sizeof(double) * n, sizeof(double) * n, batch,
                                     cudaMemcpyDeviceToDevice, st));
@@ -580,7 +601,7 @@ extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t
             if (int e = dgemm_device(0, batch, (long long)n * n, M.P, 1.0, W, M.P, M.A, (long long)n * n, Ab, (long long)n * n, st)) return e;
             if (int e = dgemm_device(0, batch, (long long)n * m, M.P, 1.0, W, M.P, M.B, (long long)n * m, Bb, (long long)n * m, st)) return e;
             if (int e = dgemm_device(0, batch, n, M.P, 1.0, W, M.P, M.d, n, db, n, st)) return e;
-            if (disc) if (int e = discretize_launch(n, m, M.discr, batch, dt, Ab, Bb, db, Ab, Bb, db, st)) return e;
+            if (disc) if (int e = discretize_any(n, m, M.discr, batch, dt, Ab, Bb, db, zws, zws_bytes, st)) return e;
             tpwl_step_kernel<<<grid, 128, 0, st>>>(n, m, batch, Ab, Bb, db, x + (long long)t * n, xs, u + (long long)t * m, us,
                                                    x + (long long)(t + 1) * n, xs);
             SRCB_LAUNCH_CHECK("tpwl_step_kernel");

@@ -224,7 +224,13 @@ class TPWL:
         """CUDA tensors x0 (Bt, n), u (Bt, N, m) -> x (Bt, N+1, n), z (Bt, N+1, n_z) or None [, idx (Bt, N)]."""
         torch = L.torch_mod()
         Bt, N = u.shape[0], u.shape[1]
-        h = self.device_model(dt)
+        if (self.tpwl_method == 'nn' and self.discr_method == 'zoh' and dt is not None and
+                not (self.pre_discretized_dt is not None and dt == self.pre_discretized_dt)):
+            # the reference runs expm on the selected entry at every step (tpwl.py:261-263); discretising the whole
+            # bank once for this dt gives the same matrices
+            h = self._zoh_bank_model(dt)
+        else:
+            h = self.device_model(dt)
         x = L.empty((Bt, N + 1, self.state_dim))
         z = L.empty((Bt, N + 1, h.nz)) if (want_z and h.nz > 0) else None
         idx = L.empty((Bt, N), torch.int32) if (want_idx and self.tpwl_method == 'nn') else None
@@ -233,6 +239,34 @@ class TPWL:
         L.check(L.lib().srcb200_tpwl_rollout_batch(h, Bt, N, L.ptr(x0), L.ptr(u), float(dt), L.ptr(x), L.ptr(z),
                                                    L.ptr(idx), L.ptr(ws), ws.numel() * 8, L.stream_ptr()))
         return (x, z, idx) if want_idx else (x, z)
+
+    def _discretize_bank_device(self, dt):
+        """(A_d, B_d, d_d) CUDA tensors of the whole bank for step dt with self.discr_method."""
+        bank = self._bank()
+        n, m = self.state_dim, self.input_dim
+        A, B, d = L.empty(bank['A'].shape), L.empty(bank['B'].shape), L.empty(bank['d'].shape)
+        if self.discr_method == 'zoh':
+            wsb = int(L.lib().srcb200_zoh_workspace(n, m, self.num_points))
+            ws = L.empty((wsb // 8 + 1,))
+            L.check(L.lib().srcb200_zoh_batch(n, m, self.num_points, float(dt), L.ptr(bank['A']), L.ptr(bank['B']),
+                                              L.ptr(bank['d']), L.ptr(A), L.ptr(B), L.ptr(d), L.ptr(ws),
+                                              ws.numel() * 8, L.stream_ptr()))
+        else:
+            L.check(L.lib().srcb200_discretize_batch(n, m, L.DISCR[self.discr_method], self.num_points, float(dt),
+                                                     L.ptr(bank['A']), L.ptr(bank['B']), L.ptr(bank['d']), L.ptr(A),
+                                                     L.ptr(B), L.ptr(d), L.stream_ptr()))
+        return A, B, d
+
+    def _zoh_bank_model(self, dt):
+        cache = getattr(self, '_zoh_cache', None)
+        if cache is None or cache[0] != dt:
+            cache = (dt, self._discretize_bank_device(dt))
+            self._zoh_cache = cache
+        h = self.device_model(continuous=True)
+        A, B, d = cache[1]
+        h.A, h.B, h.d = L.ptr(A), L.ptr(B), L.ptr(d)
+        h._keep = h._keep + (A, B, d)
+        return h
 
     def rollout(self, x0, u, dt):
         """tpwl.py:193-216.  x0 (n,) & u (N, m) -> x (N+1, n), z (N+1, n_z) or None; batched with a leading axis."""
@@ -267,9 +301,6 @@ class TPWLATV(TPWL):
         torch = L.torch_mod()
         cnt, n, m = x.shape[0], self.state_dim, self.input_dim
         h = self.device_model(dt)
-        if h.discr_method == L.DISCR['zoh']:
-            raise NotImplementedError("per-evaluation zoh is not available on the device: call pre_discretize(dt) "
-                                      "first (nn) -- the reference's own configs do (tpwl_config.py:38-55)")
         A, B, d = L.empty((cnt, n, n)), L.empty((cnt, n, m)), L.empty((cnt, n))
         idx = L.empty((cnt,), torch.int32) if self.tpwl_method == 'nn' else None
         wsb = L.lib().srcb200_tpwl_linearize_workspace(h, cnt)
@@ -295,8 +326,6 @@ class TPWLATV(TPWL):
         """tpwl.py:272-297 for one or a stack of (A_c, B_c, d_c); fe/be/bil run csrc/tpwl.cu discretize_kernel."""
         if self.discr_method not in ('fe', 'be', 'bil', 'zoh'):
             raise RuntimeError('self.discr_method must be in [fe, be, bil, zoh]')
-        if self.discr_method == 'zoh':
-            raise NotImplementedError("zoh discretisation (batched expm) is not built yet on the device")
         L.require_gpu()
         A_c = np.asarray(A_c, dtype=np.float64)
         single = (A_c.ndim == 2)
@@ -304,8 +333,14 @@ class TPWLATV(TPWL):
         A = L.to_dev(A_c.reshape(-1, n, n))
         B = L.to_dev(np.asarray(B_c, dtype=np.float64).reshape(-1, n, m))
         d = L.to_dev(np.asarray(d_c, dtype=np.float64).reshape(-1, n))
-        L.check(L.lib().srcb200_discretize_batch(n, m, L.DISCR[self.discr_method], A.shape[0], float(dt), L.ptr(A),
-                                                 L.ptr(B), L.ptr(d), L.ptr(A), L.ptr(B), L.ptr(d), L.stream_ptr()))
+        if self.discr_method == 'zoh':
+            wsb = int(L.lib().srcb200_zoh_workspace(n, m, A.shape[0]))
+            ws = L.empty((wsb // 8 + 1,))
+            L.check(L.lib().srcb200_zoh_batch(n, m, A.shape[0], float(dt), L.ptr(A), L.ptr(B), L.ptr(d), L.ptr(A),
+                                              L.ptr(B), L.ptr(d), L.ptr(ws), ws.numel() * 8, L.stream_ptr()))
+        else:
+            L.check(L.lib().srcb200_discretize_batch(n, m, L.DISCR[self.discr_method], A.shape[0], float(dt), L.ptr(A),
+                                                     L.ptr(B), L.ptr(d), L.ptr(A), L.ptr(B), L.ptr(d), L.stream_ptr()))
         res = (L.to_host(A), L.to_host(B), L.to_host(d))
         return tuple(r[0] for r in res) if single else res
 
@@ -315,14 +350,7 @@ class TPWLATV(TPWL):
             raise RuntimeError('tpwl method should be nn to pre-discretize')
         if self.discr_method not in ('fe', 'be', 'bil', 'zoh'):
             raise RuntimeError('self.discr_method must be in [fe, be, bil, zoh]')
-        if self.discr_method == 'zoh':
-            raise NotImplementedError("zoh pre-discretisation (batched expm) is not built yet on the device")
-        bank = self._bank()
-        n, m = self.state_dim, self.input_dim
-        A, B, d = L.empty(bank['A'].shape), L.empty(bank['B'].shape), L.empty(bank['d'].shape)
-        L.check(L.lib().srcb200_discretize_batch(n, m, L.DISCR[self.discr_method], self.num_points, float(dt),
-                                                 L.ptr(bank['A']), L.ptr(bank['B']), L.ptr(bank['d']), L.ptr(A),
-                                                 L.ptr(B), L.ptr(d), L.stream_ptr()))
+        A, B, d = self._discretize_bank_device(dt)
         self._dev_d = dict(A=A, B=B, d=d)
         self.A_d, self.B_d, self.d_d = L.to_host(A), L.to_host(B), L.to_host(d)
         self.pre_discretized_dt = dt

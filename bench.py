@@ -372,6 +372,53 @@ def run_ssm_rollout(args, rank, world, dev_index):
                          "note": "dense algorithmic flops (model contraction + discretisation + step) / event time, of measured cuBLAS DGEMM"}}
 
 
+def run_ssm_eval(args, rank, world, dev_index):
+    """Kernel (b): batched evaluation + linearisation, continuous Jacobians (A, d, H, c, z) of `count` states."""
+    import torch
+    import torch.distributed as dist
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200 import _lib as L
+    from sofacontrol_b200.SSM.ssm import SSMDynamics
+    count = args.batch * 1024
+    s = synth.trunk_ssm(8)
+    g = SSMDynamics(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
+    gen = torch.Generator(device="cuda").manual_seed(1 + rank)
+    x = torch.randn((count, 6), device="cuda", dtype=torch.float64, generator=gen)
+    u = torch.rand((count, 8), device="cuda", dtype=torch.float64, generator=gen) * 800
+    want = ('A', 'd', 'H', 'c', 'z')
+    for _ in range(args.warmup):
+        out = g._eval_device(x, u, -1.0, 'cont_raw', want)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(dev_index) as clk:
+        for s_, e_ in ev:
+            s_.record()
+            out = g._eval_device(x, u, -1.0, 'cont_raw', want)
+            e_.record()
+        torch.cuda.synchronize()
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt[0])
+    hbm, hsrc, fp64 = measured_peaks()
+    ach = count * 13944.0 / (t_dev / args.steps) / 1e12
+    byts = count * (14 + 36 + 6 + 36 + 6 + 6) * 8
+    return {"metric": "ssm_eval_linearize_states_per_sec", "value": count * world * args.steps / t_dev, "unit": "states/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Trunk SSM batched evaluation + linearisation: %d states per GPU, outputs A_c, d_c, H, c, z "
+                                   "(inputs %.0f MB + outputs %.0f MB per launch: larger than L2)" % (count, count * 14 * 8 / 1e6, byts / 1e6 - count * 14 * 8 / 1e6)},
+            "e2e": None, "gpu_launches": args.steps, "clocks": clk.summary(),
+            "roofline": {"kernel": "ssm_eval_dmma_kernel<8>", "bound": "tensor", "achieved": ach, "peak": fp64, "unit": "TFLOP/s",
+                         "frac": ach / fp64, "traffic": None, "hbm_gbs": byts / (t_dev / args.steps) / 1e9,
+                         "note": "13944 algorithmic flop per state (dense count, SURVEY 8d); 42 DMMA m8n8k4 per state execute "
+                                 "21504 flop (padding 16x84x8); peak = measured cuBLAS DGEMM"}}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU port on the host cores, same workload/metric (bounded sample)."""
     t_all = []
@@ -396,7 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ilqr_trunk_ssm",
-                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting", "ssm_rollout"])
+                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting", "ssm_rollout", "ssm_eval"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--cpu-per-core", type=int, default=2)
@@ -424,6 +471,8 @@ def main():
         res = run_ilqr(args, rank, world, local)
     elif args.workload == "ssm_rollout":
         res = run_ssm_rollout(args, rank, world, local)
+    elif args.workload == "ssm_eval":
+        res = run_ssm_eval(args, rank, world, local)
     else:
         res = run_tpwl_rollout(args, rank, world, local, "nn" if args.workload.endswith("nn") else "weighting")
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "ilqr_trunk_ssm":

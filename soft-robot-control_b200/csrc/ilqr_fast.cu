@@ -988,7 +988,245 @@ ssm_rollout_fast_kernel(const __grid_constant__ SsmDev Mdl, long long batch, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Batched evaluation + linearisation on the FP64 tensor pipe (kernel "b" of BASELINE.json): per state ONE dense
+// contraction   [r_coeff; w_coeff] (16 x 84, zero padded)  x  [phi | dphi/dx_1..6 | 0] (84 x 8)   = 42 DMMA tiles,
+// coefficient fragments resident in registers for the whole launch, the monomial / derivative fragments generated
+// on the fly from x.  Output tile: rows 0..5 (f | A_c), rows 8..13 (z | H).  A warp walks states grid-stride.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int EV_WARPS = 4;
+constexpr int EV_KS = 21;   // k4 steps (84 / 4)
+
+template <int M>
+__global__ void __launch_bounds__(EV_WARPS * 32, 4)
+ssm_eval_dmma_kernel(const __grid_constant__ SsmDev Mdl, long long count, const double* __restrict__ xg,
+                     const double* __restrict__ ug, double dt, double* __restrict__ Ao, double* __restrict__ Bo,
+                     double* __restrict__ dout, double* __restrict__ Ho, double* __restrict__ co, double* __restrict__ zo) {
+    __shared__ double s_xe[EV_WARPS][8];
+    __shared__ double s_u[EV_WARPS][8];
+    __shared__ double s_br[6 * 8];
+    __shared__ __align__(16) double s_tiles[EV_WARPS][6 * TILE];   // A_c, A_d, inv(A_c), sep, B_d, W0 (be / bil only)
+    __shared__ double s_dc[EV_WARPS][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const int nf = Mdl.nfeat, discr = Mdl.discr;
+    for (int e = threadIdx.x; e < 6 * M; e += blockDim.x) s_br[e] = Mdl.B[e];
+    // ---- coefficient fragments a[mt][s][lane] = C_mt[g][4 s + q], shared by the warps of the CTA (conflict-free LDS)
+    __shared__ double s_af[2][EV_KS][32];
+    for (int e = threadIdx.x; e < EV_KS * 32; e += blockDim.x) {
+        const int s = e >> 5, l = e & 31, gg = l >> 2, k = 4 * s + (l & 3);
+        const bool ok = (gg < 6) && (k < nf);
+        s_af[0][s][l] = ok ? Mdl.r[gg * nf + k] : 0.0;
+        s_af[1][s][l] = ok ? Mdl.w[gg * nf + k] : 0.0;
+    }
+    // ---- recipes of the B fragment: entry(k = 4 s + q, col = g) = mult * xe[a] * xe[b] * xe[c]   (xe[7] = 1)
+    unsigned rec[EV_KS];
+#pragma unroll
+    for (int s = 0; s < EV_KS; ++s) {
+        const int k = 4 * s + q;
+        unsigned r = 0;   // mult = 0
+        if (k < nf && g < 7) {
+            int idx[3];
+            for (int t = 0; t < 3; ++t) { const int v = Mdl.mono[k * SRCB200_SSM_MAX_ORDER + t]; idx[t] = (v == 0xFF) ? 7 : v; }
+            if (g == 0) {
+                r = (unsigned)idx[0] | ((unsigned)idx[1] << 3) | ((unsigned)idx[2] << 6) | (1u << 9);
+            } else {
+                const int var = g - 1;
+                int mult = 0, rest[3] = {7, 7, 7}, nr = 0;
+                bool removed = false;
+                for (int t = 0; t < 3; ++t) {
+                    if (idx[t] == var) ++mult;
+                    if (idx[t] == var && !removed) { removed = true; continue; }
+                    rest[nr++] = idx[t];
+                }
+                if (mult > 0) r = (unsigned)rest[0] | ((unsigned)rest[1] << 3) | ((unsigned)rest[2] << 6) | ((unsigned)mult << 9);
+            }
+        }
+        rec[s] = r;
+    }
+    __syncthreads();
+    double* xe = s_xe[warp];
+    double* su = s_u[warp];
+    double* AC = s_tiles[warp];          double* AD = AC + TILE;       double* IA = AC + 2 * TILE;
+    double* SP = AC + 3 * TILE;          double* W0 = AC + 5 * TILE;
+    double* DC = s_dc[warp];
+    const bool want_dyn = (Ao || Bo || dout);
+    const bool need_inv = want_dyn && dt >= 0.0 && (discr == SRCB200_DISCR_BE || discr == SRCB200_DISCR_BIL);
+    for (int t = 0; t < 6; ++t) zero_tile(AC + t * TILE, lane);
+    const long long nwarps = (long long)gridDim.x * EV_WARPS;
+    const long long st0 = (long long)blockIdx.x * EV_WARPS + warp;
+    double px = (st0 < count && lane < 6) ? xg[st0 * 6 + lane] : 0.0;            // state of the next iteration, prefetched
+    double pu = (st0 < count && ug && lane < M) ? ug[st0 * M + lane] : 0.0;
+    for (long long st = st0; st < count; st += nwarps) {
+        asm volatile("" ::: "memory");   // keep the coefficient fragments in shared memory (no hoisting into registers)
+        if (lane < 8) {
+            xe[lane] = lane < 6 ? px : (lane == 7 ? 1.0 : 0.0);
+            su[lane] = pu;
+        }
+        {
+            const long long nx = st + nwarps;
+            px = (nx < count && lane < 6) ? xg[nx * 6 + lane] : 0.0;
+            pu = (nx < count && ug && lane < M) ? ug[nx * M + lane] : 0.0;
+        }
+        __syncwarp();
+        // three independent accumulation chains per output tile (the DMMA latency would otherwise serialise the
+        // 21 k-steps), summed at the end
+        Frag p0[3] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}, p1[3] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int s = 0; s < EV_KS; ++s) {
+            const unsigned r = rec[s];
+            double b = xe[r & 7];
+            b = __dmul_rn(b, xe[(r >> 3) & 7]);
+            b = __dmul_rn(b, xe[(r >> 6) & 7]);
+            b = __dmul_rn(b, (double)(r >> 9));
+            dmma(p0[s % 3], s_af[0][s][lane], b);
+            dmma(p1[s % 3], s_af[1][s][lane], b);
+        }
+        Frag c0{__dadd_rn(__dadd_rn(p0[0].c0, p0[1].c0), p0[2].c0), __dadd_rn(__dadd_rn(p0[0].c1, p0[1].c1), p0[2].c1)};
+        Frag c1{__dadd_rn(__dadd_rn(p1[0].c0, p1[1].c0), p1[2].c0), __dadd_rn(__dadd_rn(p1[0].c1, p1[1].c1), p1[2].c1)};
+        // ---- epilogue.  lane (g, q) holds columns 2q, 2q+1 of row g: col 0 = value, col 1 + j = d/dx_j
+        // observation outputs
+        if (g < 6) {
+            if (Ho) {
+                if (q == 0) Ho[st * 36 + g * 6 + 0] = c1.c1;
+                else {
+                    Ho[st * 36 + g * 6 + 2 * q - 1] = c1.c0;
+                    if (q < 3) Ho[st * 36 + g * 6 + 2 * q] = c1.c1;
+                }
+            }
+        }
+        if (zo || co) {
+            // H x : partial sums inside the quad
+            double hx = 0.0;
+            if (q == 0) hx = __dmul_rn(c1.c1, xe[0]);
+            else { hx = __dmul_rn(c1.c0, xe[2 * q - 1]); if (q < 3) hx = fma(c1.c1, xe[2 * q], hx); }
+            hx += __shfl_xor_sync(FULL, hx, 1);
+            hx += __shfl_xor_sync(FULL, hx, 2);
+            if (g < 6 && q == 0) {
+                if (zo) zo[st * 6 + g] = __dadd_rn(c1.c0, Mdl.zref[g]);
+                if (co) co[st * 6 + g] = __dsub_rn(c1.c0, hx);
+            }
+        }
+        if (want_dyn) {
+            // f = r phi + B u ; d_c = (f - A_c x) - B u : quad-level partial sums
+            double ax = 0.0, bu = 0.0;
+            if (q == 0) ax = __dmul_rn(c0.c1, xe[0]);
+            else { ax = __dmul_rn(c0.c0, xe[2 * q - 1]); if (q < 3) ax = fma(c0.c1, xe[2 * q], ax); }
+            if (g < 6) {
+#pragma unroll
+                for (int jj = 0; jj < M / 4; ++jj) bu = fma(s_br[g * M + q * (M / 4) + jj], su[q * (M / 4) + jj], bu);
+            }
+            ax += __shfl_xor_sync(FULL, ax, 1);  ax += __shfl_xor_sync(FULL, ax, 2);
+            bu += __shfl_xor_sync(FULL, bu, 1);  bu += __shfl_xor_sync(FULL, bu, 2);
+            const double fpoly = __shfl_sync(FULL, c0.c0, lane & ~3);     // column 0 lives in lane q = 0 of the quad
+            const double dc = __dsub_rn(__dsub_rn(__dadd_rn(fpoly, bu), ax), bu);
+            const bool cont = (dt < 0.0) || discr == SRCB200_DISCR_NONE;
+            if (cont || discr == SRCB200_DISCR_FE) {
+                const double sc = cont ? 1.0 : dt;
+                if (g < 6) {
+                    // A (continuous, or I + dt A_c), straight from the accumulators
+                    auto put = [&](int col, double v) {
+                        double o = cont ? v : __dmul_rn(dt, v);
+                        if (!cont && col == g) o = __dadd_rn(1.0, o);
+                        if (Ao) Ao[st * 36 + g * 6 + col] = o;
+                    };
+                    if (q == 0) put(0, c0.c1);
+                    else { put(2 * q - 1, c0.c0); if (q < 3) put(2 * q, c0.c1); }
+                    if (Bo) {
+#pragma unroll
+                        for (int jj = 0; jj < M / 4; ++jj) {
+                            const int col = q * (M / 4) + jj;
+                            Bo[st * 6 * M + g * M + col] = cont ? s_br[g * M + col] : __dmul_rn(sc, s_br[g * M + col]);
+                        }
+                    }
+                    if (dout && q == 0) dout[st * 6 + g] = cont ? dc : __dmul_rn(dt, dc);
+                }
+            } else if (need_inv) {
+                // be / bil: A_c to its tile, the two 6x6 inverses by the shuffle sweep, products on the tensor pipe
+                if (g < 6) {
+                    if (q == 0) AC[g * LD + 0] = c0.c1;
+                    else { AC[g * LD + 2 * q - 1] = c0.c0; if (q < 3) AC[g * LD + 2 * q] = c0.c1; }
+                    if (q == 0) DC[g] = dc;
+                }
+                __syncwarp();
+                const double h = (discr == SRCB200_DISCR_BE) ? dt : 0.5 * dt;
+                const int hm = lane >> 4, j = lane & 15;
+                double col[6];
+#pragma unroll
+                for (int r2 = 0; r2 < 6; ++r2) {
+                    double v = 0.0;
+                    if (j < 6) {
+                        const double av = AC[r2 * LD + j];
+                        v = hm ? av : __dsub_rn(r2 == j ? 1.0 : 0.0, __dmul_rn(h, av));
+                    } else if (j < 12) {
+                        v = (r2 == j - 6) ? 1.0 : 0.0;
+                    }
+                    col[r2] = v;
+                }
+                gj6_pair(col, lane, hm ? IA : (discr == SRCB200_DISCR_BE ? AD : W0));
+                __syncwarp();
+                if (discr == SRCB200_DISCR_BIL) {
+                    Frag f{0.0, 0.0};
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        const int kk = 4 * s2 + q;
+                        const double av = (g < 6 && kk < 6) ? __dadd_rn(g == kk ? 1.0 : 0.0, __dmul_rn(h, AC[g * LD + kk])) : 0.0;
+                        dmma(f, av, W0[kk * LD + g]);
+                    }
+                    store_frag(AD, f, g, q);
+                    __syncwarp();
+                }
+                Frag sp{0.0, 0.0};
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int kk = 4 * s2 + q;
+                    const double bv = (kk < 6 && g < 6) ? __dsub_rn(AD[kk * LD + g], kk == g ? 1.0 : 0.0) : 0.0;
+                    dmma(sp, IA[g * LD + kk], bv);
+                }
+                store_frag(SP, sp, g, q);
+                __syncwarp();
+                if (Ao) {
+                    for (int e2 = lane; e2 < 36; e2 += 32) Ao[st * 36 + e2] = AD[(e2 / 6) * LD + e2 % 6];
+                }
+                if (Bo) {
+                    for (int e2 = lane; e2 < 6 * M; e2 += 32) {
+                        const int i = e2 / M, jj = e2 % M;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int kk = 0; kk < 6; ++kk) acc = fma(SP[i * LD + kk], s_br[kk * M + jj], acc);
+                        Bo[st * 6 * M + e2] = acc;
+                    }
+                }
+                if (dout && lane < 6) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < 6; ++kk) acc = fma(SP[lane * LD + kk], DC[kk], acc);
+                    dout[st * 6 + lane] = acc;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace fast
+
+int ssm_eval_dmma_launch(const SsmDev& M, long long count, const double* x, const double* u, double dt, double* A,
+                         double* B, double* d, double* H, double* c, double* z, cudaStream_t st, bool* handled) {
+    *handled = false;
+    const char* env = getenv("SRCB200_ILQR_GENERIC");
+    if (env && env[0] == '1') return 0;
+    if (!(M.n == 6 && M.nz == 6 && M.order == 3 && M.nfeat == fast::NFEAT && (M.m == 4 || M.m == 8))) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ctas = (count + fast::EV_WARPS - 1) / fast::EV_WARPS;
+    const int grid = (int)(ctas < 5LL * sms ? ctas : 5LL * sms);
+    if (M.m == 8) fast::ssm_eval_dmma_kernel<8><<<grid, fast::EV_WARPS * 32, 0, st>>>(M, count, x, u, dt, A, B, d, H, c, z);
+    else          fast::ssm_eval_dmma_kernel<4><<<grid, fast::EV_WARPS * 32, 0, st>>>(M, count, x, u, dt, A, B, d, H, c, z);
+    SRCB_LAUNCH_CHECK("ssm_eval_dmma_kernel");
+    *handled = true;
+    return 0;
+}
 
 // Rollout dispatch (called from ssm.cu): returns handled = true when the specialised kernel ran.
 int ssm_rollout_fast_launch(const SsmDev& M, long long batch, int N, const double* x0, const double* u, double dt,

@@ -7,6 +7,9 @@ namespace srcb {
 int ssm_rollout_fast_launch(const SsmDev& M, long long batch, int N, const double* x0, const double* u, double dt,
                             double* x, double* z, cudaStream_t st, bool* handled);   // ilqr_fast.cu
 
+int ssm_eval_dmma_launch(const SsmDev& M, long long count, const double* x, const double* u, double dt, double* A,
+                         double* B, double* d, double* H, double* c, double* z, cudaStream_t st, bool* handled);   // ilqr_fast.cu
+
 int check_ssm_model(const srcb200_ssm_model* s) {
     if (!s) return fail(SRCB200_E_NULL, "ssm model is NULL");
     if (s->n < 1 || s->n > SRCB200_SSM_MAX_N || s->m < 1 || s->m > SRCB200_SSM_MAX_M ||
@@ -158,6 +161,11 @@ extern "C" int srcb200_ssm_eval_linearize_batch(const srcb200_ssm_model* mdl, in
     if (!x) return fail(SRCB200_E_NULL, "x is NULL");
     if ((A || B || d) && !u) return fail(SRCB200_E_NULL, "u is NULL (Need to supply current input)");
     SsmDev M = to_dev(*mdl);
+    {   // Trunk / Diamond shape: dense contraction on the FP64 tensor pipe (DMMA)
+        bool handled = false;
+        if (int e = ssm_eval_dmma_launch(M, count, x, u, dt, A, B, d, H, c, z, (cudaStream_t)stream, &handled)) return e;
+        if (handled) return 0;
+    }
     const int n = M.n, m = M.m, nz = M.nz;
     const size_t smem = sizeof(double) * (n + m + n * n + n * m + n + 2 * nz + nz * n + ssm_eval_scratch_doubles(n, m, M.nfeat));
     SRCB_CUDA(cudaFuncSetAttribute(ssm_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

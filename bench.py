@@ -419,6 +419,55 @@ def run_ssm_eval(args, rank, world, dev_index):
                                  "21504 flop (padding 16x84x8); peak = measured cuBLAS DGEMM"}}
 
 
+def run_pod_gram(args, rank, world, dev_index):
+    """Kernel (d): POD Gram X^T X with the rows (DOFs) of X sharded across ranks + ONE NCCL all-reduce of G."""
+    import torch
+    import torch.distributed as dist
+    from sofacontrol_b200.mor import pod
+    from sofacontrol_b200 import parallel
+    nf_local, ns = 131072, 8192
+    gen = torch.Generator(device="cuda").manual_seed(5 + rank)
+    X = torch.randn((nf_local, ns), device="cuda", dtype=torch.float64, generator=gen)
+    G = torch.empty((ns, ns), device="cuda", dtype=torch.float64)
+    for _ in range(max(1, args.warmup - 1)):
+        pod.gram_device(X, G)
+        parallel.allreduce_sum_(G)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(dev_index) as clk:
+        for s_, m_, e_ in ev:
+            s_.record()
+            pod.gram_device(X, G)
+            m_.record()
+            parallel.allreduce_sum_(G)
+            e_.record()
+        torch.cuda.synchronize()
+    t_gram = sum(a.elapsed_time(b) for a, b, _ in ev) * 1e-3
+    t_all = sum(a.elapsed_time(c) for a, _, c in ev) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_gram, t_all], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_gram, t_all = float(tt[0]), float(tt[1])
+    hbm, hsrc, fp64 = measured_peaks()
+    fl = 2.0 * nf_local * ns * ns
+    ach = fl / (t_gram / args.steps) / 1e12
+    return {"metric": "pod_gram_tflops", "value": world * fl * args.steps / t_all / 1e12, "unit": "TFLOP/s (algorithmic, incl. all-reduce)",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "POD snapshot Gram (BASELINE configs[4] per-GPU slice, reduced): X_g %d x %d FP64 per GPU (%.1f GB), "
+                                   "G = sum_g X_g^T X_g, one all-reduce of %d x %d" % (nf_local, ns, nf_local * ns * 8 / 1e9, ns, ns),
+                       "allreduce_ms": 1e3 * (t_all - t_gram) / args.steps},
+            "e2e": None, "gpu_launches": args.steps, "clocks": clk.summary(),
+            "roofline": {"kernel": "dgemm_kernel<true,true,true> (SYRK)", "bound": "tensor", "achieved": ach, "peak": fp64,
+                         "unit": "TFLOP/s", "frac": ach / fp64, "traffic": None,
+                         "note": "algorithmic 2 nf ns^2 flop; the SYRK kernel executes only the upper tiles (half), so frac can exceed 1; "
+                                 "peak = measured cuBLAS DGEMM"}}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU port on the host cores, same workload/metric (bounded sample)."""
     t_all = []
@@ -443,7 +492,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ilqr_trunk_ssm",
-                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting", "ssm_rollout", "ssm_eval"])
+                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting", "ssm_rollout", "ssm_eval", "pod_gram"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--cpu-per-core", type=int, default=2)
@@ -473,6 +522,8 @@ def main():
         res = run_ssm_rollout(args, rank, world, local)
     elif args.workload == "ssm_eval":
         res = run_ssm_eval(args, rank, world, local)
+    elif args.workload == "pod_gram":
+        res = run_pod_gram(args, rank, world, local)
     else:
         res = run_tpwl_rollout(args, rank, world, local, "nn" if args.workload.endswith("nn") else "weighting")
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "ilqr_trunk_ssm":

@@ -27,7 +27,7 @@ constexpr int LD = 12;            // tile row stride (doubles): A-/B-fragment lo
 constexpr int TILE = 8 * LD;
 constexpr int WARPS = 8;          // problems in flight per CTA (2 CTAs per SM; 20-24 warps at 96/80 registers measured slower)
 constexpr int NJ = 28;            // terms per partial dot
-constexpr int NPD = 128;          // partial-dot slots: 4 rounds x 32 lanes (108 used)
+constexpr int NPD = 120;          // partial-dot slots: 4 rounds x 32 lanes (108 used; lanes >= 24 of round 3 read zeros)
 constexpr int TS = 30;            // table row stride (doubles)
 constexpr int NFEAT = 83;
 constexpr unsigned FULL = 0xffffffffu;
@@ -53,8 +53,8 @@ constexpr int W_DX = 136;                       // x_t - x_prev_t (6)
 constexpr int W_QE = 144;
 constexpr int W_RDU = 152;
 constexpr int W_TILES = 160;
-constexpr int NTILES = 9;
-constexpr int W_SIZE = W_TILES + NTILES * TILE; // 1024 doubles = 8 KB per warp
+constexpr int NTILES = 11;
+constexpr int W_SIZE = W_TILES + NTILES * TILE; // 1216 doubles = 9.5 KB per warp
 constexpr size_t SMEM_BYTES = sizeof(double) * (SH_END + WARPS * W_SIZE);
 
 struct Frag { double c0, c1; };
@@ -194,7 +194,7 @@ __device__ __forceinline__ double ssm_eval_fast(const Ctx c, const Scatter sc, d
     const double* t0 = T + lane * TS;
     const double* t1 = T + (32 + lane) * TS;
     const double* t2 = T + (64 + lane) * TS;
-    const double* t3 = T + (96 + lane) * TS;
+    const double* t3 = T + (96 + (lane < 24 ? lane : 23 - 12)) * TS;   // lanes >= 24 have no round-3 slot: any row x zero operand
     const double* op3 = PHI + (lane < 12 ? 28 : 56);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;   // even / odd terms
 #pragma unroll
@@ -228,35 +228,42 @@ __device__ __forceinline__ double ssm_eval_fast(const Ctx c, const Scatter sc, d
 // (tile, LD) for each half.  Zero pivots produce inf/nan exactly like the singular case would.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gj6_pair(double (&col)[6], int lane, double* __restrict__ dst) {
+    // rows are exchanged physically (static register indices): at step c only rows c..5 are pivot candidates, the
+    // pivot row / pivot value / eliminations need no select chains, and the right half ends up as the inverse.
     const int j = lane & 15;
-    unsigned used = 0, cmap = 0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
         const int src = (lane & 16) | c;
         double cc[6];
 #pragma unroll
         for (int r = 0; r < 6; ++r) cc[r] = __shfl_sync(FULL, col[r], src);
-        double best = -1.0;
-        int p = 0;
+        // partial pivoting: first maximal |a_rc|, r >= c
+        double best = fabs(cc[c]);
+        int p = c;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
+        for (int r = c + 1; r < 6; ++r) {
             const double av = fabs(cc[r]);
-            const bool take = !((used >> r) & 1u) && (av > best);
+            const bool take = av > best;
             best = take ? av : best;
             p = take ? r : p;
         }
-        used |= 1u << p;
-        cmap |= (unsigned)c << (4 * p);
-        double piv = cc[0], pv = col[0];
 #pragma unroll
-        for (int r = 1; r < 6; ++r) { piv = (p == r) ? cc[r] : piv; pv = (p == r) ? col[r] : pv; }
-        const double pc = __dmul_rn(pv, __drcp_rn(piv));
+        for (int r = c + 1; r < 6; ++r) {
+            if (p == r) {
+                const double t0 = col[c]; col[c] = col[r]; col[r] = t0;
+                const double t1 = cc[c];  cc[c] = cc[r];   cc[r] = t1;
+            }
+        }
+        const double pc = __dmul_rn(col[c], __drcp_rn(cc[c]));
+        col[c] = pc;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) col[r] = (p == r) ? pc : fma(-cc[r], pc, col[r]);
+        for (int r = 0; r < 6; ++r) {
+            if (r != c) col[r] = fma(-cc[r], pc, col[r]);
+        }
     }
     if (j >= 6 && j < 12) {
 #pragma unroll
-        for (int r = 0; r < 6; ++r) dst[((cmap >> (4 * r)) & 7u) * LD + (j - 6)] = col[r];
+        for (int r = 0; r < 6; ++r) dst[r * LD + (j - 6)] = col[r];
     }
 }
 
@@ -543,21 +550,59 @@ struct BwdResult { double rho, drho; int restarts; int give_up; };
         pup = ((tt) == 0) ? (ulast ? ulast[lane & (M - 1)] : 0.0) : rc.u[((tt) - 1) * M + (lane & (M - 1))]; \
     } while (0)
 
+// Solve Q_uu~ X = (Q_ux~ | Q_u) by an un-pivoted Gauss-Jordan sweep on [Q_uu~ | rhs] (one column per lane, rows in
+// registers) and return the PD verdict from the pivots.  X replaces the explicit inv(Q_uu~) @ rhs of ilqr.py:289-292
+// (same elimination, the product with the identity block is skipped).  Writes -(X) = (K | k) into `out`.
+template <int M>
+__device__ __forceinline__ bool gj_solve_spd(const double* __restrict__ quut, const double* __restrict__ rhs,
+                                             double* __restrict__ out, int lane) {
+    double col[M];
+    const int j = lane;
+#pragma unroll
+    for (int r = 0; r < M; ++r) col[r] = (j < M) ? quut[r * LD + j] : ((j < M + 7) ? rhs[r * LD + (j - M)] : 0.0);
+    bool pd = true;
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+        double cc[M];
+#pragma unroll
+        for (int r = 0; r < M; ++r) cc[r] = __shfl_sync(FULL, col[r], c);
+        const double piv = cc[c];
+        pd = pd && (piv > 0.0) && !isinf(piv);
+        const double pc = __dmul_rn(col[c], __drcp_rn(piv));
+#pragma unroll
+        for (int r = 0; r < M; ++r) col[r] = (r == c) ? pc : fma(-cc[r], pc, col[r]);
+    }
+    if (j >= M && j < M + 7) {
+#pragma unroll
+        for (int r = 0; r < M; ++r) out[r * LD + (j - M)] = -col[r];
+#pragma unroll
+        for (int r = M; r < 8; ++r) out[r * LD + (j - M)] = 0.0;      // K rows beyond m stay zero in the 8 x 8 tile
+    }
+    return pd;
+}
+
 template <int M>
 __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const Rec rc, const double* __restrict__ ulast,
                                            double* __restrict__ Kout, double* __restrict__ kout, double* __restrict__ ab,
                                            double rho, double drho) {
     const int lane = c.lane, g = c.g, q = c.q, N = a.N;
     double* ws = CTX_WS(c);
-    double* P = ws + W_TILES + 0 * TILE;     // (P | p)
+    // tiles.  One backward step is five dependency levels separated by one __syncwarp each; within a level all
+    // products are independent, so their fragment loads and DMMAs overlap.
+    double* P = ws + W_TILES + 0 * TILE;     // (P | p); between levels 2 and 5 it holds the right-hand side (Q_ux~ | Q_u)
     double* A = ws + W_TILES + 1 * TILE;     // A_t with A[6][6] = 1
     double* B = ws + W_TILES + 2 * TILE;     // B_t
-    double* H = ws + W_TILES + 3 * TILE;     // (H | e), then B^T P, B^T(P+rho I), K^T Q_uu
-    double* W = ws + W_TILES + 4 * TILE;     // H^T Q, then A^T P, then (Q_ux~ | Q_u)
-    double* QUU = ws + W_TILES + 5 * TILE;
-    double* QUX = ws + W_TILES + 6 * TILE;   // (Q_ux | Q_u)
-    double* INV = ws + W_TILES + 7 * TILE;
-    double* KT = ws + W_TILES + 8 * TILE;    // (K | k)
+    double* H = ws + W_TILES + 3 * TILE;     // (H_t | e_t)
+    double* W = ws + W_TILES + 4 * TILE;     // level 1: (H|e)^T Q ; level 3..5: (K | k)
+    double* ATP = ws + W_TILES + 5 * TILE;   // level 1: A'^T (P|p) ; level 4..5: K^T Q_uu
+    double* BTP = ws + W_TILES + 6 * TILE;   // B^T (P|p)
+    double* BTPR = ws + W_TILES + 7 * TILE;  // B^T (P + rho I)
+    double* QUU = ws + W_TILES + 8 * TILE;
+    double* QUX = ws + W_TILES + 9 * TILE;   // (Q_ux | Q_u)
+    double* QT = ws + W_TILES + 10 * TILE;   // Q_uu~
+    double* RHS = P;
+    double* KT = W;
+    double* KQ = ATP;
     double* CU = ws + W_DC;
     double* DU = ws + W_DD;
     const double* Qt = CTX_SH + SH_Q;  const double* Rt = CTX_SH + SH_R;  const double* Qft = CTX_SH + SH_QF;
@@ -566,6 +611,7 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
     const bool inc = cf.include_input_var_constraint != 0;
     const int bo0 = (lane / M) * LD + lane % M;
     const int bo1 = ((32 + lane) / M) * LD + (32 + lane) % M;
+    const int ko0 = (lane / 6) * LD + lane % 6, ko1 = ((32 + lane) / 6) * LD + (32 + lane) % 6;   // K elements lane, 32+lane
     int restarts = 0;
     int give_up = 0;
     double pa0, pa1, ph0, ph1, pb0, pb1, pe, pu, pup;   // record of the next step to process, in registers
@@ -579,23 +625,23 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
         if (lane < 6) H[lane * LD + 6] = rc.e[N * 6 + lane];
         LOAD_STEP(N - 1);
         __syncwarp();
+        Frag pf{0.0, 0.0};
         {
             Frag f{0.0, 0.0};
             mma88<true, false>(f, H, Qft, g, q);
             store_frag(W, f, g, q);
             __syncwarp();
-            Frag p{0.0, 0.0};
-            mma88<false, false>(p, W, H, g, q);
-            if (g >= 6) { p.c0 = 0.0; p.c1 = 0.0; }
-            if (q == 3) p.c1 = 0.0;
-            store_frag(P, p, g, q);
+            mma88<false, false>(pf, W, H, g, q);
+            if (g >= 6) { pf.c0 = 0.0; pf.c1 = 0.0; }
+            if (q == 3) pf.c1 = 0.0;
+            store_frag(P, pf, g, q);
         }
         if (lane == 0) A[6 * LD + 6] = 1.0;
         __syncwarp();
 
         bool ok = true;
         for (int t = N - 1; t >= 0; --t) {
-            // ---- stage A_t, B_t, (H_t | e_t), du from the prefetched registers; fetch step t-1
+            // ---- level 0: stage A_t, B_t, (H_t | e_t), du from the prefetched registers; fetch step t-1
             A[c.off0] = pa0;
             H[c.off0] = ph0;
             if (lane < 4) { A[c.off1] = pa1; H[c.off1] = ph1; }
@@ -605,101 +651,88 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
             if (lane < M) DU[lane] = inc ? __dsub_rn(pu, pup) : pu;
             if (t > 0) LOAD_STEP(t - 1);
             __syncwarp();
-            if (lane >= 8 && lane < 8 + M) {
-                const int i = lane - 8;
-                double acc = 0.0;
+            // ---- level 1: W = (H|e)^T Q, A'^T (P|p), B^T (P|p), B^T (P + rho I), c_u = R du
+            {
+                Frag w{0.0, 0.0}, atp{0.0, 0.0}, btp{0.0, 0.0}, btpr{0.0, 0.0};
+                mma88<true, false>(w, H, Qt, g, q);
+                mma88<true, false>(atp, A, P, g, q);
+                mma88<true, false>(btp, B, P, g, q);
+                if (sreg) {
 #pragma unroll
-                for (int jj = 0; jj < M; ++jj) acc = fma(Rt[i * LD + jj], DU[jj], acc);
-                CU[i] = acc;                                                     // c_u = R du
+                    for (int s = 0; s < 2; ++s) {
+                        const int kk = 4 * s + q;
+                        double pv = P[kk * LD + g];
+                        if (kk == g && kk < 6) pv = __dadd_rn(pv, rho);     // P + rho I (ilqr.py:266-267)
+                        dmma(btpr, B[kk * LD + g], pv);
+                    }
+                }
+                if (lane >= 8 && lane < 8 + M) {
+                    const int i = lane - 8;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < M; ++jj) acc = fma(Rt[i * LD + jj], DU[jj], acc);
+                    CU[i] = acc;                                                 // c_u = R du
+                }
+                store_frag(W, w, g, q);
+                store_frag(ATP, atp, g, q);
+                store_frag(BTP, btp, g, q);
+                if (sreg) store_frag(BTPR, btpr, g, q);
             }
-            // ---- cost derivatives: W = (H|e)^T Q ; (c_xx | c_x) = W (H | e)      (ilqr.py:186-190)
-            Frag w{0.0, 0.0};
-            mma88<true, false>(w, H, Qt, g, q);
-            store_frag(W, w, g, q);
             __syncwarp();
+            // ---- level 2: (Q_xx|Q_x), Q_uu, (Q_ux|Q_u), Q_uu~, Q_ux~                 (ilqr.py:258-274)
             Frag qxx{0.0, 0.0};
-            mma88<false, false>(qxx, W, H, g, q);
-            __syncwarp();
-            // ---- A^T (P | p) -> W ;  B^T (P | p) -> H
-            Frag atp{0.0, 0.0}, btp{0.0, 0.0};
-            mma88<true, false>(atp, A, P, g, q);
-            mma88<true, false>(btp, B, P, g, q);
-            store_frag(W, atp, g, q);
-            store_frag(H, btp, g, q);
-            __syncwarp();
-            // ---- (Q_xx | Q_x) = (c_xx | c_x) + (A^T P | A^T p) A'                (ilqr.py:258,260)
-            mma88<false, false>(qxx, W, A, g, q);
-            // ---- Q_uu = R + (B^T P) B ; (Q_ux | Q_u) = (0 | c_u) + (B^T P | B^T p) A'   (ilqr.py:259,261,262)
-            Frag quu = load_frag(Rt, g, q);
-            mma88<false, false>(quu, H, B, g, q);
-            Frag qux{(q == 3 && g < M) ? CU[g] : 0.0, 0.0};
-            mma88<false, false>(qux, H, A, g, q);
-            store_frag(QUU, quu, g, q);
-            store_frag(QUX, qux, g, q);
-            __syncwarp();
-            // ---- regularised terms                                               (ilqr.py:264-274)
-            Frag quut, quxt;
-            if (sreg) {
-                Frag btpr{0.0, 0.0};
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int kk = 4 * s + q;
-                    double pv = P[kk * LD + g];
-                    if (kk == g && kk < 6) pv = __dadd_rn(pv, rho);
-                    dmma(btpr, B[kk * LD + g], pv);
+            {
+                mma88<false, false>(qxx, W, H, g, q);                  // (c_xx | c_x) = W (H | e)
+                mma88<false, false>(qxx, ATP, A, g, q);                // + (A^T P | A^T p) A'
+                Frag quu = load_frag(Rt, g, q);
+                mma88<false, false>(quu, BTP, B, g, q);                // R + (B^T P) B
+                Frag qux{(q == 3 && g < M) ? CU[g] : 0.0, 0.0};
+                mma88<false, false>(qux, BTP, A, g, q);                // (0 | c_u) + (B^T P | B^T p) A'
+                Frag quut, quxt;
+                if (sreg) {
+                    quut = load_frag(Rt, g, q);
+                    mma88<false, false>(quut, BTPR, B, g, q);
+                    quxt = Frag{0.0, 0.0};
+                    mma88<false, false>(quxt, BTPR, A, g, q);
+                } else {
+                    quut = quu;
+                    quxt = qux;
+                    if (cf.regularize) {
+                        if (2 * q == g) quut.c0 = __dadd_rn(quut.c0, rho);
+                        if (2 * q + 1 == g) quut.c1 = __dadd_rn(quut.c1, rho);
+                    }
                 }
-                store_frag(H, btpr, g, q);
-                __syncwarp();
-                quut = load_frag(Rt, g, q);
-                mma88<false, false>(quut, H, B, g, q);
-                quxt = Frag{0.0, 0.0};
-                mma88<false, false>(quxt, H, A, g, q);
-            } else {
-                quut = quu;
-                quxt = qux;
-                if (cf.regularize) {
-                    if (2 * q == g) quut.c0 = __dadd_rn(quut.c0, rho);
-                    if (2 * q + 1 == g) quut.c1 = __dadd_rn(quut.c1, rho);
+                if (g >= M) {   // keep the padding block of Q_uu~ an identity so the sweep is well defined
+                    quut.c0 = (2 * q == g) ? 1.0 : 0.0;
+                    quut.c1 = (2 * q + 1 == g) ? 1.0 : 0.0;
                 }
+                if (q == 3) { quxt.c0 = qux.c0; quxt.c1 = 0.0; }       // right-hand side (Q_ux~ | Q_u)
+                store_frag(QUU, quu, g, q);
+                store_frag(QUX, qux, g, q);
+                store_frag(QT, quut, g, q);
+                store_frag(RHS, quxt, g, q);                           // P is dead until level 5
             }
-            if (g >= M) {   // keep the padding block of Q_uu~ an identity so the sweep below is well defined
-                quut.c0 = (2 * q == g) ? 1.0 : 0.0;
-                quut.c1 = (2 * q + 1 == g) ? 1.0 : 0.0;
-            }
-            store_frag(INV, quut, g, q);
-            // right-hand side (Q_ux~ | Q_u)
-            if (q == 3) { quxt.c0 = qux.c0; quxt.c1 = 0.0; }
-            store_frag(W, quxt, g, q);
             __syncwarp();
-            // ---- PD test + explicit inverse                                       (ilqr.py:276-289)
-            const bool pd = gj_spd<M>(INV, lane);
+            // ---- level 3: PD test + gains (K | k) = -Q_uu~^-1 (Q_ux~ | Q_u)         (ilqr.py:276-292)
+            const bool pd = gj_solve_spd<M>(QT, RHS, KT, lane);
             if (!pd && cf.regularize) {
                 rho_update(cf, true, rho, drho);
                 ok = false;
                 break;
             }
-            // ---- (K | k) = -inv (Q_ux~ | Q_u)                                     (ilqr.py:291-292)
-            Frag kf{0.0, 0.0};
-            mma88<false, false>(kf, INV, W, g, q);
-            kf.c0 = -kf.c0; kf.c1 = -kf.c1;
-            if (g >= M) { kf.c0 = 0.0; kf.c1 = 0.0; }
-            if (q == 3) kf.c1 = 0.0;
-            store_frag(KT, kf, g, q);
-            if (g < M) {
-                if (q < 3) {
-                    *reinterpret_cast<double2*>(Kout + ((long long)t * M + g) * 6 + 2 * q) = make_double2(kf.c0, kf.c1);
-                } else {
-                    kout[t * M + g] = kf.c0;
-                }
+            __syncwarp();
+            // ---- level 4: K^T Q_uu ; gains to global
+            {
+                Frag kq{0.0, 0.0};
+                mma88<true, false>(kq, KT, QUU, g, q);
+                if (lane < 6 * M) Kout[(long long)t * M * 6 + lane] = KT[ko0];
+                if (32 + lane < 6 * M) Kout[(long long)t * M * 6 + 32 + lane] = KT[ko1];
+                if (lane < M) kout[t * M + lane] = KT[lane * LD + 6];
+                store_frag(KQ, kq, g, q);
             }
             __syncwarp();
-            // ---- K^T Q_uu -> H                                                    (ilqr.py:294-295)
-            Frag kq{0.0, 0.0};
-            mma88<true, false>(kq, KT, QUU, g, q);
-            store_frag(H, kq, g, q);
-            __syncwarp();
-            // ---- (P | p) = (((Q_xx|Q_x) + KQ (K|k)) + K^T (Q_ux|Q_u)) + Q_ux^T (K|k)
-            mma88<false, false>(qxx, H, KT, g, q);
+            // ---- level 5: (P | p) = (((Q_xx|Q_x) + KQ (K|k)) + K^T (Q_ux|Q_u)) + Q_ux^T (K|k)   (ilqr.py:294-295)
+            mma88<false, false>(qxx, KQ, KT, g, q);
             mma88<true, false>(qxx, KT, QUX, g, q);
             mma88<true, false>(qxx, QUX, KT, g, q);
             // line-search scalars: a_t = k . Q_u, b_t = (k^T Q_uu) . k              (ilqr.py:69-71)
@@ -707,7 +740,7 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
             if (lane < M) {
                 const double kv = KT[lane * LD + 6];
                 pa = __dmul_rn(kv, QUX[lane * LD + 6]);
-                pb = __dmul_rn(H[6 * LD + lane], kv);
+                pb = __dmul_rn(KQ[6 * LD + lane], kv);
             }
 #pragma unroll
             for (int off = 1; off < 8; off <<= 1) {
@@ -715,11 +748,11 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
                 pb = __dadd_rn(pb, __shfl_xor_sync(FULL, pb, off));
             }
             if (lane == 0) { ab[2 * t] = pa; ab[2 * t + 1] = pb; }
-            __syncwarp();
             if (g >= 6) { qxx.c0 = 0.0; qxx.c1 = 0.0; }
             if (q == 3) qxx.c1 = 0.0;
+            __syncwarp();                       // every lane has read the right-hand side held in P's tile
             store_frag(P, qxx, g, q);
-            __syncwarp();
+            // the (K | k) tile is W next step: its column 7 must be zero again, rows >= M too (they are: K rows >= M = 0)
         }
         if (ok) {
             rho_update(cf, false, rho, drho);

@@ -202,3 +202,75 @@ def test_specialised_kernels_agree_with_generic_kernels():
     assert relerr(res["fast"][4], res["generic"][4]) < TOL
     for a, b in zip(res["fast_roll"], res["generic_roll"]):
         assert relerr(a, b) < 1e-11
+
+
+def test_receding_horizon_closed_loop_matches_oracle_loop():
+    """Config-4 driver (receding-horizon iLQR with shifted warm start + u_last) vs the same loop written with the
+    numpy oracle solver and model, noise-free, small case."""
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.mpc import RecedingHorizonILQR
+    from oracle.ilqr_np import ILQRNP
+    from oracle.utils_np import QuadraticCost
+    m, N, steps, Bt = 4, 10, 4, 3
+    s_, model = _ssm(m)
+    rng = np.random.default_rng(11)
+    zref = synth.figure8_targets(s_['z_ref'], steps + N, [3.0, 6.0, 9.0], [0.0, 1.0, 2.0])      # (Bt, steps+N+1, 6)
+    x0 = rng.uniform(-0.3, 0.3, size=(Bt, 6)) * np.array([1, 1, 1, 0, 0, 0])
+    sol = _solver(model, m, zref[:, :N + 1])
+    out = RecedingHorizonILQR(sol).run(x0, zref, steps)
+    Q, R, Qf = synth.trunk_ilqr_costs(6, m)
+    for b in range(Bt):
+        om = _oracle_ssm(m)
+        x = x0[b].copy()
+        u_plan, u_last = None, np.zeros(m)
+        for k in range(steps):
+            o = ILQRNP(0.02, om, QuadraticCost(Q, R, Qf), N)
+            o.set_target(zref[b, k:k + N + 1])
+            o.set_u_last(u_last)
+            ws = None if u_plan is None else np.vstack((u_plan[1:], u_plan[-1:]))
+            _, u_plan, _ = o.ilqr_computation(x, ws)
+            assert out['iterations'][b, k] == o.iterations
+            assert relerr(out['u'][b, k], u_plan[0]) < 1e-8
+            x = om.ssm.update_state(x, u_plan[0], 0.02)
+            u_last = u_plan[0]
+            assert relerr(out['x'][b, k + 1], x) < 1e-8
+
+
+def test_tpwl_diamond_size_solve_vs_oracle():
+    """Diamond TPWL shape (n = 72, m = 4, P = 1000, zoh pre-discretised on the device), horizon 30: generic
+    one-CTA-per-problem kernel vs the numpy oracle (which is pinned bitwise to the reference class)."""
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.tpwl.tpwl import TPWLATV
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost
+    from oracle.tpwl_np import TPWLATVNP
+    from oracle.ilqr_np import ILQRNP
+    from oracle.utils_np import QuadraticCost as QCo
+    data, Hf = synth.tpwl_bank()
+    params = {'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}
+    g = TPWLATV(data, params=params, Hf=Hf, discr_method='zoh')
+    g.pre_discretize(0.01)
+    o_model = TPWLATVNP(data, params=params, Hf=Hf, discr_method='zoh')
+    # the oracle gets the DEVICE-discretised bank so that both sides linearise with identical matrices
+    o_model.A_d, o_model.B_d, o_model.d_d, o_model.pre_discretized_dt = list(g.A_d), list(g.B_d), list(g.d_d), 0.01
+    N = 30
+    Q = np.zeros((6, 6)); Q[3, 3] = Q[4, 4] = 100.0
+    R = 1e-5 * np.eye(4)
+    Qf = np.zeros((6, 6))
+    th = np.linspace(0, 2 * np.pi, N + 1)
+    x0s, _ = synth.tpwl_rollout_batch(2, N=1, seed=21)
+    zts = []
+    for b in range(2):
+        zt = np.tile(g.z_ref, (N + 1, 1))
+        zt[:, 3] += (0.5 + b) * np.sin(th); zt[:, 4] += (0.5 + b) * np.sin(2 * th)
+        zts.append(zt)
+    zts = np.array(zts)
+    s = iLQR(0.01, g, QuadraticCost(Q, R, Qf), N)
+    s.set_target(zts)
+    x, u, K = s.ilqr_computation(x0s)
+    for b in range(2):
+        o = ILQRNP(0.01, o_model, QCo(Q, R, Qf), N)
+        o.set_target(zts[b])
+        xo, uo, Ko = o.ilqr_computation(x0s[b])
+        assert s.info['iterations'][b] == o.iterations
+        assert relerr(x[b], xo) < 1e-8 and relerr(u[b], uo) < 1e-8 and relerr(K[b], Ko) < 1e-8

@@ -274,3 +274,88 @@ def test_tpwl_diamond_size_solve_vs_oracle():
         xo, uo, Ko = o.ilqr_computation(x0s[b])
         assert s.info['iterations'][b] == o.iterations
         assert relerr(x[b], xo) < 1e-8 and relerr(u[b], uo) < 1e-8 and relerr(K[b], Ko) < 1e-8
+
+
+def _pair(m, N, tweak, zt, Qscale=1.0, x0=None, Qneg=False):
+    """Solve the same problem with the CUDA kernel and the oracle after applying `tweak(params)` to both configs."""
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost as QC
+    from oracle.ilqr_np import ILQRNP
+    from oracle.utils_np import QuadraticCost
+    _, model = _ssm(m)
+    Q, R, Qf = synth.trunk_ilqr_costs(6, m)
+    Q = Q * Qscale
+    if Qneg:
+        Q = Q.copy(); Q[2, 2] = -5000.0          # indefinite stage cost: Q_uu~ loses positive definiteness
+    s = iLQR(0.02, model, QC(Q, R, Qf), N, trace=True)
+    o = ILQRNP(0.02, _oracle_ssm(m), QuadraticCost(Q, R, Qf), N, max_pd_restarts=60)
+    for obj in (s, o):
+        tweak(obj.params)
+        obj.set_target(zt)
+    x0 = np.zeros(6) if x0 is None else x0
+    return s, o, s.ilqr_computation(x0), x0
+
+
+def test_branch_paths_line_search_failure_and_abandon():
+    """improv_lb = 0.99999 rejects every step: five trials per iteration, rho bumped (scaled + 10) each time,
+    abandoned after counter_limit failures (ilqr.py:76-103)."""
+    import sofacontrol_b200.synth as synth
+    s_, _ = _ssm(4)
+    zt = synth.figure8_targets(s_['z_ref'], 20, 5.0)[0]
+
+    def tweak(p):
+        p.improv_lb = 0.99999
+    s, o, (x, u, K), x0 = _pair(4, 20, tweak, zt)
+    xo, uo, Ko = o.ilqr_computation(x0)
+    assert s.info['iterations'] == o.iterations
+    assert s.info['status'] & 4                                            # abandoned after counter_limit failures
+    assert sum(1 for ev in o.trace if not ev['accepted']) == 5
+    assert s.info['trials'] == sum(len(ev['trials']) for ev in o.trace)
+    assert abs(float(s.info['rho']) - float(o.rho)) <= 1e-12 * float(o.rho)
+    assert relerr(x, xo) < TOL and relerr(K, Ko) < TOL and relerr(u, uo) < TOL
+    for ev in o.trace:
+        assert (s.info['trace'][ev['it'], 1] > 0) == ev['accepted']
+        assert abs(s.info['trace'][ev['it'], 2] - ev['rho_after_bwd']) <= 1e-12 * max(1.0, ev['rho_after_bwd'])
+
+
+def test_branch_paths_non_pd_restarts():
+    """An indefinite stage cost makes Q_uu~ non-PD: the backward pass restarts with increased rho until the
+    Cholesky test passes (ilqr.py:276-287); restart counts and the rho schedule must match the oracle."""
+    import sofacontrol_b200.synth as synth
+    s_, _ = _ssm(4)
+    zt = synth.figure8_targets(s_['z_ref'], 15, 3.0)[0]
+
+    def tweak(p):
+        p.max_iter = 2
+    s, o, (x, u, K), x0 = _pair(4, 15, tweak, zt, Qneg=True)
+    xo, uo, Ko = o.ilqr_computation(x0)
+    assert sum(ev['pd_restarts'] for ev in o.trace) > 0                    # the path is really exercised
+    assert s.info['iterations'] == o.iterations
+    for ev in o.trace:
+        assert s.info['trace'][ev['it'], 3] == ev['pd_restarts']
+        assert abs(s.info['trace'][ev['it'], 2] - ev['rho_after_bwd']) <= 1e-12 * max(1.0, ev['rho_after_bwd'])
+    assert relerr(x, xo) < 1e-8 and relerr(u, uo) < 1e-8 and relerr(K, Ko) < 1e-8
+
+
+def test_branch_paths_max_iter_and_no_linesearch():
+    import sofacontrol_b200.synth as synth
+    s_, _ = _ssm(8)
+    zt = synth.figure8_targets(s_['z_ref'], 30, 12.0, 0.7)[0]
+
+    def tweak(p):
+        p.max_iter = 1
+        p.epsilon = 1e-12
+    s, o, (x, u, K), x0 = _pair(8, 30, tweak, zt)
+    xo, uo, Ko = o.ilqr_computation(x0)
+    assert s.info['iterations'] == o.iterations == 2 and (s.info['status'] & 2)       # nbr_iter <= max_iter quirk: 2 passes
+    assert relerr(x, xo) < TOL and relerr(u, uo) < TOL and relerr(K, Ko) < TOL
+
+    def tweak2(p):
+        p.do_linesearch = False
+        p.max_iter = 3
+        p.regularize = False
+    s, o, (x, u, K), x0 = _pair(8, 30, tweak2, zt)
+    xo, uo, Ko = o.ilqr_computation(x0)
+    assert s.info['iterations'] == o.iterations
+    assert relerr(x, xo) < TOL and relerr(u, uo) < TOL and relerr(K, Ko) < TOL

@@ -53,6 +53,42 @@ __device__ __forceinline__ void mm(double* __restrict__ C, int ldc, const double
     }
 }
 
+// Same contract as mm<>, on the FP64 tensor pipe: each warp owns 8 x 8 output tiles (two at a time for ILP) and
+// walks K in steps of 4 with mma.sync.m8n8k4.f64; fragment loads are masked, so any M, N, K works.  Operands may be
+// in shared or global memory.  Used for the n x n x n products of the Riccati sweep when n is large (TPWL, n = 72).
+__device__ __forceinline__ void dmma_m8n8k4_acc(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+template <int NT, bool TA, bool TB>
+__device__ __forceinline__ void mm_dmma(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda,
+                                        const double* __restrict__ B, int ldb, int M, int N, int K,
+                                        const double* __restrict__ D = nullptr, int ldd = 0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, NW = NT / 32;
+    const int tm = (M + 7) / 8, tn = (N + 7) / 8, tn2 = (tn + 1) / 2;
+    for (int tile = warp; tile < tm * tn2; tile += NW) {
+        const int i0 = (tile / tn2) * 8, j0 = (tile % tn2) * 16;
+        const int row = i0 + g, colA = j0 + g, colB = j0 + 8 + g;
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            const int k = k0 + q;
+            const bool kok = k < K;
+            const double a = (row < M && kok) ? (TA ? A[k * lda + row] : A[row * lda + k]) : 0.0;
+            const double b0 = (colA < N && kok) ? (TB ? B[colA * ldb + k] : B[k * ldb + colA]) : 0.0;
+            const double b1 = (colB < N && kok) ? (TB ? B[colB * ldb + k] : B[k * ldb + colB]) : 0.0;
+            dmma_m8n8k4_acc(c00, c01, a, b0);
+            dmma_m8n8k4_acc(c10, c11, a, b1);
+        }
+        if (row < M) {
+            const int ca = j0 + 2 * q, cb = j0 + 8 + 2 * q;
+            if (ca < N)     C[row * ldc + ca]     = D ? (D[row * ldd + ca] + c00) : c00;
+            if (ca + 1 < N) C[row * ldc + ca + 1] = D ? (D[row * ldd + ca + 1] + c01) : c01;
+            if (cb < N)     C[row * ldc + cb]     = D ? (D[row * ldd + cb] + c10) : c10;
+            if (cb + 1 < N) C[row * ldc + cb + 1] = D ? (D[row * ldd + cb + 1] + c11) : c11;
+        }
+    }
+}
+
 // y[i] = (d ? d[i] : 0) + sum_k opA(i,k) x[k]
 template <int NT, bool TA>
 __device__ __forceinline__ void mv(double* __restrict__ y, const double* __restrict__ A, int lda,

@@ -11,7 +11,7 @@ namespace srcb {
 // ---------------------------------------------------------------------------------------------------------------
 struct Layout {                 // offsets in doubles inside one trajectory record / the per-problem workspace
     long long x, u, e, H, A, B, idx, rec;       // record fields, record size
-    long long k, ab, total;                     // backward outputs (K goes straight to the result buffer)
+    long long k, ab, cxx, total;                // backward outputs (K goes straight to the result buffer); constant c_xx
 };
 
 __host__ __device__ inline Layout make_layout(int n, int m, int nz, int N, bool gn, bool index_lin) {
@@ -28,6 +28,7 @@ __host__ __device__ inline Layout make_layout(int n, int m, int nz, int N, bool 
     o = 2 * L.rec;
     L.k = o;  o += (long long)N * m;
     L.ab = o; o += 2LL * N;
+    L.cxx = o; o += gn ? 0 : (long long)n * n;  // constant-H mode: H^T Q H lives here (global, L2) instead of shared memory
     L.total = (o + 1) & ~1LL;
     return L;
 }

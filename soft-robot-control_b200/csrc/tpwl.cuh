@@ -71,11 +71,35 @@ __device__ inline double np_pairwise_sumsq(const double* __restrict__ bankT, int
     return __dadd_rn(np_pairwise_sumsq(bankT, P, p, c, lo, lo + n2), np_pairwise_sumsq(bankT, P, p, c, lo + n2, hi));
 }
 
+// r = 36 (Diamond) with everything unrolled: 8 accumulators over the first 32 terms, 4 sequential tail terms --
+// exactly the order np_pairwise_sumsq takes for n = 36, without the loop / branch overhead.
+__device__ __forceinline__ double np_pairwise_sumsq_36(const double* __restrict__ bankT, int P, int p,
+                                                       const double* __restrict__ c) {
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = sq_diff(bankT, P, p, c, k);
+#pragma unroll
+    for (int i = 8; i < 32; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], sq_diff(bankT, P, p, c, i + k));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+    for (int i = 32; i < 36; ++i) res = __dadd_rn(res, sq_diff(bankT, P, p, c, i));
+    return res;
+}
+
 // d_p = wq * ||Q_p - q|| + wv * ||V_p - v||  with x = [v; q]  (utils.py:133-142, tpwl.py:165-168)
 // A zero weight contributes +0.0 (numpy computes 0 * norm; identical unless the norm is inf/nan).
 __device__ __forceinline__ double tpwl_distance(const TpwlDev& M, const double* __restrict__ x, int p) {
     const int r = M.r;
     double dq = 0.0, dv = 0.0;
+    if (r == 36) {
+        if (M.wq != 0.0) dq = __dmul_rn(M.wq, sqrt(np_pairwise_sumsq_36(M.qT, M.P, p, x + r)));
+        if (M.wv != 0.0) dv = __dmul_rn(M.wv, sqrt(np_pairwise_sumsq_36(M.vT, M.P, p, x)));
+        return __dadd_rn(dq, dv);
+    }
     if (M.wq != 0.0) dq = __dmul_rn(M.wq, sqrt(np_pairwise_sumsq(M.qT, M.P, p, x + r, 0, r)));
     if (M.wv != 0.0) dv = __dmul_rn(M.wv, sqrt(np_pairwise_sumsq(M.vT, M.P, p, x, 0, r)));
     return __dadd_rn(dq, dv);

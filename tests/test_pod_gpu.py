@@ -113,3 +113,25 @@ def test_row_sharded_pod_two_gpus_nccl():
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["ok"] and out["world"] == 2 and out["subspace_angle"] < 1e-8
+
+
+def test_run_pod_and_load_pod_roundtrip(tmp_path):
+    """run_POD / load_POD (pod.py:93-141) on a snapshot pickle with the reference's schema."""
+    from sofacontrol_b200.mor import pod
+    from sofacontrol_b200 import utils as scutils
+    import sofacontrol_b200.synth as synth
+    from oracle import pod_np
+    X, _, _ = synth.pod_snapshots(300, 60, seed=7)          # (nf, ns)
+    snaps = {'q': list(X.T + 1.0), 'v': list(X.T), 'v+': list(2 * X.T)}
+    f_in, f_out = str(tmp_path / "snap.pkl"), str(tmp_path / "out" / "pod.pkl")
+    scutils.save_data(f_in, snaps)
+    cfg = pod.pod_config()
+    cfg.pod_tolerance = 1e-4
+    res = pod.run_POD(f_in, f_out, cfg)
+    _, Uo, nbo, So = pod_np.compute_POD(X, 1e-4)
+    assert res['POD_info']['U'].shape == Uo.shape and res['config']['pod_type'] == 'v'
+    assert pod_np.subspace_angle(Uo, res['POD_info']['U'])[0] < 1e-8
+    rom = pod.load_POD(f_out)
+    assert rom.rom_dim == nbo and np.array_equal(rom.q_ref, snaps['q'][0])
+    with pytest.raises(RuntimeError):
+        pod.load_POD(str(tmp_path / "missing.pkl"))

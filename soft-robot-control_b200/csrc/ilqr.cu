@@ -35,6 +35,9 @@ using namespace srcb;
         const srcb200_tpwl_model* mm_ = (const srcb200_tpwl_model*)(model);                         \
         if (int e = check_tpwl_model(mm_)) return e;                                                \
         TpwlDev M = to_dev(*mm_);                                                                   \
+        if (M.discr == SRCB200_DISCR_ZOH && pr->dt >= 0.0)                                          \
+            return fail(SRCB200_E_METHOD, "iLQR on a TPWL model with zoh needs a pre-discretised bank "        \
+                                          "(pre_discretize(dt)): per-step expm is not available inside the solver"); \
         return CALL_TPWL;                                                                           \
     }                                                                                               \
     return fail(SRCB200_E_DIM, "unknown model_kind %d", (int)(kind));

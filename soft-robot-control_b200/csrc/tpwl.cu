@@ -9,8 +9,27 @@ extern "C" int srcb200_zoh_batch(int32_t n, int32_t m, int64_t count, double dt,
 
 namespace srcb {
 
+size_t blend_stream_workspace(int width);
+int blend_stream(const double* bank, int P, int width, const double* W, long long count, double* out, void* ws,
+                 cudaStream_t st);   // blend_stream.cu: TMA-staged bank stream for small batches (-1: not applicable)
+
+constexpr long long kBlendStreamMaxBatch = 32;   // above this the DMMA GEMM (bank tile reused across the batch) wins
+
+// W (count x P) @ bank (P x width): bank stream for small batches, DMMA GEMM otherwise
+static int blend(const double* bank, int P, long long width, const double* W, long long count, double* out, void* stream_ws,
+                 cudaStream_t st);
+
 int dgemm_device(int transA, long long M, long long N, long long K, double alpha, const double* A, long long lda,
                  const double* B, long long ldb, double* C, long long ldc, cudaStream_t st);
+
+static int blend(const double* bank, int P, long long width, const double* W, long long count, double* out, void* stream_ws,
+                 cudaStream_t st) {
+    if (stream_ws && count <= kBlendStreamMaxBatch) {
+        const int rc = blend_stream(bank, P, (int)width, W, count, out, stream_ws, st);
+        if (rc >= 0) return rc;
+    }
+    return dgemm_device(0, count, width, P, 1.0, W, P, bank, width, out, width, st);
+}
 
 int check_tpwl_model(const srcb200_tpwl_model* s) {
     if (!s) return fail(SRCB200_E_NULL, "tpwl model is NULL");
@@ -494,7 +513,7 @@ extern "C" size_t srcb200_tpwl_linearize_workspace(const srcb200_tpwl_model* mdl
     TpwlDev M = to_dev(*mdl);
     const size_t z = (M.discr == SRCB200_DISCR_ZOH) ? align_up(srcb200_zoh_workspace(M.n, M.m, count), 256) : 0;
     if (M.method == SRCB200_TPWL_NN) return align_up(sizeof(int32_t) * (size_t)count, 256) + z;
-    return align_up(sizeof(double) * (size_t)count * M.P, 256) + z;
+    return align_up(sizeof(double) * (size_t)count * M.P, 256) + z + align_up(blend_stream_workspace(M.n * M.n), 256);
 }
 
 extern "C" int srcb200_tpwl_linearize_batch(const srcb200_tpwl_model* mdl, int64_t count, const double* x, double dt,
@@ -520,15 +539,17 @@ extern "C" int srcb200_tpwl_linearize_batch(const srcb200_tpwl_model* mdl, int64
     } else {
         // the bank is three arrays (A, B, d) -> three GEMMs against the same weight matrix
         double* W = (double*)workspace;
+        void* sws = (char*)workspace + workspace_bytes - align_up(blend_stream_workspace(n * n), 256);   // tail of the workspace
         if (int e = srcb200_tpwl_weights_batch(mdl, count, x, W, stream)) return e;
-        if (int e = dgemm_device(0, count, (long long)n * n, M.P, 1.0, W, M.P, M.A, (long long)n * n, A, (long long)n * n, st)) return e;
-        if (int e = dgemm_device(0, count, (long long)n * m, M.P, 1.0, W, M.P, M.B, (long long)n * m, B, (long long)n * m, st)) return e;
-        if (int e = dgemm_device(0, count, n, M.P, 1.0, W, M.P, M.d, n, d, n, st)) return e;
+        if (int e = blend(M.A, M.P, (long long)n * n, W, count, A, sws, st)) return e;
+        if (int e = blend(M.B, M.P, (long long)n * m, W, count, B, sws, st)) return e;
+        if (int e = blend(M.d, M.P, n, W, count, d, sws, st)) return e;
     }
     if (disc) {
         const size_t first = (M.method == SRCB200_TPWL_NN) ? align_up(sizeof(int32_t) * (size_t)count, 256)
                                                            : align_up(sizeof(double) * (size_t)count * M.P, 256);
-        return discretize_any(n, m, M.discr, count, dt, A, B, d, (char*)workspace + first, workspace_bytes - first, st);
+        const size_t zb = (M.discr == SRCB200_DISCR_ZOH) ? align_up(srcb200_zoh_workspace(n, m, count), 256) : 0;
+        return discretize_any(n, m, M.discr, count, dt, A, B, d, (char*)workspace + first, zb, st);
     }
     return 0;
 }
@@ -540,7 +561,8 @@ extern "C" size_t srcb200_tpwl_rollout_workspace(const srcb200_tpwl_model* mdl, 
     if (M.method == SRCB200_TPWL_NN) return 256;
     const size_t z = (M.discr == SRCB200_DISCR_ZOH) ? align_up(srcb200_zoh_workspace(M.n, M.m, batch), 256) : 0;
     return align_up(sizeof(double) * (size_t)batch * M.P, 256) + align_up(sizeof(double) * (size_t)batch * M.n * M.n, 256) +
-           align_up(sizeof(double) * (size_t)batch * M.n * M.m, 256) + align_up(sizeof(double) * (size_t)batch * M.n, 256) + z;
+           align_up(sizeof(double) * (size_t)batch * M.n * M.m, 256) + align_up(sizeof(double) * (size_t)batch * M.n, 256) + z +
+           align_up(blend_stream_workspace(M.n * M.n), 256);
 }
 
 extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t batch, int32_t N, const double* x0,
@@ -587,7 +609,8 @@ extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t
         double* Bb = (double*)wp;  wp += align_up(sizeof(double) * (size_t)batch * n * m, 256);
         double* db = (double*)wp;  wp += align_up(sizeof(double) * (size_t)batch * n, 256);
         void* zws = wp;
-        const size_t zws_bytes = workspace_bytes - (size_t)(wp - (char*)workspace);
+        const size_t zws_bytes = (M.discr == SRCB200_DISCR_ZOH) ? align_up(srcb200_zoh_workspace(n, m, batch), 256) : 0;
+        void* sws = (char*)workspace + workspace_bytes - align_up(blend_stream_workspace(n * n), 256);
         const long long xs = (long long)(N + 1) * n, us = (long long)N * m;
         SRCB_CUDA(cudaMemcpy2DAsync(x, sizeof(double) * xs, x0, sizeof(double) * n, sizeof(double) * n, batch,
                                     cudaMemcpyDeviceToDevice, st));
@@ -598,9 +621,9 @@ extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t
             // the states of step t live strided inside x: x[b, t, :]
             tpwl_weights_kernel<<<grid, kSel, wsmem, st>>>(M, batch, x + (long long)t * n, xs, W);
             SRCB_LAUNCH_CHECK("tpwl_weights_kernel");
-            if (int e = dgemm_device(0, batch, (long long)n * n, M.P, 1.0, W, M.P, M.A, (long long)n * n, Ab, (long long)n * n, st)) return e;
-            if (int e = dgemm_device(0, batch, (long long)n * m, M.P, 1.0, W, M.P, M.B, (long long)n * m, Bb, (long long)n * m, st)) return e;
-            if (int e = dgemm_device(0, batch, n, M.P, 1.0, W, M.P, M.d, n, db, n, st)) return e;
+            if (int e = blend(M.A, M.P, (long long)n * n, W, batch, Ab, sws, st)) return e;
+            if (int e = blend(M.B, M.P, (long long)n * m, W, batch, Bb, sws, st)) return e;
+            if (int e = blend(M.d, M.P, n, W, batch, db, sws, st)) return e;
             if (disc) if (int e = discretize_any(n, m, M.discr, batch, dt, Ab, Bb, db, zws, zws_bytes, st)) return e;
             tpwl_step_kernel<<<grid, 128, 0, st>>>(n, m, batch, Ab, Bb, db, x + (long long)t * n, xs, u + (long long)t * m, us,
                                                    x + (long long)(t + 1) * n, xs);

@@ -77,7 +77,11 @@ class iLQR:
     def _model_handle(self):
         if self._kind == L.ILQR_MODEL_SSM:
             return self.model.device_model()
-        return self.model.device_model(self.dt)
+        m = self.model
+        if (m.tpwl_method == 'nn' and m.discr_method == 'zoh' and
+                not (m.pre_discretized_dt is not None and self.dt == m.pre_discretized_dt)):
+            return m._zoh_bank_model(self.dt)      # same matrices the reference recomputes with expm at every step
+        return m.device_model(self.dt)
 
     def _nz(self):
         return int(self.model.get_output_dim())

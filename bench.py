@@ -471,6 +471,57 @@ def run_pod_gram(args, rank, world, dev_index):
                                  "peak = measured cuBLAS DGEMM"}}
 
 
+def run_mpc(args, rank, world, dev_index):
+    """BASELINE configs[3]: closed-loop receding-horizon Monte Carlo -- every control step re-solves all problems
+    (horizon 20, warm start = shifted previous plan, u_last) and steps the plant with process noise."""
+    import torch
+    import torch.distributed as dist
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200 import _lib as L
+    from sofacontrol_b200.SSM.ssm import SSMDynamics
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.mpc import RecedingHorizonILQR
+    from sofacontrol_b200.utils import QuadraticCost
+    batch = args.batch if args.batch != 4096 else 16384
+    N, steps = 20, 20
+    s = synth.trunk_ssm(8)
+    model = SSMDynamics(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
+    Q, R, Qf = synth.trunk_ilqr_costs(6, 8)
+    solver = iLQR(0.02, model, QuadraticCost(Q, R, Qf), N)
+    rng = np.random.default_rng(4 + rank)
+    amp, ph = rng.uniform(2, 15, size=batch), rng.uniform(0, 2 * np.pi, size=batch)
+    T = steps + N
+    th = np.linspace(0, 2 * np.pi * T / 100.0, T + 1)[None, :] + ph[:, None]
+    zref = np.tile(s['z_ref'], (batch, T + 1, 1))
+    zref[:, :, 0] += -amp[:, None] * np.sin(th); zref[:, :, 1] += amp[:, None] * np.sin(2 * th)
+    x0 = np.zeros((batch, 6)); x0[:, :3] = rng.uniform(-0.5, 0.5, size=(batch, 3))
+    mpc = RecedingHorizonILQR(solver, process_noise_std=1e-3, seed=4 + rank)
+    x0d, zd = L.to_dev(x0), L.to_dev(zref)
+    mpc.run_device(x0d, zd, 2)                                   # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    with ClockSampler(dev_index) as clk:
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        out = mpc.run_device(x0d, zd, steps)
+        e_.record()
+        torch.cuda.synchronize()
+    t_dev = s_.elapsed_time(e_) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt[0])
+    its = out['iterations'].float().mean().item()
+    return {"metric": "mpc_problem_steps_per_sec", "value": batch * steps * world / t_dev, "unit": "receding-horizon solves/s",
+            "n_gpus": world, "steps": steps, "warmup": 2, "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "closed-loop receding-horizon iLQR Monte Carlo (BASELINE configs[3], SSM plant): %d problems per "
+                                   "GPU x %d control steps, horizon %d, warm start + u_last, process noise 1e-3" % (batch, steps, N),
+                       "mean_iterations_per_solve": its, "converged_frac": float((out['status'] & 1).float().mean().item())},
+            "e2e": None, "gpu_launches": steps * 2, "clocks": clk.summary(), "roofline": None}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU port on the host cores, same workload/metric (bounded sample)."""
     t_all = []
@@ -495,7 +546,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ilqr_trunk_ssm",
-                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting", "ssm_rollout", "ssm_eval", "pod_gram"])
+                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting", "ssm_rollout", "ssm_eval", "pod_gram", "mpc"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--cpu-per-core", type=int, default=2)
@@ -527,6 +578,8 @@ def main():
         res = run_ssm_eval(args, rank, world, local)
     elif args.workload == "pod_gram":
         res = run_pod_gram(args, rank, world, local)
+    elif args.workload == "mpc":
+        res = run_mpc(args, rank, world, local)
     else:
         res = run_tpwl_rollout(args, rank, world, local, "nn" if args.workload.endswith("nn") else "weighting")
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "ilqr_trunk_ssm":

@@ -122,3 +122,37 @@ def test_empty_batch_and_zero_horizon():
     assert A.shape == (0, 6, 6) and B.shape == (0, 6, 4) and d.shape == (0, 6)
     x, z = g.rollout(np.ones((3, 6)) * 0.1, np.zeros((3, 0, 4)), 0.01)
     assert x.shape == (3, 1, 6) and z.shape == (3, 1, 6)
+
+
+def test_c_abi_error_codes_on_device():
+    """Argument / workspace validation of the C ABI with a live device: negative codes, no launch, message set."""
+    import ctypes
+    import torch
+    from sofacontrol_b200 import _lib as L
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.lqr.ilqr import iLQR, C_addr
+    from sofacontrol_b200.utils import QuadraticCost
+    g, _ = _models(4, discrete=False, discr_method='be')
+    lib = L.lib()
+    h = g.device_model()
+    x = torch.zeros((2, 6), device="cuda", dtype=torch.float64)
+    assert lib.srcb200_ssm_eval_linearize_batch(h, 2, L.ptr(x), None, 0.01, L.ptr(x), None, None, None, None, None, None) == L.E_NULL
+    assert b"u is NULL" in lib.srcb200_last_error_string()
+    assert lib.srcb200_ssm_map_batch(h, 5, 0, 2, L.ptr(x), None, L.ptr(x), None) == L.E_DIM
+    s_ = synth.trunk_ssm(4)
+    zt = synth.figure8_targets(s_['z_ref'], 10, 5.0)[0]
+    Q, R, Qf = synth.trunk_ilqr_costs(6, 4)
+    sol = iLQR(0.02, g, QuadraticCost(Q, R, Qf), 10)
+    sol.set_target(zt)
+    pr = sol._problem(2, x, None, L.to_dev(zt), None)
+    res = L.IlqrResult()
+    assert lib.srcb200_ilqr_solve_batch(L.ILQR_MODEL_SSM, C_addr(h), sol._cfg(), pr, res, None, 0, None) == L.E_NULL
+    out = {k: L.empty(s) for k, s in (('x', (2, 11, 6)), ('u', (2, 10, 4)), ('K', (2, 10, 4, 6)), ('cost', (2,)))}
+    it = L.empty((2,), torch.int32); st = L.empty((2,), torch.int32)
+    res = L.IlqrResult(x=L.ptr(out['x']), u=L.ptr(out['u']), K=L.ptr(out['K']), cost=L.ptr(out['cost']),
+                       iterations=L.ptr(it), status=L.ptr(st))
+    small = L.empty((16,))
+    assert lib.srcb200_ilqr_solve_batch(L.ILQR_MODEL_SSM, C_addr(h), sol._cfg(), pr, res, L.ptr(small), 128, None) == L.E_WORKSPACE
+    assert lib.srcb200_ilqr_solve_batch(7, C_addr(h), sol._cfg(), pr, res, L.ptr(small), 128, None) == L.E_DIM
+    with pytest.raises(L.Srcb200Error):
+        L.check(L.E_WORKSPACE)

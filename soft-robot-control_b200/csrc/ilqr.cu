@@ -54,7 +54,7 @@ extern "C" size_t srcb200_ilqr_workspace_bytes(int32_t model_kind, const void* m
         n = M.n; m = M.m; nz = M.nz; il = (M.method == SRCB200_TPWL_NN) && (M.discr == SRCB200_DISCR_NONE || pr->dt < 0.0);   // == TpwlPolicy::index_lin
     }
     const Layout L = make_layout(n, m, nz, pr->N, pr->gauss_newton != 0, il);
-    return sizeof(double) * (size_t)L.total * (size_t)pr->batch + 256;   // + the work counter of the fast kernel
+    return sizeof(double) * (size_t)L.total * (size_t)pr->batch + ilqr_queue_bytes(pr->batch);   // + the task queue of the fast kernel
 }
 
 extern "C" int srcb200_ilqr_solve_batch(int32_t model_kind, const void* model, const srcb200_ilqr_config* cfg,

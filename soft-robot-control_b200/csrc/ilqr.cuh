@@ -11,7 +11,8 @@ namespace srcb {
 // ---------------------------------------------------------------------------------------------------------------
 struct Layout {                 // offsets in doubles inside one trajectory record / the per-problem workspace
     long long x, u, e, H, A, B, idx, rec;       // record fields, record size
-    long long k, ab, cxx, total;                // backward outputs (K goes straight to the result buffer); constant c_xx
+    long long k, ab, cxx, state, total;         // backward outputs (K goes straight to the result buffer); constant c_xx;
+                                                // solver state of a suspended problem (fast kernel, 8 doubles)
 };
 
 __host__ __device__ inline Layout make_layout(int n, int m, int nz, int N, bool gn, bool index_lin) {
@@ -29,6 +30,8 @@ __host__ __device__ inline Layout make_layout(int n, int m, int nz, int N, bool 
     L.k = o;  o += (long long)N * m;
     L.ab = o; o += 2LL * N;
     L.cxx = o; o += gn ? 0 : (long long)n * n;  // constant-H mode: H^T Q H lives here (global, L2) instead of shared memory
+    o = (o + 1) & ~1LL;
+    L.state = o; o += 8;
     L.total = (o + 1) & ~1LL;
     return L;
 }
@@ -43,6 +46,12 @@ __device__ inline Rec rec_at(double* base, const Layout& L) {
     return r;
 }
 
+// Task queue of the fast kernel behind the per-problem scratch: 64 ints of counters + the slot ring.  The ring must be
+// longer than (problems that can be queued) + (warps that can wait on a ticket at the same time), see ilqr_fast.cu.
+constexpr int kIlqrQueueWaiters = 8192;
+inline long long ilqr_queue_cap(long long batch) { return 2 * batch + kIlqrQueueWaiters; }
+inline size_t ilqr_queue_bytes(long long batch) { return 256 + sizeof(int) * (size_t)ilqr_queue_cap(batch); }
+
 struct IlqrArgs {
     int n, m, nz, N, gn, index_lin, shared_target;
     long long batch;
@@ -54,7 +63,8 @@ struct IlqrArgs {
     double* ws;
     Layout L;
     int model_scratch;          // doubles of model scratch in shared memory
-    int* work_counter;          // device int (zeroed before launch) handing problems to warps in the fast kernel
+    int* work_counter;          // fast kernel's task queue: ints [head, tail, remaining, pad..64) then `queue_cap` slots
+    int queue_cap;
 };
 
 // rho schedule (ilqr.py:198-217), including the `dhro` typo: drho is never lowered.

@@ -300,9 +300,9 @@ __device__ __forceinline__ bool gj_spd(double* __restrict__ tile, int lane) {
 // into registers while step t computes.
 // ---------------------------------------------------------------------------------------------------------------
 template <int M>
-__device__ __noinline__ double fwd_fast(const Ctx c, const IlqrArgs& a, int discr, const double* __restrict__ nx,
-                                        const double* __restrict__ nu, double alpha, const double* __restrict__ K,
-                                        const double* __restrict__ k, const Rec tr, const double* __restrict__ ztar,
+__device__ __noinline__ double fwd_fast(const Ctx c, const IlqrArgs& a, int discr, const double* nx,
+                                        const double* nu, double alpha, const double* K,
+                                        const double* k, const Rec tr, const double* __restrict__ ztar,
                                         const double* __restrict__ ulast) {
     const int lane = c.lane, g = c.g, q = c.q, N = a.N;
     double* ws = CTX_WS(c);
@@ -765,8 +765,54 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Solve kernel (ilqr.py:27-107): one warp per problem, problems handed out through an atomic work counter
+// Solve kernel (ilqr.py:27-107): one warp per problem AND per iteration.  A task is "the next iteration of problem
+// b"; after it the warp saves the solver state (rho, drho, cost, counters: 8 doubles in the problem's scratch) and
+// puts b back at the end of a FIFO task queue unless the solve finished, then takes the oldest waiting task.  The
+// iteration counts of a batch are very uneven (5 .. 50); handing out whole problems leaves most of the GPU idle
+// while the last long solves finish, handing out iterations round-robin keeps every warp busy until the total work
+// is done.  Everything a task needs lives in global memory (records, gains), so any warp on any SM can resume it.
+//
+// Queue: ticket ring.  pop: t = head++, wait until slot[t % cap] holds an id (or no problem remains), take it and
+// mark the slot empty.  push: p = tail++, slot[p % cap] = id.  Pushes are numbered in order, so while ticket t waits
+// no later ticket is served and every other warp holds at most one ticket: two waiting tickets are less than
+// (warps in the grid) apart and never share a slot once cap >= that.  A problem is in the queue at most once, so at
+// most `batch` slots are occupied; cap = 2 * batch + kIlqrQueueWaiters covers both with room to spare.
 // ---------------------------------------------------------------------------------------------------------------
+__global__ void ilqr_queue_init_kernel(int* q, int cap, int batch, double* ws, long long total, long long state) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) q[64 + i] = i < batch ? i : -1;
+    if (i < batch) reinterpret_cast<int*>(ws + i * total + state + 3)[5] = 0;      // "not started"
+
+    if (i == 0) { q[0] = 0; q[1] = batch; q[2] = batch; }
+}
+
+__device__ __forceinline__ int queue_pop(int* q, int cap, int lane) {
+    int id = -1;
+    if (lane == 0) {
+        const int t = atomicAdd(q + 0, 1);
+        volatile int* slot = q + 64 + (t % cap);
+        volatile int* remaining = q + 2;
+        while (true) {
+            const int v = *slot;
+            if (v >= 0) { id = v; *slot = -1; break; }
+            if (*remaining <= 0) break;
+            __nanosleep(256);
+        }
+    }
+    id = __shfl_sync(FULL, id, 0);
+    __threadfence();            // acquire: what the previous owner of this problem wrote is visible (L1 invalidated)
+    return id;
+}
+
+__device__ __forceinline__ void queue_push(int* q, int cap, int lane, int id) {
+    __threadfence();            // release: this warp's records / gains / state before the id becomes visible
+    __syncwarp();
+    if (lane == 0) {
+        const int p = atomicAdd(q + 1, 1);
+        atomicExch(q + 64 + (p % cap), id);
+    }
+}
+
 template <int M>
 __global__ void __launch_bounds__(WARPS * 32, 2)
 ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__ IlqrArgs a) {
@@ -782,12 +828,13 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
     const int lane = c.lane, N = a.N;
     const srcb200_ilqr_config& cf = a.cfg;
     const int discr = Mdl.discr;
+    // a warp may resume a problem with the backward pass before it ever ran a forward pass: start from a clean work area
+    for (int e = lane; e < W_SIZE; e += 32) CTX_WS(c)[e] = 0.0;
+    __syncwarp();
 
     while (true) {
-        long long b = 0;
-        if (lane == 0) b = (long long)atomicAdd(a.work_counter, 1);
-        b = __shfl_sync(FULL, b, 0);
-        if (b >= a.batch) break;
+        const long long b = queue_pop(a.work_counter, a.queue_cap, lane);
+        if (b < 0) break;
         double* wsb = a.ws + b * a.L.total;
         double* kbuf = wsb + a.L.k;
         double* ab = wsb + a.L.ab;
@@ -795,80 +842,97 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
         const double* ztar = a.z_target + (a.shared_target ? 0 : b * (long long)(N + 1) * 6);
         const double* ulast = a.u_last ? a.u_last + b * M : nullptr;
         double* trace = a.otrace ? a.otrace + b * (long long)(cf.max_iter + 1) * 4 : nullptr;
+        double* sv = wsb + a.L.state;           // [rho, drho, cost, (fails, cur), (status, trials), (it, started)]
+        int* svi = reinterpret_cast<int*>(sv + 3);
 
-        double rho = cf.rho0, drho = cf.drho0;
-        int fails = 0, cur = 0, status = 0, trials = 0;
-        {
-            const Rec nom = rec_at(wsb + a.L.rec, a.L);
+        double rho, drho, cost;
+        int fails, cur, status, trials, it;
+        if (svi[5] != 0x5ca1ab1e) {
+            // first task of this problem: nominal rollout (ilqr.py:38-40)
+            rho = cf.rho0; drho = cf.drho0;
+            fails = 0; cur = 0; status = 0; trials = 0; it = 0;
+            const Rec nom = rec_at(wsb + a.L.rec, a.L), tr0 = rec_at(wsb, a.L);
             if (lane < 6) nom.x[lane] = a.x0[b * 6 + lane];
             for (int e = lane; e < N * M; e += 32) nom.u[e] = a.u_init ? a.u_init[b * (long long)N * M + e] : 0.0;
             __syncwarp();
             __threadfence_block();
-        }
-        double cost;
-        {
-            const Rec nom = rec_at(wsb + a.L.rec, a.L), tr0 = rec_at(wsb, a.L);
             cost = fwd_fast<M>(c, a, discr, nom.x, nom.u, 1.0, nullptr, nullptr, tr0, ztar, ulast);
+            if (a.ocost0 && lane == 0) a.ocost0[b] = cost;
+        } else {
+            rho = sv[0]; drho = sv[1]; cost = sv[2];
+            fails = svi[0]; cur = svi[1]; status = svi[2]; trials = svi[3]; it = svi[4];
         }
-        if (a.ocost0 && lane == 0) a.ocost0[b] = cost;
 
-        bool conv = false;
-        int it = 0;
-        while (!conv && it <= cf.max_iter) {
+        bool conv = false, stop = false;
+        if (it <= cf.max_iter) {                // one pass of the `while not converged and nbr_iter <= max_iter` loop
             const Rec rcur = rec_at(wsb + (cur ? a.L.rec : 0), a.L), rtrial = rec_at(wsb + (cur ? 0 : a.L.rec), a.L);
             const BwdResult br = bwd_fast<M>(c, a, rcur, ulast, Kbuf, kbuf, ab, rho, drho);
             rho = br.rho; drho = br.drho;
             const int restarts = br.restarts;
             const double rho_bwd = rho;
-            if (br.give_up) { status |= SRCB200_ILQR_ST_PD_GIVEUP; break; }
-            __syncwarp();
-            const double prev_cost = cost;
-            double alpha = cf.alpha0;
-            bool improved = false, failed = false;
-            double cost_t = cost, alpha_acc = 0.0;
-            while (!improved && !failed) {
-                improved = true;
-                cost_t = fwd_fast<M>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
-                ++trials;
-                double dc = 0.0;
-                const double a2 = __dmul_rn(__dmul_rn(alpha, alpha), 0.5);
-                for (int t = 0; t < N; ++t)
-                    dc = __dadd_rn(dc, __dadd_rn(__dmul_rn(alpha, ab[2 * t]), __dmul_rn(a2, ab[2 * t + 1])));
-                alpha_acc = alpha;
-                if (cf.do_linesearch) {
-                    const double ratio = __ddiv_rn(__dsub_rn(cost_t, prev_cost), dc);
-                    if (ratio <= cf.improv_lb || ratio > cf.improv_ub) {
-                        alpha = __dmul_rn(cf.alpha_scaling, alpha);
-                        improved = false;
-                        if (alpha < cf.alpha_min) {
-                            rho_update(cf, true, rho, drho);
-                            rho = __dadd_rn(rho, cf.rho_increase_fp);
-                            failed = true;
+            if (br.give_up) {
+                status |= SRCB200_ILQR_ST_PD_GIVEUP;
+                stop = true;
+            } else {
+                __syncwarp();
+                const double prev_cost = cost;
+                double alpha = cf.alpha0;
+                bool improved = false, failed = false;
+                double cost_t = cost, alpha_acc = 0.0;
+                while (!improved && !failed) {
+                    improved = true;
+                    cost_t = fwd_fast<M>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
+                    ++trials;
+                    double dc = 0.0;
+                    const double a2 = __dmul_rn(__dmul_rn(alpha, alpha), 0.5);
+                    for (int t = 0; t < N; ++t)
+                        dc = __dadd_rn(dc, __dadd_rn(__dmul_rn(alpha, ab[2 * t]), __dmul_rn(a2, ab[2 * t + 1])));
+                    alpha_acc = alpha;
+                    if (cf.do_linesearch) {
+                        const double ratio = __ddiv_rn(__dsub_rn(cost_t, prev_cost), dc);
+                        if (ratio <= cf.improv_lb || ratio > cf.improv_ub) {
+                            alpha = __dmul_rn(cf.alpha_scaling, alpha);
+                            improved = false;
+                            if (alpha < cf.alpha_min) {
+                                rho_update(cf, true, rho, drho);
+                                rho = __dadd_rn(rho, cf.rho_increase_fp);
+                                failed = true;
+                            }
                         }
                     }
                 }
+                if (!failed) {
+                    cur ^= 1;
+                    cost = cost_t;
+                    const double dJ = __dsub_rn(prev_cost, cost);
+                    conv = (dJ < cf.epsilon) && (dJ >= 0.0);
+                    if (conv) status |= SRCB200_ILQR_ST_CONVERGED;
+                    fails = 0;
+                } else {
+                    ++fails;
+                    if (fails >= cf.counter_limit) { conv = true; status |= SRCB200_ILQR_ST_ABANDONED; }
+                }
+                if (trace && lane == 0) {
+                    trace[it * 4 + 0] = cost;
+                    trace[it * 4 + 1] = failed ? 0.0 : alpha_acc;
+                    trace[it * 4 + 2] = rho_bwd;
+                    trace[it * 4 + 3] = (double)restarts;
+                }
+                ++it;
+                if (!isfinite(cost)) { status |= SRCB200_ILQR_ST_NONFINITE; stop = true; }
             }
-            if (!failed) {
-                cur ^= 1;
-                cost = cost_t;
-                const double dJ = __dsub_rn(prev_cost, cost);
-                conv = (dJ < cf.epsilon) && (dJ >= 0.0);
-                if (conv) status |= SRCB200_ILQR_ST_CONVERGED;
-                fails = 0;
-            } else {
-                ++fails;
-                if (fails >= cf.counter_limit) { conv = true; status |= SRCB200_ILQR_ST_ABANDONED; }
-            }
-            if (trace && lane == 0) {
-                trace[it * 4 + 0] = cost;
-                trace[it * 4 + 1] = failed ? 0.0 : alpha_acc;
-                trace[it * 4 + 2] = rho_bwd;
-                trace[it * 4 + 3] = (double)restarts;
-            }
-            ++it;
-            if (!isfinite(cost)) { status |= SRCB200_ILQR_ST_NONFINITE; break; }
         }
-        if (!conv && it > cf.max_iter) status |= SRCB200_ILQR_ST_MAXITER;
+        if (!conv && !stop && it <= cf.max_iter) {
+            // not finished: save the state and hand the problem to whichever warp is free next
+            __syncwarp();
+            if (lane == 0) {
+                sv[0] = rho; sv[1] = drho; sv[2] = cost;
+                svi[0] = fails; svi[1] = cur; svi[2] = status; svi[3] = trials; svi[4] = it; svi[5] = 0x5ca1ab1e;
+            }
+            queue_push(a.work_counter, a.queue_cap, lane, (int)b);
+            continue;
+        }
+        if (!conv && !stop && it > cf.max_iter) status |= SRCB200_ILQR_ST_MAXITER;
 
         __syncwarp();
         const Rec fin = rec_at(wsb + (cur ? a.L.rec : 0), a.L);
@@ -880,6 +944,8 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
             a.oiter[b] = it;
             a.ostatus[b] = status;
             if (a.otrials) a.otrials[b] = trials;
+            __threadfence();
+            atomicSub(a.work_counter + 2, 1);
         }
         __syncwarp();
     }
@@ -1291,14 +1357,17 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
     *handled = false;
     const char* env = getenv("SRCB200_ILQR_GENERIC");
     if (env && env[0] == '1') return 0;
-    if (!(M.n == 6 && M.nz == 6 && M.order == 3 && M.nfeat == fast::NFEAT && (M.m == 4 || M.m == 8) && a.gn && !a.index_lin))
+    if (!(M.n == 6 && M.nz == 6 && M.order == 3 && M.nfeat == fast::NFEAT && (M.m == 4 || M.m == 8) && a.gn && !a.index_lin) || a.batch > (1LL << 29))
         return 0;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ctas = (a.batch + fast::WARPS - 1) / fast::WARPS;
-    const int grid = (int)(ctas < 2LL * sms ? ctas : 2LL * sms);   // persistent: 2 CTAs (16 warps) per SM
-    SRCB_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
+    int grid = (int)(ctas < 2LL * sms ? ctas : 2LL * sms);   // persistent: 2 CTAs (16 warps) per SM
+    if (grid * fast::WARPS > kIlqrQueueWaiters) grid = kIlqrQueueWaiters / fast::WARPS;
+    fast::ilqr_queue_init_kernel<<<(a.queue_cap + 255) / 256, 256, 0, st>>>(a.work_counter, a.queue_cap, (int)a.batch, a.ws,
+                                                                                 a.L.total, a.L.state);
+    SRCB_LAUNCH_CHECK("ilqr_queue_init_kernel");
     if (M.m == 8) {
         SRCB_CUDA(cudaFuncSetAttribute(fast::ilqr_ssm_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
         fast::ilqr_ssm_fast_kernel<8><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, a);

@@ -763,10 +763,11 @@ static int solve_impl(const typename MP::Dev& M, const srcb200_ilqr_config* cfg,
     if (int e = fill_args<MP>(M, cfg, pr, a, smem)) return e;
     if (!res || !res->x || !res->u || !res->K || !res->cost || !res->iterations || !res->status)
         return fail(SRCB200_E_NULL, "ilqr: result x/u/K/cost/iterations/status must be provided");
-    if (!ws || ws_bytes < sizeof(double) * (size_t)a.L.total * (size_t)a.batch + 256)
+    if (!ws || ws_bytes < sizeof(double) * (size_t)a.L.total * (size_t)a.batch + ilqr_queue_bytes(a.batch))
         return fail(SRCB200_E_WORKSPACE, "ilqr: workspace too small (%zu < %zu)", ws_bytes,
-                    sizeof(double) * (size_t)a.L.total * (size_t)a.batch + 256);
+                    sizeof(double) * (size_t)a.L.total * (size_t)a.batch + ilqr_queue_bytes(a.batch));
     a.work_counter = reinterpret_cast<int*>((double*)ws + (size_t)a.L.total * (size_t)a.batch);
+    a.queue_cap = (int)ilqr_queue_cap(a.batch);
     a.ox = res->x; a.ou = res->u; a.oK = res->K; a.ocost = res->cost; a.ocost0 = res->cost0; a.orho = res->rho;
     a.otrace = res->trace; a.oiter = res->iterations; a.ostatus = res->status; a.otrials = res->trials;
     a.ws = (double*)ws;

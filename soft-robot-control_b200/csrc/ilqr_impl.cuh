@@ -25,6 +25,7 @@ struct LinRef {            // where the linearisation of one step lives (shared 
 struct SsmPolicy {
     using Dev = SsmDev;
     static constexpr int NT = 32;
+    static constexpr int CN = 0, CM = 0, CNZ = 0;      // compile-time dimensions (0 = run time)
     __host__ __device__ static int n(const Dev& M) { return M.n; }
     __host__ __device__ static int m(const Dev& M) { return M.m; }
     __host__ __device__ static int nz(const Dev& M) { return M.nz; }
@@ -44,9 +45,13 @@ struct SsmPolicy {
     __device__ static LinRef bank(const Dev&, int) { return LinRef{nullptr, nullptr, nullptr}; }
 };
 
-struct TpwlPolicy {
+// CN/CM/CNZ > 0 fix n/m/nz at compile time (the Diamond shape gets its own instantiation: constant strides, unrolled
+// m-loops, divisions by constants); 0 keeps them run-time values.
+template <int CN_, int CM_, int CNZ_>
+struct TpwlPolicyT {
     using Dev = TpwlDev;
-    static constexpr int NT = 256;
+    static constexpr int NT = 512;
+    static constexpr int CN = CN_, CM = CM_, CNZ = CNZ_;
     __host__ __device__ static int n(const Dev& M) { return M.n; }
     __host__ __device__ static int m(const Dev& M) { return M.m; }
     __host__ __device__ static int nz(const Dev& M) { return M.nz; }
@@ -64,10 +69,10 @@ struct TpwlPolicy {
                                 double* sd, double* sz, double* sH, double* scr, LinRef& lin, int& idx) {
         __shared__ double red_d[NT / 32];
         __shared__ int red_i[NT / 32];
-        const int n = M.n, m = M.m, tid = threadIdx.x;
+        const int n = CN_ ? CN_ : M.n, m = CM_ ? CM_ : M.m, tid = threadIdx.x;
         (void)su; (void)sH;
         // z = H x + z_ref (tpwl.py:121-122)
-        for (int i = tid; i < M.nz; i += NT) {
+        for (int i = tid; i < (CNZ_ ? CNZ_ : M.nz); i += NT) {
             double acc = 0.0;
             for (int k = 0; k < n; ++k) acc = fma(M.H[i * n + k], sx[k], acc);
             sz[i] = __dadd_rn(acc, M.zref[i]);
@@ -134,17 +139,21 @@ struct TpwlPolicy {
         lin.A = sA; lin.B = sB; lin.d = sd;
     }
     __device__ static void observe(const Dev& M, const double* sx, double* sz, double*, double*) {
-        for (int i = threadIdx.x; i < M.nz; i += NT) {
+        const int n = CN_ ? CN_ : M.n;
+        for (int i = threadIdx.x; i < (CNZ_ ? CNZ_ : M.nz); i += NT) {
             double acc = 0.0;
-            for (int k = 0; k < M.n; ++k) acc = fma(M.H[i * M.n + k], sx[k], acc);
+            for (int k = 0; k < n; ++k) acc = fma(M.H[i * n + k], sx[k], acc);
             sz[i] = __dadd_rn(acc, M.zref[i]);
         }
         __syncthreads();
     }
     __device__ static LinRef bank(const Dev& M, int p) {
-        return LinRef{M.A + (long long)p * M.n * M.n, M.B + (long long)p * M.n * M.m, M.d + (long long)p * M.n};
+        const int n = CN_ ? CN_ : M.n, m = CM_ ? CM_ : M.m;
+        return LinRef{M.A + (long long)p * n * n, M.B + (long long)p * n * m, M.d + (long long)p * n};
     }
 };
+using TpwlPolicy = TpwlPolicyT<0, 0, 0>;
+using TpwlPolicyDiamond = TpwlPolicyT<72, 4, 6>;        // n = 72 (r = 36), m = 4, n_z = 6
 
 // shared-memory plan (doubles); forward and backward phases alias the same region after the common header
 struct Smem {
@@ -221,7 +230,7 @@ __device__ double fwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const S
                            const double* __restrict__ ztar, const double* __restrict__ ulast,
                            double* __restrict__ dout) {
     constexpr int NT = MP::NT;
-    const int n = a.n, m = a.m, nz = a.nz, N = a.N, tid = threadIdx.x;
+    const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     double* sx = sm + S.x;  double* sxn = sm + S.xn;  double* su = sm + S.u;  double* sup = sm + S.uprev;
     double* sdx = sm + S.dx; double* sz = sm + S.z;   double* se = sm + S.e;  double* sA = sm + S.A;
     double* sB = sm + S.B;  double* sd = sm + S.d;    double* sH = sm + S.H;  double* sQe = sm + S.Qe;
@@ -328,7 +337,7 @@ __device__ int bwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const Smem
                         double* __restrict__ ab, double* __restrict__ Quout, double* __restrict__ Quuout,
                         double& rho, double& drho, bool& give_up, double* __restrict__ cxx_global) {
     constexpr int NT = MP::NT;
-    const int n = a.n, m = a.m, nz = a.nz, N = a.N, tid = threadIdx.x;
+    const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     double* P = sm + S.P;      double* p = sm + S.p;      double* AtP = sm + S.AtP;   double* BtP = sm + S.BtP;
     double* BtPr = sm + S.BtPr; double* Qux = sm + S.Qux; double* Quxt = sm + S.Quxt; double* Quu = sm + S.Quu;
     double* Quut = sm + S.Quut; double* Lc = sm + S.Lc;   double* LU = sm + S.LU;     double* inv = sm + S.inv;
@@ -522,7 +531,7 @@ __device__ int bwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const Smem
 template <class MP>
 __device__ __forceinline__ void load_costs(const IlqrArgs& a, const Smem& S, double* sm) {
     constexpr int NT = MP::NT;
-    const int n = a.n, m = a.m, nz = a.nz, tid = threadIdx.x;
+    const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, tid = threadIdx.x;
     for (int e = tid; e < nz * nz; e += NT) { sm[S.Qs + e] = a.Q[e]; sm[S.Qfs + e] = a.Qf[e]; }
     for (int e = tid; e < m * m; e += NT) sm[S.Rs + e] = a.R[e];
     for (int e = tid; e < nz * n; e += NT) sm[S.Hcs + e] = a.Hc ? a.Hc[e] : 0.0;
@@ -534,8 +543,8 @@ __global__ void __launch_bounds__(MP::NT)
 ilqr_solve_kernel(typename MP::Dev M, IlqrArgs a) {
     constexpr int NT = MP::NT;
     extern __shared__ __align__(16) double sm[];
-    const Smem S = make_smem(a.n, a.m, a.nz, a.model_scratch, a.gn);
-    const int n = a.n, m = a.m, nz = a.nz, N = a.N, tid = threadIdx.x;
+    const Smem S = make_smem(MP::CN ? MP::CN : a.n, MP::CM ? MP::CM : a.m, MP::CNZ ? MP::CNZ : a.nz, a.model_scratch, a.gn);
+    const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     const srcb200_ilqr_config& c = a.cfg;
     load_costs<MP>(a, S, sm);
 
@@ -645,8 +654,8 @@ ilqr_forward_kernel(typename MP::Dev M, IlqrArgs a, const double* __restrict__ x
                     double* __restrict__ dout) {
     constexpr int NT = MP::NT;
     extern __shared__ __align__(16) double sm[];
-    const Smem S = make_smem(a.n, a.m, a.nz, a.model_scratch, a.gn);
-    const int n = a.n, m = a.m, nz = a.nz, N = a.N, tid = threadIdx.x;
+    const Smem S = make_smem(MP::CN ? MP::CN : a.n, MP::CM ? MP::CM : a.m, MP::CNZ ? MP::CNZ : a.nz, a.model_scratch, a.gn);
+    const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     load_costs<MP>(a, S, sm);
     for (long long b = blockIdx.x; b < a.batch; b += gridDim.x) {
         double* wsb = a.ws + b * a.L.total;
@@ -680,8 +689,8 @@ ilqr_backward_kernel(typename MP::Dev M, IlqrArgs a, const double* __restrict__ 
                      double* __restrict__ drho_io, int* __restrict__ restarts_o) {
     constexpr int NT = MP::NT;
     extern __shared__ __align__(16) double sm[];
-    const Smem S = make_smem(a.n, a.m, a.nz, a.model_scratch, a.gn);
-    const int n = a.n, m = a.m, nz = a.nz, N = a.N, tid = threadIdx.x;
+    const Smem S = make_smem(MP::CN ? MP::CN : a.n, MP::CM ? MP::CM : a.m, MP::CNZ ? MP::CNZ : a.nz, a.model_scratch, a.gn);
+    const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     load_costs<MP>(a, S, sm);
     for (long long b = blockIdx.x; b < a.batch; b += gridDim.x) {
         double* wsb = a.ws + b * a.L.total;

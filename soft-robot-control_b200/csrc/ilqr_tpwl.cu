@@ -1,9 +1,16 @@
 // ilqr_tpwl.cu -- generic iLQR kernels instantiated for the TPWL bank policy (see ilqr_impl.cuh).
+#include <cstdlib>
 #include "ilqr_impl.cuh"
 
 namespace srcb {
 int ilqr_solve_tpwl(const TpwlDev& M, const srcb200_ilqr_config* cfg, const srcb200_ilqr_problem* pr, const srcb200_ilqr_result* res,
-                    void* ws, size_t ws_bytes, cudaStream_t st) { return solve_impl<TpwlPolicy>(M, cfg, pr, res, ws, ws_bytes, st); }
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
+    // the Diamond shape (n = 72, m = 4, n_z = 6) runs the instantiation with compile-time dimensions
+    const char* env = getenv("SRCB200_ILQR_GENERIC");
+    if (M.n == 72 && M.m == 4 && M.nz == 6 && !(env && env[0] == '1'))
+        return solve_impl<TpwlPolicyDiamond>(M, cfg, pr, res, ws, ws_bytes, st);
+    return solve_impl<TpwlPolicy>(M, cfg, pr, res, ws, ws_bytes, st);
+}
 int ilqr_forward_tpwl(const TpwlDev& M, const srcb200_ilqr_config* cfg, const srcb200_ilqr_problem* pr, const double* xp,
                       const double* up, double alpha, const double* K, const double* k, double* x, double* u, double* cost,
                       double* A, double* B, double* d, void* ws, size_t ws_bytes, cudaStream_t st) {

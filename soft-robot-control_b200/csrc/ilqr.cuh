@@ -46,6 +46,34 @@ __device__ inline Rec rec_at(double* base, const Layout& L) {
     return r;
 }
 
+// Shared-memory plan of the TPWL nearest-neighbour forward pass (ilqr_fwd_tpwl.cuh), in doubles from its base
+struct FwdNNPlan {
+    int pre0, pre1, PRE, Acur, dh, cand, red, misc, qf, vf, end;
+    int screen;                 // 1: FP32 screening banks are resident
+};
+constexpr int kFwdNNCandCap = 512;
+
+__host__ __device__ inline FwdNNPlan make_fwdnn(int n, int m, int nz, int P, int r, bool useq, bool usev, int nt) {
+    FwdNNPlan F;
+    int o = 0;
+    auto take = [&o](int cnt) { const int at = o; o += (cnt + 1) & ~1; return at; };
+    F.PRE = (n + 2 * m + m * n + nz + 1) & ~1;
+    F.pre0 = take(F.PRE);
+    F.pre1 = take(F.PRE);
+    F.Acur = take(n * n + n * m + n);
+    F.dh = take((P + 1) / 2);               // P floats
+    F.cand = take(kFwdNNCandCap / 2 + 2);   // ints: [count, pad, candidates...]
+    F.red = take(2 * (nt / 32) + 2);
+    F.misc = take(16);
+    const int nb = (useq ? 1 : 0) + (usev ? 1 : 0);
+    const long long bank = ((long long)P * r + 1) / 2;          // doubles per FP32 bank
+    F.screen = (nb > 0 && nb * bank * 8 <= 150 * 1024) ? 1 : 0;
+    F.qf = o; if (F.screen && useq) o += (int)((bank + 1) & ~1LL);
+    F.vf = o; if (F.screen && usev) o += (int)((bank + 1) & ~1LL);
+    F.end = o;
+    return F;
+}
+
 // Task queue of the fast kernel behind the per-problem scratch: 64 ints of counters + the slot ring.  The ring must be
 // longer than (problems that can be queued) + (warps that can wait on a ticket at the same time), see ilqr_fast.cu.
 constexpr int kIlqrQueueWaiters = 8192;

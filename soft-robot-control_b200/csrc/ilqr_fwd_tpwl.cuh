@@ -1,0 +1,310 @@
+// ilqr_fwd_tpwl.cuh -- forward rollout of the iLQR line search (sofacontrol/lqr/ilqr.py:117-175) specialised for a
+// TPWL model in nearest-neighbour mode on a bank that needs no per-step discretisation (tpwl.py:160-168, 236-244:
+// the linearisation of a step is an index into the bank).  Included by ilqr_impl.cuh; one CTA of NT threads per problem.
+//
+// What makes the generic step slow on this model is (1) the exact nearest-point search streaming the whole FP64
+// point bank from L2 every step and (2) a chain of small dependent global-memory round trips.  Here
+//   * the search is a two-stage EXACT search: an FP32 copy of the point bank lives in shared memory for the whole
+//     pass; every step computes FP32 distances d^ with a rigorous error bound eps (below), keeps the candidates
+//     {p : d^_p - eps_p <= min_p' (d^_p' + eps_p')} -- the FP64 argmin is provably among them -- and evaluates only
+//     those with the bit-exact numpy-order FP64 distance (tpwl.cuh).  The selected index is identical to the full
+//     search, ties included (first occurrence).  If the bank does not fit or anything is off (no candidate, NaN,
+//     candidate overflow) the step falls back to the full FP64 search.
+//   * the inputs of step t+1 (nominal x/u, gains K/k, target) are cp.async-prefetched into shared memory during
+//     step t, and [A | B | d] of the current bank index stays in shared memory while the index does not change.
+//
+// Error bound of the screening distance (u = 2^-24, a_j = Q_pj - q_j exact, a^_j its FP32 evaluation from rounded
+// operands): ||a^ - a|| <= u (1+u) (||Q_p|| + ||q||) + u ||a||;  the FP32 sum of 36 squares and the square root add at
+// most 20 u ||a^||.  eps_p = 2^-24 (32 d^_p + 2 (max_p ||Q_p|| + ||q||)) + 1e-14 d^_p covers both with margin.
+#pragma once
+
+namespace srcb {
+
+// FP32 screening distance of point p: sqrt(sum_j (bank[j*P+p] - x[j])^2), bank and x rounded to FP32
+__device__ __forceinline__ void screen2(const float* __restrict__ bank, int P, int r, const double* __restrict__ x,
+                                        int p0, int p1, bool has1, float& d0, float& d1) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < r; ++j) {
+        const float xj = (float)x[j];
+        const float a0 = bank[j * P + p0] - xj;
+        s0 = fmaf(a0, a0, s0);
+        if (has1) {
+            const float a1 = bank[j * P + p1] - xj;
+            s1 = fmaf(a1, a1, s1);
+        }
+    }
+    d0 = sqrtf(s0);
+    d1 = sqrtf(s1);
+}
+
+template <class MP>
+__device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Smem& S, double* sm,
+                                   const double* __restrict__ nx, const double* __restrict__ nu, double alpha,
+                                   const double* __restrict__ K, const double* __restrict__ k, const Rec& tr,
+                                   const double* __restrict__ ztar, const double* __restrict__ ulast,
+                                   double* __restrict__ dout) {
+    constexpr int NT = MP::NT;
+    constexpr int NW = NT / 32;
+    const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = M.P, r = n / 2;
+    const bool useq = M.wq != 0.0, usev = M.wv != 0.0;
+    const FwdNNPlan F = make_fwdnn(n, m, nz, P, r, useq, usev, NT);
+    double* base = sm + S.mscr;
+    double* sxa = sm + S.x;   double* sxb = sm + S.xn;  double* su = sm + S.u;   double* sup = sm + S.uprev;
+    double* sz = sm + S.z;    double* se = sm + S.e;    double* sQe = sm + S.Qe; double* sRdu = sm + S.Rdu;
+    const double* sQ = sm + S.Qs; const double* sR = sm + S.Rs; const double* sQf = sm + S.Qfs;
+    const double* sH = sm + S.Hcs;                       // constant output matrix H (n_z x n), staged by load_costs
+    double* scal = sm + S.scal;
+    double* Acur = base + F.Acur;
+    float* dh = reinterpret_cast<float*>(base + F.dh);
+    int* cand = reinterpret_cast<int*>(base + F.cand);
+    double* red_d = base + F.red;
+    int* red_i = reinterpret_cast<int*>(red_d + NW);
+    double* misc = base + F.misc;                        // [0] = bank norm bound, [1] = min upper bound
+    float* qf = reinterpret_cast<float*>(base + F.qf);
+    float* vf = reinterpret_cast<float*>(base + F.vf);
+    const bool screen = F.screen && M.wq >= 0.0 && M.wv >= 0.0;
+    const int PRE_NX = 0, PRE_NU = n, PRE_KK = n + m, PRE_K = n + 2 * m, PRE_ZT = n + 2 * m + m * n;
+
+    auto prefetch = [&](int t) {
+        double* dst = base + ((t & 1) ? F.pre1 : F.pre0);
+        for (int e = tid; e < n; e += NT) cp_async8(dst + PRE_NX + e, nx + (long long)t * n + e);
+        for (int e = tid; e < m; e += NT) cp_async8(dst + PRE_NU + e, nu + t * m + e);
+        if (k) for (int e = tid; e < m; e += NT) cp_async8(dst + PRE_KK + e, k + t * m + e);
+        if (K) for (int e = tid; e < m * n; e += NT) cp_async8(dst + PRE_K + e, K + (long long)t * m * n + e);
+        for (int e = tid; e < nz; e += NT) cp_async8(dst + PRE_ZT + e, ztar + t * nz + e);
+    };
+
+    // ---- pass prologue: state, FP32 banks + the largest weighted point norm (the error bound needs it)
+    for (int i = tid; i < n; i += NT) { sxa[i] = nx[i]; tr.x[i] = nx[i]; }
+    for (int i = tid; i < m; i += NT) sup[i] = ulast ? ulast[i] : 0.0;
+    if (N > 0) prefetch(0);
+    if (screen) {
+        double bmax = 0.0;
+        for (int p = tid; p < P; p += NT) {
+            double sq = 0.0, sv = 0.0;
+            for (int j = 0; j < r; ++j) {
+                if (useq) { const double v = M.qT[(size_t)j * P + p]; qf[j * P + p] = (float)v; sq = fma(v, v, sq); }
+                if (usev) { const double v = M.vT[(size_t)j * P + p]; vf[j * P + p] = (float)v; sv = fma(v, v, sv); }
+            }
+            bmax = fmax(bmax, M.wq * sqrt(sq) + M.wv * sqrt(sv));
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, off));
+        if (lane == 0) red_d[warp] = bmax;
+        __syncthreads();
+        if (tid == 0) {
+            double b2 = 0.0;
+            for (int w = 0; w < NW; ++w) b2 = fmax(b2, red_d[w]);
+            misc[0] = b2 * (1.0 + 1e-6);
+        }
+    }
+    __syncthreads();
+    const double bank_norm = screen ? misc[0] : 0.0;
+    const bool screen_ok = screen && isfinite(bank_norm) && bank_norm < 1e100;
+    int cur_idx = -1;
+    double cost = 0.0;                                   // meaningful on the cost warp's lane 0
+    double* sx = sxa;
+    double* sxn = sxb;
+
+    for (int t = 0; t < N; ++t) {
+        cp_async_wait_all();
+        __syncthreads();                                 // inputs of step t are in shared memory; sx is final
+        const double* pre = base + ((t & 1) ? F.pre1 : F.pre0);
+        if (t + 1 < N) prefetch(t + 1);
+        // ---- phase 1: u_t = u_prev + alpha k + K (x - x_prev) (ilqr.py:140) by warps 0..m-1, z_t = H x + z_ref
+        //      (tpwl.py:121-122) by warps m..m+nz-1 (one row each, lanes split the sum), screening by everybody
+        for (int row = warp; row < m + nz; row += NW) {
+            if (row < m) {
+                double acc = 0.0;
+                if (K) for (int j = lane; j < n; j += 32) acc = fma(pre[PRE_K + row * n + j], __dsub_rn(sx[j], pre[PRE_NX + j]), acc);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                if (lane == 0) {
+                    double v = pre[PRE_NU + row];
+                    if (k) v = __dadd_rn(v, __dmul_rn(alpha, pre[PRE_KK + row]));
+                    if (K) v = __dadd_rn(v, acc);
+                    su[row] = v;
+                    tr.u[t * m + row] = v;
+                }
+            } else {
+                const int i = row - m;
+                double acc = 0.0;
+                for (int j = lane; j < n; j += 32) acc = fma(sH[i * n + j], sx[j], acc);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                if (lane == 0) {
+                    const double z = __dadd_rn(acc, M.zref[i]);
+                    const double e = __dsub_rn(z, pre[PRE_ZT + i]);
+                    sz[i] = z;
+                    se[i] = e;
+                    tr.e[t * nz + i] = e;
+                }
+            }
+        }
+        int idx = -1;
+        bool full_search = !screen_ok;
+        if (screen_ok) {
+            double xq = 0.0, xv = 0.0;
+            for (int j = 0; j < r; ++j) {
+                if (usev) xv = fma(sx[j], sx[j], xv);
+                if (useq) xq = fma(sx[r + j], sx[r + j], xq);
+            }
+            const double slack = 2.0 * (bank_norm + M.wq * sqrt(xq) + M.wv * sqrt(xv));
+            const double u24 = 5.9604644775390625e-08;   // 2^-24
+            double ubmin = INFINITY;
+            for (int p0 = tid; p0 < P; p0 += 2 * NT) {
+                const int p1 = p0 + NT;
+                const bool has1 = p1 < P;
+                float q0 = 0.f, q1 = 0.f, v0 = 0.f, v1 = 0.f;
+                if (useq) screen2(qf, P, r, sx + r, p0, has1 ? p1 : p0, has1, q0, q1);
+                if (usev) screen2(vf, P, r, sx, p0, has1 ? p1 : p0, has1, v0, v1);
+                const double d0 = M.wq * (double)q0 + M.wv * (double)v0;
+                const double d1 = M.wq * (double)q1 + M.wv * (double)v1;
+                dh[p0] = (float)d0;
+                // (float)d rounds once more: fold that rounding into the bound by using the rounded value + 2 u d
+                const double e0 = u24 * (34.0 * d0 + slack) + 1e-14 * d0;
+                ubmin = fmin(ubmin, d0 + e0);
+                if (has1) {
+                    dh[p1] = (float)d1;
+                    const double e1 = u24 * (34.0 * d1 + slack) + 1e-14 * d1;
+                    ubmin = fmin(ubmin, d1 + e1);
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) ubmin = fmin(ubmin, __shfl_xor_sync(0xffffffffu, ubmin, off));
+            if (lane == 0) red_d[warp] = ubmin;
+            if (tid == 0) cand[0] = 0;
+            __syncthreads();
+            double U = red_d[0];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) U = fmin(U, red_d[w]);
+            // candidates: lower bound <= smallest upper bound
+            for (int p = tid; p < P; p += NT) {
+                const double d = (double)dh[p];
+                const double e = u24 * (36.0 * d + slack) + 1e-14 * d;
+                if (d - e <= U) {
+                    const int pos = atomicAdd(&cand[0], 1);
+                    if (pos < kFwdNNCandCap) cand[2 + pos] = p;
+                }
+            }
+            __syncthreads();
+            const int cnt = cand[0];
+            if (cnt >= 1 && cnt <= kFwdNNCandCap && cnt <= NT) {
+                double best = INFINITY;
+                int bi = 0x7fffffff;
+                if (tid < cnt) {
+                    const int p = cand[2 + tid];
+                    const double dd = tpwl_distance(M, sx, p);       // bit-exact numpy-order FP64 distance
+                    if (dd < best) { best = dd; bi = p; }
+                }
+                cta_argmin<NT>(best, bi, red_d, red_i);
+                if (bi == 0x7fffffff) full_search = true;            // NaN distances: let the full search decide
+                else idx = bi;
+            } else {
+                full_search = true;
+            }
+        } else {
+            __syncthreads();
+        }
+        if (full_search) idx = tpwl_nearest<NT>(M, sx, nullptr, red_d, red_i, nullptr);
+        // ---- phase 2: the linearisation of this step: [A | B | d] of bank entry idx (kept while idx is unchanged)
+        if (idx != cur_idx) {
+            const LinRef b = MP::bank(M, idx);
+            for (int e = tid; e < n * n; e += NT) Acur[e] = b.A[e];
+            for (int e = tid; e < n * m; e += NT) Acur[n * n + e] = b.B[e];
+            for (int e = tid; e < n; e += NT) Acur[n * n + n * m + e] = b.d[e];
+            cur_idx = idx;
+        }
+        __syncthreads();                                  // su, se, Acur ready
+        if (tid == 0) tr.idx[t] = idx;
+        if (dout) for (int e = tid; e < n; e += NT) dout[(long long)t * n + e] = Acur[n * n + n * m + e];
+        // ---- step cost (ilqr.py:168-175) on the last warp: .5 e^T Q e + .5 du^T R du, row vector times matrix first
+        if (warp == NW - 1) {
+            double du = 0.0;
+            if (lane < m) {
+                du = a.cfg.include_input_var_constraint ? __dsub_rn(su[lane], sup[lane]) : su[lane];
+            }
+            __syncwarp();
+            if (lane < m) sup[lane] = du;
+            __syncwarp();
+            if (lane < nz) {
+                double acc = 0.0;
+                for (int i = 0; i < nz; ++i) acc = fma(se[i], sQ[i * nz + lane], acc);
+                sQe[lane] = acc;
+            }
+            if (lane < m) {
+                double acc = 0.0;
+                for (int i = 0; i < m; ++i) acc = fma(sup[i], sR[i * m + lane], acc);
+                sRdu[lane] = acc;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int j = 0; j < nz; ++j) s1 = fma(sQe[j], se[j], s1);
+                for (int j = 0; j < m; ++j) s2 = fma(sRdu[j], sup[j], s2);
+                cost = __dadd_rn(cost, __dadd_rn(__dmul_rn(0.5, s1), __dmul_rn(0.5, s2)));
+            }
+            __syncwarp();
+            if (lane < m) sup[lane] = su[lane];           // u_{t-1} of the next step
+        }
+        // ---- x_{t+1} = (A x + B u) + d  (tpwl.py:231-234): one row per warp at a time, lanes split the sums
+        {
+            const double* A = Acur;
+            const double* B = Acur + n * n;
+            const double* d = Acur + n * n + n * m;
+            for (int i = warp; i < n; i += NW) {
+                double ax = 0.0, bu = 0.0;
+                for (int kk = lane; kk < n; kk += 32) ax = fma(A[i * n + kk], sx[kk], ax);
+                for (int kk = lane; kk < m; kk += 32) bu = fma(B[i * m + kk], su[kk], bu);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    ax += __shfl_xor_sync(0xffffffffu, ax, off);
+                    bu += __shfl_xor_sync(0xffffffffu, bu, off);
+                }
+                if (lane == 0) {
+                    const double v = __dadd_rn(__dadd_rn(ax, bu), d[i]);
+                    sxn[i] = v;
+                    tr.x[(long long)(t + 1) * n + i] = v;
+                }
+            }
+        }
+        double* tmp = sx; sx = sxn; sxn = tmp;
+    }
+    __syncthreads();
+    // ---- terminal cost (ilqr.py:164-166)
+    for (int row = warp; row < nz; row += NW) {
+        double acc = 0.0;
+        for (int j = lane; j < n; j += 32) acc = fma(sH[row * n + j], sx[j], acc);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) {
+            const double e = __dsub_rn(__dadd_rn(acc, M.zref[row]), ztar[N * nz + row]);
+            se[row] = e;
+            tr.e[N * nz + row] = e;
+        }
+    }
+    __syncthreads();
+    if (warp == NW - 1) {
+        if (lane < nz) {
+            double acc = 0.0;
+            for (int i = 0; i < nz; ++i) acc = fma(se[i], sQf[i * nz + lane], acc);
+            sQe[lane] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double s1 = 0.0;
+            for (int j = 0; j < nz; ++j) s1 = fma(sQe[j], se[j], s1);
+            cost = __dadd_rn(cost, __dmul_rn(0.5, s1));
+            scal[0] = cost;
+        }
+    }
+    __syncthreads();
+    cost = scal[0];
+    __syncthreads();
+    return cost;
+}
+
+}  // namespace srcb

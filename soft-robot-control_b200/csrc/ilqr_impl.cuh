@@ -60,6 +60,8 @@ struct TpwlPolicyT {
         return M.method == SRCB200_TPWL_NN && (M.discr == SRCB200_DISCR_NONE || dt < 0.0);
     }
     __host__ __device__ static int scratch_doubles(const Dev& M, double dt) {
+        if (index_lin(M, dt))       // the specialised forward pass (ilqr_fwd_tpwl.cuh) lays its buffers out here
+            return make_fwdnn(M.n, M.m, M.nz, M.P, M.n / 2, M.wq != 0.0, M.wv != 0.0, NT).end + 8;
         int s = 0;
         if (M.method == SRCB200_TPWL_WEIGHTING) s += M.P;
         if (!index_lin(M, dt)) s += discretize_scratch_doubles(M.n, M.m);
@@ -161,7 +163,10 @@ struct Smem {
     int P, p, AtP, BtP, BtPr, Qux, Quxt, Quu, Quut, Lc, LU, inv, K, k, KQ, Qx, Qu, cx, cu, T1, cxx, T1f, bwd_end;
     int Qs, Rs, Qfs, Hcs, scal, ints, total;
 };
-__host__ __device__ inline Smem make_smem(int n, int m, int nz, int mscr, bool gn) {
+__host__ __device__ inline int big_plan_end(int n, int m, int nz, int base);     // ilqr_bwd_big.cuh
+// big: the backward pass runs bwd_pass_big (ilqr_bwd_big.cuh), whose shared-memory plan replaces the one below
+__host__ __device__ inline bool use_big_bwd(int nt, int n, bool gn) { return nt > 32 && n >= 16 && !gn; }
+__host__ __device__ inline Smem make_smem(int n, int m, int nz, int mscr, bool gn, bool big = false, bool index_lin = false) {
     Smem S;
     int o = 0;
     // persistent header: cost matrices + constant H + scalars
@@ -174,7 +179,9 @@ __host__ __device__ inline Smem make_smem(int n, int m, int nz, int mscr, bool g
     const int base = o;
     // forward
     S.x = o; o += n;  S.xn = o; o += n;  S.u = o; o += m;  S.uprev = o; o += m;  S.dx = o; o += n;
-    S.z = o; o += nz; S.e = o; o += nz;  S.A = o; o += n * n; S.B = o; o += n * m; S.d = o; o += n;
+    S.z = o; o += nz; S.e = o; o += nz;
+    // index_lin: a step's linearisation is a pointer into the bank, no shared-memory copy
+    S.A = o; o += index_lin ? 0 : n * n; S.B = o; o += index_lin ? 0 : n * m; S.d = o; o += index_lin ? 0 : n;
     S.H = o; o += nz * n; S.Qe = o; o += nz; S.Rdu = o; o += m; S.mscr = o; o += mscr;
     S.fwd_end = o;
     // backward (aliases the forward region)
@@ -184,7 +191,7 @@ __host__ __device__ inline Smem make_smem(int n, int m, int nz, int mscr, bool g
     S.Lc = o; o += m * m;  S.LU = o; o += m * m;  S.inv = o; o += m * m;  S.K = o; o += m * n;  S.k = o; o += m;
     S.KQ = o; o += n * m;  S.Qx = o; o += n;  S.Qu = o; o += m;  S.cx = o; o += n;  S.cu = o; o += m;
     S.T1 = o; o += n * nz; S.cxx = o; o += gn ? n * n : 0; S.T1f = o; o += n * nz;
-    S.bwd_end = o;
+    S.bwd_end = big ? big_plan_end(n, m, nz, base) : o;
     // the backward pass also needs H_t / e_t / u rows staged: reuse tail
     S.total = (S.fwd_end > S.bwd_end ? S.fwd_end : S.bwd_end) + nz * n + nz + 2 * m + 4;
     return S;
@@ -218,6 +225,11 @@ __device__ __forceinline__ void affine_step(const LinRef& lin, const double* __r
     cta_sync<NT>();
 }
 
+}  // namespace srcb
+#include "ilqr_bwd_big.cuh"
+#include "ilqr_fwd_tpwl.cuh"
+namespace srcb {
+
 // ---------------------------------------------------------------------------------------------------------------
 // Forward pass (ilqr.py:117-162).  nom: nominal trajectory (x_prev, u_prev); K/k may be nullptr (zeros).
 // Writes the trial record `tr` (x, u, e = z - z*, H_t, A_t/B_t or idx_t) and returns the cost to every thread.
@@ -230,6 +242,9 @@ __device__ double fwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const S
                            const double* __restrict__ ztar, const double* __restrict__ ulast,
                            double* __restrict__ dout) {
     constexpr int NT = MP::NT;
+    if constexpr (MP::NT > 32) {
+        if (a.index_lin && !a.gn) return fwd_pass_tpwl_nn<MP>(M, a, S, sm, nx, nu, alpha, K, k, tr, ztar, ulast, dout);
+    }
     const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     double* sx = sm + S.x;  double* sxn = sm + S.xn;  double* su = sm + S.u;  double* sup = sm + S.uprev;
     double* sdx = sm + S.dx; double* sz = sm + S.z;   double* se = sm + S.e;  double* sA = sm + S.A;
@@ -337,6 +352,11 @@ __device__ int bwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const Smem
                         double* __restrict__ ab, double* __restrict__ Quout, double* __restrict__ Quuout,
                         double& rho, double& drho, bool& give_up, double* __restrict__ cxx_global) {
     constexpr int NT = MP::NT;
+    if constexpr (MP::NT > 32) {
+        if (use_big_bwd(NT, MP::CN ? MP::CN : a.n, a.gn))
+            return bwd_pass_big<MP>(M, a, S, sm, rc, Adense, Bdense, ulast, Kout, kout, ab, Quout, Quuout, rho, drho,
+                                    give_up, cxx_global);
+    }
     const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     double* P = sm + S.P;      double* p = sm + S.p;      double* AtP = sm + S.AtP;   double* BtP = sm + S.BtP;
     double* BtPr = sm + S.BtPr; double* Qux = sm + S.Qux; double* Quxt = sm + S.Quxt; double* Quu = sm + S.Quu;
@@ -539,11 +559,12 @@ __device__ __forceinline__ void load_costs(const IlqrArgs& a, const Smem& S, dou
 }
 
 template <class MP>
-__global__ void __launch_bounds__(MP::NT)
+__global__ void __launch_bounds__(MP::NT, 1)
 ilqr_solve_kernel(typename MP::Dev M, IlqrArgs a) {
     constexpr int NT = MP::NT;
     extern __shared__ __align__(16) double sm[];
-    const Smem S = make_smem(MP::CN ? MP::CN : a.n, MP::CM ? MP::CM : a.m, MP::CNZ ? MP::CNZ : a.nz, a.model_scratch, a.gn);
+    const Smem S = make_smem(MP::CN ? MP::CN : a.n, MP::CM ? MP::CM : a.m, MP::CNZ ? MP::CNZ : a.nz, a.model_scratch, a.gn,
+                              use_big_bwd(MP::NT, MP::CN ? MP::CN : a.n, a.gn), a.index_lin != 0);
     const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     const srcb200_ilqr_config& c = a.cfg;
     load_costs<MP>(a, S, sm);
@@ -647,14 +668,15 @@ ilqr_solve_kernel(typename MP::Dev M, IlqrArgs a) {
 
 // standalone forward pass (srcb200_ilqr_forward_pass)
 template <class MP>
-__global__ void __launch_bounds__(MP::NT)
+__global__ void __launch_bounds__(MP::NT, 1)
 ilqr_forward_kernel(typename MP::Dev M, IlqrArgs a, const double* __restrict__ xprev, const double* __restrict__ uprev,
                     double alpha, const double* __restrict__ K, const double* __restrict__ k, double* __restrict__ xo,
                     double* __restrict__ uo, double* __restrict__ costo, double* __restrict__ Ao, double* __restrict__ Bo,
                     double* __restrict__ dout) {
     constexpr int NT = MP::NT;
     extern __shared__ __align__(16) double sm[];
-    const Smem S = make_smem(MP::CN ? MP::CN : a.n, MP::CM ? MP::CM : a.m, MP::CNZ ? MP::CNZ : a.nz, a.model_scratch, a.gn);
+    const Smem S = make_smem(MP::CN ? MP::CN : a.n, MP::CM ? MP::CM : a.m, MP::CNZ ? MP::CNZ : a.nz, a.model_scratch, a.gn,
+                              use_big_bwd(MP::NT, MP::CN ? MP::CN : a.n, a.gn), a.index_lin != 0);
     const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     load_costs<MP>(a, S, sm);
     for (long long b = blockIdx.x; b < a.batch; b += gridDim.x) {
@@ -682,14 +704,15 @@ ilqr_forward_kernel(typename MP::Dev M, IlqrArgs a, const double* __restrict__ x
 
 // standalone backward pass (srcb200_ilqr_backward_pass): e_t / H_t are rebuilt from x first
 template <class MP>
-__global__ void __launch_bounds__(MP::NT)
+__global__ void __launch_bounds__(MP::NT, 1)
 ilqr_backward_kernel(typename MP::Dev M, IlqrArgs a, const double* __restrict__ x, const double* __restrict__ u,
                      const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ K,
                      double* __restrict__ k, double* __restrict__ Qu, double* __restrict__ Quu, double* __restrict__ rho_io,
                      double* __restrict__ drho_io, int* __restrict__ restarts_o) {
     constexpr int NT = MP::NT;
     extern __shared__ __align__(16) double sm[];
-    const Smem S = make_smem(MP::CN ? MP::CN : a.n, MP::CM ? MP::CM : a.m, MP::CNZ ? MP::CNZ : a.nz, a.model_scratch, a.gn);
+    const Smem S = make_smem(MP::CN ? MP::CN : a.n, MP::CM ? MP::CM : a.m, MP::CNZ ? MP::CNZ : a.nz, a.model_scratch, a.gn,
+                              use_big_bwd(MP::NT, MP::CN ? MP::CN : a.n, a.gn), a.index_lin != 0);
     const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     load_costs<MP>(a, S, sm);
     for (long long b = blockIdx.x; b < a.batch; b += gridDim.x) {
@@ -746,7 +769,7 @@ static int fill_args(const typename MP::Dev& M, const srcb200_ilqr_config* cfg, 
     a.Q = pr->Q; a.R = pr->R; a.Qf = pr->Qf; a.Hc = pr->H_const;
     a.L = make_layout(a.n, a.m, a.nz, a.N, a.gn, a.index_lin);
     a.model_scratch = MP::scratch_doubles(M, pr->dt);
-    const Smem S = make_smem(a.n, a.m, a.nz, a.model_scratch, a.gn);
+    const Smem S = make_smem(a.n, a.m, a.nz, a.model_scratch, a.gn, use_big_bwd(MP::NT, a.n, a.gn), a.index_lin != 0);
     smem = sizeof(double) * (size_t)S.total;
     if (smem > 227 * 1024) return fail(SRCB200_E_DIM, "ilqr: n=%d m=%d needs %zu B of shared memory per CTA", a.n, a.m, smem);
     return 0;

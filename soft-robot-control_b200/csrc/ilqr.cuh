@@ -48,7 +48,7 @@ __device__ inline Rec rec_at(double* base, const Layout& L) {
 
 // Shared-memory plan of the TPWL nearest-neighbour forward pass (ilqr_fwd_tpwl.cuh), in doubles from its base
 struct FwdNNPlan {
-    int pre0, pre1, PRE, Acur, dh, cand, red, misc, qf, vf, end;
+    int pre0, pre1, PRE, Acur, LDA, xf, dh, cand, red, misc, qf, vf, end;
     int screen;                 // 1: FP32 screening banks are resident
 };
 constexpr int kFwdNNCandCap = 512;
@@ -60,7 +60,9 @@ __host__ __device__ inline FwdNNPlan make_fwdnn(int n, int m, int nz, int P, int
     F.PRE = (n + 2 * m + m * n + nz + 1) & ~1;
     F.pre0 = take(F.PRE);
     F.pre1 = take(F.PRE);
-    F.Acur = take(n * n + n * m + n);
+    F.LDA = n; while ((F.LDA & 15) != 4 && (F.LDA & 15) != 12) ++F.LDA;      // conflict-free row stride of A
+    F.Acur = take(n * F.LDA + n * m + n);
+    F.xf = take((n + 1) / 2);               // FP32 copy of the state
     F.dh = take((P + 1) / 2);               // P floats
     F.cand = take(kFwdNNCandCap / 2 + 2);   // ints: [count, pad, candidates...]
     F.red = take(2 * (nt / 32) + 2);

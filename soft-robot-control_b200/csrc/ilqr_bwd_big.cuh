@@ -19,14 +19,14 @@
 
 namespace srcb {
 
-__host__ __device__ inline int cf_ld(int v) {           // smallest leading dimension >= v without LDS.64 bank conflicts
+__host__ __device__ constexpr int cf_ld(int v) {           // smallest leading dimension >= v without LDS.64 bank conflicts
     while ((v & 15) != 4 && (v & 15) != 12) ++v;
     return v;
 }
 
 struct BigPlan {
     int LD, L3;
-    int Pp, Ap0, Ap1, S1, Q2, L3b, R3b, T1, T1f, se, sdu, sut, cx, cu, Qx, Qu, Quu, Quut, Lc, LU, inv, end;
+    int Pp, Ap0, Ap1, S1, Q2, L3b, R3b, T1, T1f, se, pf0, pf1, Qx, Qu, Quu, Quut, Lc, LU, inv, end;
 };
 
 __host__ __device__ inline BigPlan make_big(int n, int m, int nz, int base) {
@@ -44,8 +44,9 @@ __host__ __device__ inline BigPlan make_big(int n, int m, int nz, int base) {
     B.R3b = take(3 * m * B.LD);
     B.T1 = take(n * nz);
     B.T1f = take(n * nz);
-    B.se = take(nz);  B.sdu = take(m);  B.sut = take(m);
-    B.cx = take(n);   B.cu = take(m);   B.Qx = take(n);   B.Qu = take(m);
+    B.se = take(nz);
+    B.pf0 = take(nz + 2 * m);  B.pf1 = take(nz + 2 * m);          // prefetched e_t, u_t, u_{t-1}
+    B.Qx = take(n);   B.Qu = take(m);
     B.Quu = take(m * m);  B.Quut = take(m * m);  B.Lc = take(m * m);  B.LU = take(m * m);  B.inv = take(m * m);
     B.end = o;
     return B;
@@ -119,6 +120,166 @@ __device__ __forceinline__ void dmma_blocks(int M, int N, int K, AF a, BF b, ST 
     }
 }
 
+// The same product with strided operand views instead of element functors -- no per-element masks or index
+// arithmetic inside the k loop, which unrolls completely when the segment lengths are compile-time constants.
+// A view describes op(X)(i, k) = p[i * is + k * ks] for i < valid (zero rows beyond); the K range is the
+// concatenation of NSEG segments (len[s] a multiple of 4), each with its own pair of views.
+struct OpView { const double* p; int is, ks, valid; };
+
+template <int NSEG, class ST>
+__device__ __forceinline__ void dmma_blocks_v(int M, int N, const int (&len)[NSEG], const OpView (&A)[NSEG],
+                                              const OpView (&B)[NSEG], ST store, int nwarps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int tm = (M + 7) >> 3, tn = (N + 7) >> 3, bm = (tm + 1) >> 1, bn = (tn + 1) >> 1;
+    for (int blk = warp; blk < bm * bn; blk += nwarps) {
+        const int bi = blk / bn;
+        const int i0 = bi * 16, j0 = (blk - bi * bn) * 16;
+        const bool r1 = i0 + 8 < M, c1 = j0 + 8 < N;
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0, c20 = 0.0, c21 = 0.0, c30 = 0.0, c31 = 0.0;
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) {
+            const bool va0 = i0 + g < A[s].valid, va1 = r1 && (i0 + 8 + g < A[s].valid);
+            const bool vb0 = j0 + g < B[s].valid, vb1 = c1 && (j0 + 8 + g < B[s].valid);
+            const double* pa0 = A[s].p + (va0 ? (i0 + g) * A[s].is : 0) + q * A[s].ks;
+            const double* pa1 = A[s].p + (va1 ? (i0 + 8 + g) * A[s].is : 0) + q * A[s].ks;
+            const double* pb0 = B[s].p + (vb0 ? (j0 + g) * B[s].is : 0) + q * B[s].ks;
+            const double* pb1 = B[s].p + (vb1 ? (j0 + 8 + g) * B[s].is : 0) + q * B[s].ks;
+            const int aks = 4 * A[s].ks, bks = 4 * B[s].ks;
+#pragma unroll
+            for (int k0 = 0; k0 < len[s]; k0 += 4) {
+                const int kk = k0 >> 2;
+                double a0 = pa0[kk * aks], b0 = pb0[kk * bks], a1 = pa1[kk * aks], b1 = pb1[kk * bks];
+                if (!va0) a0 = 0.0;
+                if (!va1) a1 = 0.0;
+                if (!vb0) b0 = 0.0;
+                if (!vb1) b1 = 0.0;
+                dmma_m8n8k4_acc(c00, c01, a0, b0);
+                if (c1) dmma_m8n8k4_acc(c10, c11, a0, b1);
+                if (r1) dmma_m8n8k4_acc(c20, c21, a1, b0);
+                if (r1 && c1) dmma_m8n8k4_acc(c30, c31, a1, b1);
+            }
+        }
+        store(i0 + g, j0 + 2 * q, c00, c01);
+        if (c1) store(i0 + g, j0 + 8 + 2 * q, c10, c11);
+        if (r1) store(i0 + 8 + g, j0 + 2 * q, c20, c21);
+        if (r1 && c1) store(i0 + 8 + g, j0 + 8 + 2 * q, c30, c31);
+    }
+}
+
+// One 8 x 8 tile per warp at a time with the K range split over two accumulator chains (short products: 2m x (n+m)).
+template <class ST>
+__device__ __forceinline__ void dmma_tiles_v(int M, int N, int len, const OpView& A, const OpView& B, ST store, int nwarps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int tm = (M + 7) >> 3, tn = (N + 7) >> 3;
+    for (int tile = warp; tile < tm * tn; tile += nwarps) {
+        const int ti = tile / tn;
+        const int i0 = ti * 8, j0 = (tile - ti * tn) * 8;
+        const bool va = i0 + g < A.valid, vb = j0 + g < B.valid;
+        const double* pa = A.p + (va ? (i0 + g) * A.is : 0) + q * A.ks;
+        const double* pb = B.p + (vb ? (j0 + g) * B.is : 0) + q * B.ks;
+        const int aks = 4 * A.ks, bks = 4 * B.ks;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < len; k0 += 8) {
+            const int kk = k0 >> 2;
+            double a0 = pa[kk * aks], b0 = pb[kk * bks];
+            if (!va) a0 = 0.0;
+            if (!vb) b0 = 0.0;
+            dmma_m8n8k4_acc(c0, c1, a0, b0);
+            if (k0 + 4 < len) {
+                double a1 = pa[(kk + 1) * aks], b1 = pb[(kk + 1) * bks];
+                if (!va) a1 = 0.0;
+                if (!vb) b1 = 0.0;
+                dmma_m8n8k4_acc(d0, d1, a1, b1);
+            }
+        }
+        store(i0 + g, j0 + 2 * q, c0 + d0, c1 + d1);
+    }
+}
+
+// Cholesky PD test (dpotf2 order, as cholesky_pd<>) and explicit inverse by LU with partial pivoting (as
+// lu_inverse<>) of an MM x MM matrix by ONE thread in registers: the same arithmetic as the cooperative routines
+// without their barriers.  Returns the PD verdict; the inverse is computed when pd or !need_pd.
+template <int MM>
+__device__ __forceinline__ bool small_chol_inv(const double* __restrict__ A, double* __restrict__ inv, bool need_pd) {
+    double L[MM][MM];
+    bool pd = true;
+#pragma unroll
+    for (int j = 0; j < MM; ++j) {
+#pragma unroll
+        for (int i = j; i < MM; ++i) {
+            double sacc = A[i * MM + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) sacc = fma(-L[i][k], L[j][k], sacc);
+            L[i][j] = sacc;
+        }
+        const double ajj = L[j][j];
+        if (!(ajj > 0.0) || isinf(ajj)) { pd = false; break; }
+        const double rj = sqrt(ajj);
+#pragma unroll
+        for (int i = j; i < MM; ++i) L[i][j] = (i == j) ? rj : L[i][j] / rj;
+    }
+    if (!pd && need_pd) return false;
+    double W[MM][MM];
+    int piv[MM];
+#pragma unroll
+    for (int i = 0; i < MM; ++i)
+#pragma unroll
+        for (int j = 0; j < MM; ++j) W[i][j] = A[i * MM + j];
+#pragma unroll
+    for (int cidx = 0; cidx < MM; ++cidx) {
+        int pr = cidx;
+        double best = fabs(W[cidx][cidx]);
+#pragma unroll
+        for (int r = cidx + 1; r < MM; ++r) {
+            const double v = fabs(W[r][cidx]);
+            if (v > best) { best = v; pr = r; }
+        }
+        piv[cidx] = pr;
+#pragma unroll
+        for (int r = cidx + 1; r < MM; ++r) {
+            if (pr == r) {
+#pragma unroll
+                for (int j = 0; j < MM; ++j) { const double tmp = W[cidx][j]; W[cidx][j] = W[r][j]; W[r][j] = tmp; }
+            }
+        }
+        const double rp = 1.0 / W[cidx][cidx];
+#pragma unroll
+        for (int r = cidx + 1; r < MM; ++r) W[r][cidx] *= rp;
+#pragma unroll
+        for (int r = cidx + 1; r < MM; ++r)
+#pragma unroll
+            for (int j = cidx + 1; j < MM; ++j) W[r][j] = fma(-W[r][cidx], W[cidx][j], W[r][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < MM; ++j) {
+        int pos = j;
+#pragma unroll
+        for (int cidx = 0; cidx < MM; ++cidx) {
+            const int pr = piv[cidx];
+            if (pos == cidx) pos = pr; else if (pos == pr) pos = cidx;
+        }
+        double x[MM];
+#pragma unroll
+        for (int i = 0; i < MM; ++i) {
+            double sacc = (i == pos) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) sacc = fma(-W[i][k], x[k], sacc);
+            x[i] = sacc;
+        }
+#pragma unroll
+        for (int i = MM - 1; i >= 0; --i) {
+            double sacc = x[i];
+#pragma unroll
+            for (int k = i + 1; k < MM; ++k) sacc = fma(-W[i][k], x[k], sacc);
+            x[i] = sacc / W[i][i];
+        }
+#pragma unroll
+        for (int i = 0; i < MM; ++i) inv[i * MM + j] = x[i];
+    }
+    return pd;
+}
+
 template <class MP>
 __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const Smem& S, double* sm, const Rec& rc,
                             const double* __restrict__ Adense, const double* __restrict__ Bdense,
@@ -132,7 +293,6 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
     const int LD = G.LD, L3 = G.L3;
     double* Pp = sm + G.Pp;    double* S1 = sm + G.S1;    double* Q2 = sm + G.Q2;    double* L3b = sm + G.L3b;
     double* R3b = sm + G.R3b;  double* T1 = sm + G.T1;    double* T1f = sm + G.T1f;  double* se = sm + G.se;
-    double* sdu = sm + G.sdu;  double* sut = sm + G.sut;  double* cx = sm + G.cx;    double* cu = sm + G.cu;
     double* Qx = sm + G.Qx;    double* Qu = sm + G.Qu;    double* Quu = sm + G.Quu;  double* Quut = sm + G.Quut;
     double* Lc = sm + G.Lc;    double* LU = sm + G.LU;    double* inv = sm + G.inv;
     const double* sQ = sm + S.Qs; const double* sR = sm + S.Rs; const double* sQf = sm + S.Qfs;
@@ -141,6 +301,7 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
     int* flag = piv + m + 2;
     const srcb200_ilqr_config& c = a.cfg;
     const bool sreg = c.regularize && c.state_regularization;
+    const bool aligned4 = (n % 4 == 0) && (m % 4 == 0);      // K segments are whole m8n8k4 steps: strided views
     int restarts = 0;
     give_up = false;
 
@@ -175,142 +336,204 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
         cta_sync<NT>();
 
         bool ok = true;
-        for (int t = N - 1; t >= 0; --t) {
-            // ---- A'_t has landed; stage e_t, du_t; start fetching A'_{t-1} into the other buffer
-            cp_async_wait_all();
-            for (int i = tid; i < nz; i += NT) se[i] = rc.e[t * nz + i];
+        auto prefetch_small = [&](int t) {
+            double* dst = sm + ((t & 1) ? G.pf1 : G.pf0);
+            for (int i = tid; i < nz; i += NT) cp_async8(dst + i, rc.e + t * nz + i);
             for (int i = tid; i < m; i += NT) {
-                const double ut = rc.u[t * m + i];
-                double du = ut;
-                if (c.include_input_var_constraint)
-                    du = __dsub_rn(ut, t == 0 ? (ulast ? ulast[i] : 0.0) : rc.u[(t - 1) * m + i]);
-                sdu[i] = du;
-                sut[i] = ut;
+                cp_async8(dst + nz + i, rc.u + t * m + i);
+                if (t > 0) cp_async8(dst + nz + m + i, rc.u + (t - 1) * m + i);
             }
+        };
+        if (N > 0) prefetch_small(N - 1);
+        for (int t = N - 1; t >= 0; --t) {
+            // ---- A'_t, e_t, u_t, u_{t-1} have landed and (P | p) of step t+1 is complete; fetch step t-1
+            cp_async_wait_all();
             cta_sync<NT>();
             const double* Ap = sm + ((t & 1) ? G.Ap1 : G.Ap0);
+            const double* pf = sm + ((t & 1) ? G.pf1 : G.pf0);
             if (t > 0) {
                 const LinRef ln = lin_of(t - 1);
                 load_lin_async<NT>(sm + (((t - 1) & 1) ? G.Ap1 : G.Ap0), LD, ln.A, ln.B, n, m);
+                prefetch_small(t - 1);
             }
-            // ---- step_cost_vectors (ilqr.py:186-196): c_x = (H^T Q) e, c_u = R du
-            mv<NT, false>(cx, T1, nz, se, n, nz);
-            mv<NT, false>(cu, sR, m, sdu, m, m);
-            // ---- product 1: S1 = A'^T P'
-            dmma_blocks(n + m, n + 1, n,
-                        [&](int r, int k) { return (r < n + m && k < n) ? Ap[k * LD + r] : 0.0; },
-                        [&](int k, int cc) { return (cc <= n && k < n) ? Pp[k * LD + cc] : 0.0; },
-                        [&](int r, int cc, double v0, double v1) {
-                            if (r < n + m) {
-                                if (cc <= n) S1[r * LD + cc] = v0;
-                                if (cc + 1 <= n) S1[r * LD + cc + 1] = v1;
-                            }
-                        }, NW);
-            cta_sync<NT>();
-            // ---- B^T (P + rho I) = B^T P + rho B^T;  Q_x = c_x + A^T p;  Q_u = c_u + B^T p   (ilqr.py:258-267)
-            for (int e = tid; e < m * n; e += NT) {
-                const int i = e / n, j = e - i * n;
-                const double v = S1[(n + i) * LD + j];
-                S1[(n + m + i) * LD + j] = sreg ? fma(rho, Ap[j * LD + n + i], v) : v;
-            }
-            for (int i = tid; i < n; i += NT) Qx[i] = __dadd_rn(cx[i], S1[i * LD + n]);
-            for (int i = tid; i < m; i += NT) Qu[i] = __dadd_rn(cu[i], S1[(n + i) * LD + n]);
-            cta_sync<NT>();
-            // ---- product 2: Q2 = [B^T P ; B^T (P + rho I)] A'
-            dmma_blocks(2 * m, n + m, n,
-                        [&](int r, int k) { return (r < 2 * m && k < n) ? S1[(n + r) * LD + k] : 0.0; },
-                        [&](int k, int cc) { return (cc < n + m && k < n) ? Ap[k * LD + cc] : 0.0; },
-                        [&](int r, int cc, double v0, double v1) {
-                            if (r < 2 * m) {
-                                if (cc < n + m) Q2[r * LD + cc] = v0;
-                                if (cc + 1 < n + m) Q2[r * LD + cc + 1] = v1;
-                            }
-                        }, NW);
-            cta_sync<NT>();
-            // ---- Q_uu = c_uu + B^T P B,  Q_uu~ (ilqr.py:261, 268-271)
-            for (int e = tid; e < m * m; e += NT) {
-                const int i = e / m, j = e - i * m;
-                const double quu = __dadd_rn(sR[e], Q2[i * LD + n + j]);
-                Quu[e] = quu;
-                if (sreg) Quut[e] = __dadd_rn(sR[e], Q2[(m + i) * LD + n + j]);
-                else Quut[e] = (c.regularize && i == j) ? __dadd_rn(quu, rho) : quu;
+            auto du_of = [&](int i) {       // du_t (ilqr.py:188-190)
+                const double ut = pf[nz + i];
+                if (!c.include_input_var_constraint) return ut;
+                return __dsub_rn(ut, t == 0 ? (ulast ? ulast[i] : 0.0) : pf[nz + m + i]);
+            };
+            // ---- product 1: S1 = A'^T P'; its epilogue also forms B^T (P + rho I) = B^T P + rho B^T,
+            //      Q_x = c_x + A^T p with c_x = (H^T Q) e, Q_u = c_u + B^T p with c_u = R du   (ilqr.py:186-196, 258-267)
+            auto put1 = [&](int r, int cc, double v) {
+                if (cc < n) {
+                    S1[r * LD + cc] = v;
+                    if (r >= n) S1[(r + m) * LD + cc] = sreg ? fma(rho, Ap[cc * LD + r], v) : v;
+                } else if (cc == n) {
+                    S1[r * LD + n] = v;
+                    if (r < n) {
+                        double acc = 0.0;
+                        for (int k2 = 0; k2 < nz; ++k2) acc = fma(T1[r * nz + k2], pf[k2], acc);
+                        Qx[r] = __dadd_rn(acc, v);
+                    } else {
+                        double acc = 0.0;
+                        for (int k2 = 0; k2 < m; ++k2) acc = fma(sR[(r - n) * m + k2], du_of(k2), acc);
+                        Qu[r - n] = __dadd_rn(acc, v);
+                    }
+                }
+            };
+            auto store1 = [&](int r, int cc, double v0, double v1) {
+                if (r < n + m) { put1(r, cc, v0); put1(r, cc + 1, v1); }
+            };
+            if (aligned4) {
+                const int len1[1] = {n};
+                const OpView A1[1] = {{Ap, 1, LD, n + m}};
+                const OpView B1[1] = {{Pp, 1, LD, n + 1}};
+                dmma_blocks_v<1>(n + m, n + 1, len1, A1, B1, store1, NW);
+            } else {
+                dmma_blocks(n + m, n + 1, n,
+                            [&](int r, int k) { return (r < n + m && k < n) ? Ap[k * LD + r] : 0.0; },
+                            [&](int k, int cc) { return (cc <= n && k < n) ? Pp[k * LD + cc] : 0.0; }, store1, NW);
             }
             cta_sync<NT>();
-            // ---- PD test by Cholesky (ilqr.py:276-287)
-            const bool pd = cholesky_pd<NT>(Quut, Lc, flag, m);
+            // ---- product 2: [B^T P ; B^T (P + rho I)] A' = [Q_ux | Q_uu - R ; Q_ux~ | Q_uu~ - R]; the epilogue adds
+            //      c_uu = R (ilqr.py:260-261, 268-271)
+            auto put2 = [&](int r, int cc, double v) {
+                if (cc < n) {
+                    Q2[r * LD + cc] = v;
+                } else if (cc < n + m) {
+                    const int j = cc - n;
+                    if (r < m) {
+                        const double quu = __dadd_rn(sR[r * m + j], v);
+                        Quu[r * m + j] = quu;
+                        if (!sreg) Quut[r * m + j] = (c.regularize && r == j) ? __dadd_rn(quu, rho) : quu;
+                    } else if (sreg) {
+                        Quut[(r - m) * m + j] = __dadd_rn(sR[(r - m) * m + j], v);
+                    }
+                }
+            };
+            auto store2 = [&](int r, int cc, double v0, double v1) {
+                if (r < 2 * m) { put2(r, cc, v0); put2(r, cc + 1, v1); }
+            };
+            if (aligned4) {
+                const OpView A2 = {S1 + n * LD, LD, 1, 2 * m};
+                const OpView B2 = {Ap, 1, LD, n + m};
+                dmma_tiles_v(2 * m, n + m, n, A2, B2, store2, NW);
+            } else {
+                dmma_blocks(2 * m, n + m, n,
+                            [&](int r, int k) { return (r < 2 * m && k < n) ? S1[(n + r) * LD + k] : 0.0; },
+                            [&](int k, int cc) { return (cc < n + m && k < n) ? Ap[k * LD + cc] : 0.0; }, store2, NW);
+            }
+            cta_sync<NT>();
+            // ---- PD test by Cholesky (ilqr.py:276-287) and the explicit inverse (ilqr.py:289): m x m, so one thread
+            //      (compile-time m) or one warp does it while the others lay out the operands that do not need it:
+            //      rows (Q_ux | Q_u) of the right factor and the Q_ux^T block of the left factor
+            if (tid < 32) {
+                if constexpr (MP::CM > 0 && MP::CM <= 8) {
+                    if (tid == 0) *flag = small_chol_inv<(MP::CM > 0 ? MP::CM : 1)>(Quut, inv, c.regularize != 0) ? 1 : 0;
+                } else {
+                    const bool pd1 = cholesky_pd<32>(Quut, Lc, flag, m);
+                    if (pd1 || !c.regularize) {
+                        for (int e = tid; e < m * m; e += 32) LU[e] = Quut[e];
+                        __syncwarp();
+                        lu_inverse<32>(LU, inv, piv, m);
+                    }
+                }
+            } else {
+                for (int e = tid - 32; e < m * (n + 1); e += NT - 32) {
+                    const int i = e / (n + 1), j = e - i * (n + 1);
+                    R3b[(m + i) * LD + j] = (j < n) ? Q2[i * LD + j] : Qu[i];
+                }
+                for (int e = tid - 32; e < n * m; e += NT - 32) {
+                    const int i = e / m, k2 = e - i * m;
+                    L3b[i * L3 + 2 * m + k2] = Q2[k2 * LD + i];
+                }
+            }
+            cta_sync<NT>();
+            const bool pd = (*flag != 0);
             if (!pd && c.regularize) {
                 rho_update(c, true, rho, drho);
                 ok = false;
                 break;
             }
-            // ---- gains (ilqr.py:289-292): explicit inverse, K = -inv Q_ux~, k = -inv Q_u
-            for (int e = tid; e < m * m; e += NT) LU[e] = Quut[e];
-            cta_sync<NT>();
-            lu_inverse<NT>(LU, inv, piv, m);
-            for (int e = tid; e < m * (n + 1); e += NT) {
-                const int i = e / (n + 1), j = e - i * (n + 1);
-                double acc = 0.0;
-                if (j < n) {
-                    for (int k2 = 0; k2 < m; ++k2) acc = fma(inv[i * m + k2], Q2[(m + k2) * LD + j], acc);
+            // ---- gains (ilqr.py:289-292): K = -inv Q_ux~, k = -inv Q_u, one column per thread, and with it that
+            //      column's part of both factors of the value update: K^T Q_uu, K^T, (K | k) twice; outputs
+            for (int i = tid; i <= n; i += NT) {
+                constexpr int MMAX = MP::CM > 0 ? MP::CM : 32;
+                constexpr int UNR = MP::CM > 0 ? MP::CM : 1;       // unroll only when m is a compile-time constant
+                double col[MMAX];
+#pragma unroll UNR
+                for (int j = 0; j < MMAX; ++j) {
+                    if (j < m) {
+                        double acc = 0.0;
+                        if (i < n) { for (int k2 = 0; k2 < m; ++k2) acc = fma(inv[j * m + k2], Q2[(m + k2) * LD + i], acc); }
+                        else       { for (int k2 = 0; k2 < m; ++k2) acc = fma(inv[j * m + k2], Qu[k2], acc); }
+                        col[j] = -acc;
+                        R3b[j * LD + i] = -acc;
+                        R3b[(2 * m + j) * LD + i] = -acc;
+                        if (i < n) Kout[(long long)t * m * n + j * n + i] = -acc;
+                        else kout[t * m + j] = -acc;
+                    }
+                }
+                if (i < n) {
+#pragma unroll UNR
+                    for (int k2 = 0; k2 < MMAX; ++k2) {
+                        if (k2 < m) {
+                            double acc = 0.0;
+#pragma unroll UNR
+                            for (int j = 0; j < MMAX; ++j) if (j < m) acc = fma(col[j], Quu[j * m + k2], acc);
+                            L3b[i * L3 + k2] = acc;
+                            L3b[i * L3 + m + k2] = col[k2];
+                        }
+                    }
                 } else {
-                    for (int k2 = 0; k2 < m; ++k2) acc = fma(inv[i * m + k2], Qu[k2], acc);
+                    // line-search scalars a_t = k . Q_u, b_t = (k^T Q_uu) . k   (ilqr.py:69-71)
+                    double sacc = 0.0, qq = 0.0;
+#pragma unroll UNR
+                    for (int j = 0; j < MMAX; ++j) if (j < m) sacc = fma(col[j], Qu[j], sacc);
+#pragma unroll UNR
+                    for (int j = 0; j < MMAX; ++j) {
+                        if (j < m) {
+                            double v = 0.0;
+#pragma unroll UNR
+                            for (int i2 = 0; i2 < MMAX; ++i2) if (i2 < m) v = fma(col[i2], Quu[i2 * m + j], v);
+                            qq = fma(v, col[j], qq);
+                        }
+                    }
+                    ab[2 * t] = sacc;
+                    ab[2 * t + 1] = qq;
+                    if (Quout) for (int j = 0; j < m; ++j) Quout[t * m + j] = Qu[j];
+                    if (Quuout) for (int e = 0; e < m * m; ++e) Quuout[(long long)t * m * m + e] = Quu[e];
                 }
-                R3b[i * LD + j] = -acc;                                    // (K | k)
-                R3b[(2 * m + i) * LD + j] = -acc;
-                R3b[(m + i) * LD + j] = (j < n) ? Q2[i * LD + j] : Qu[i];      // (Q_ux | Q_u)
-            }
-            cta_sync<NT>();
-            // ---- left factor of the value update: [K^T Q_uu | K^T | Q_ux^T]; outputs of this step
-            for (int e = tid; e < n * m; e += NT) {
-                const int i = e / m, k2 = e - i * m;
-                double acc = 0.0;
-                for (int j = 0; j < m; ++j) acc = fma(R3b[j * LD + i], Quu[j * m + k2], acc);
-                L3b[i * L3 + k2] = acc;
-                L3b[i * L3 + m + k2] = R3b[k2 * LD + i];
-                L3b[i * L3 + 2 * m + k2] = Q2[k2 * LD + i];
-            }
-            for (int e = tid; e < m * n; e += NT) {
-                const int i = e / n, j = e - i * n;
-                Kout[(long long)t * m * n + e] = R3b[i * LD + j];
-            }
-            for (int i = tid; i < m; i += NT) kout[t * m + i] = R3b[i * LD + n];
-            if (Quout) for (int i = tid; i < m; i += NT) Quout[t * m + i] = Qu[i];
-            if (Quuout) for (int e = tid; e < m * m; e += NT) Quuout[(long long)t * m * m + e] = Quu[e];
-            if (tid == NT - 1) {
-                double s = 0.0;
-                for (int i = 0; i < m; ++i) s = fma(R3b[i * LD + n], Qu[i], s);
-                double qq = 0.0;
-                for (int j = 0; j < m; ++j) {
-                    double v = 0.0;
-                    for (int i = 0; i < m; ++i) v = fma(R3b[i * LD + n], Quu[i * m + j], v);
-                    qq = fma(v, R3b[j * LD + n], qq);
-                }
-                ab[2 * t] = s;
-                ab[2 * t + 1] = qq;
             }
             cta_sync<NT>();
             // ---- product 3: (P | p) = (c_xx | Q_x) + [A^T P | K^T Q_uu | K^T | Q_ux^T] [A|0 ; K|k ; Q_ux|Q_u ; K|k]
-            dmma_blocks(n, n + 1, n + 3 * m,
-                        [&](int r, int k) {
-                            if (r >= n) return 0.0;
-                            if (k < n) return S1[r * LD + k];
-                            return (k < n + 3 * m) ? L3b[r * L3 + (k - n)] : 0.0;
-                        },
-                        [&](int k, int cc) {
-                            if (cc > n) return 0.0;
-                            if (k < n) return (cc < n) ? Ap[k * LD + cc] : 0.0;
-                            return (k < n + 3 * m) ? R3b[(k - n) * LD + cc] : 0.0;
-                        },
-                        [&](int r, int cc, double v0, double v1) {
-                            if (r < n) {
-                                if (cc < n) Pp[r * LD + cc] = __dadd_rn(cxx[r * n + cc], v0);
-                                else if (cc == n) Pp[r * LD + n] = __dadd_rn(Qx[r], v0);
-                                if (cc + 1 < n) Pp[r * LD + cc + 1] = __dadd_rn(cxx[r * n + cc + 1], v1);
-                                else if (cc + 1 == n) Pp[r * LD + n] = __dadd_rn(Qx[r], v1);
-                            }
-                        }, NW);
-            cta_sync<NT>();
+            auto store3 = [&](int r, int cc, double v0, double v1) {
+                if (r < n) {
+                    if (cc < n) Pp[r * LD + cc] = __dadd_rn(cxx[r * n + cc], v0);
+                    else if (cc == n) Pp[r * LD + n] = __dadd_rn(Qx[r], v0);
+                    if (cc + 1 < n) Pp[r * LD + cc + 1] = __dadd_rn(cxx[r * n + cc + 1], v1);
+                    else if (cc + 1 == n) Pp[r * LD + n] = __dadd_rn(Qx[r], v1);
+                }
+            };
+            if (aligned4) {
+                const int len3[2] = {n, 3 * m};
+                const OpView A3[2] = {{S1, LD, 1, n}, {L3b, L3, 1, n}};
+                const OpView B3[2] = {{Ap, 1, LD, n}, {R3b, 1, LD, n + 1}};
+                dmma_blocks_v<2>(n, n + 1, len3, A3, B3, store3, NW);
+            } else {
+                dmma_blocks(n, n + 1, n + 3 * m,
+                            [&](int r, int k) {
+                                if (r >= n) return 0.0;
+                                if (k < n) return S1[r * LD + k];
+                                return (k < n + 3 * m) ? L3b[r * L3 + (k - n)] : 0.0;
+                            },
+                            [&](int k, int cc) {
+                                if (cc > n) return 0.0;
+                                if (k < n) return (cc < n) ? Ap[k * LD + cc] : 0.0;
+                                return (k < n + 3 * m) ? R3b[(k - n) * LD + cc] : 0.0;
+                            }, store3, NW);
+            }
         }
+        cta_sync<NT>();
         if (ok) {
             rho_update(c, false, rho, drho);
             break;

@@ -20,13 +20,15 @@
 
 namespace srcb {
 
-// FP32 screening distance of point p: sqrt(sum_j (bank[j*P+p] - x[j])^2), bank and x rounded to FP32
-__device__ __forceinline__ void screen2(const float* __restrict__ bank, int P, int r, const double* __restrict__ x,
-                                        int p0, int p1, bool has1, float& d0, float& d1) {
-    float s0 = 0.f, s1 = 0.f;
+// FP32 screening distances of points p0 (and p1): sqrt(sum_j (bank[j*P+p] - x[j])^2) with bank and x rounded to FP32;
+// xn2 receives sum_j x[j]^2 (the error bound needs the norm of the state part)
+__device__ __forceinline__ void screen2(const float* __restrict__ bank, int P, int r, const float* __restrict__ xf,
+                                        int p0, int p1, bool has1, float& d0, float& d1, float& xn2) {
+    float s0 = 0.f, s1 = 0.f, sx2 = 0.f;
 #pragma unroll 4
     for (int j = 0; j < r; ++j) {
-        const float xj = (float)x[j];
+        const float xj = xf[j];
+        sx2 = fmaf(xj, xj, sx2);
         const float a0 = bank[j * P + p0] - xj;
         s0 = fmaf(a0, a0, s0);
         if (has1) {
@@ -36,6 +38,7 @@ __device__ __forceinline__ void screen2(const float* __restrict__ bank, int P, i
     }
     d0 = sqrtf(s0);
     d1 = sqrtf(s1);
+    xn2 = sx2;
 }
 
 template <class MP>
@@ -58,6 +61,8 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
     const double* sH = sm + S.Hcs;                       // constant output matrix H (n_z x n), staged by load_costs
     double* scal = sm + S.scal;
     double* Acur = base + F.Acur;
+    const int LDA = F.LDA;
+    float* sxf = reinterpret_cast<float*>(base + F.xf);
     float* dh = reinterpret_cast<float*>(base + F.dh);
     int* cand = reinterpret_cast<int*>(base + F.cand);
     double* red_d = base + F.red;
@@ -78,7 +83,7 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
     };
 
     // ---- pass prologue: state, FP32 banks + the largest weighted point norm (the error bound needs it)
-    for (int i = tid; i < n; i += NT) { sxa[i] = nx[i]; tr.x[i] = nx[i]; }
+    for (int i = tid; i < n; i += NT) { sxa[i] = nx[i]; sxf[i] = (float)nx[i]; tr.x[i] = nx[i]; }
     for (int i = tid; i < m; i += NT) sup[i] = ulast ? ulast[i] : 0.0;
     if (N > 0) prefetch(0);
     if (screen) {
@@ -147,24 +152,21 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
         int idx = -1;
         bool full_search = !screen_ok;
         if (screen_ok) {
-            double xq = 0.0, xv = 0.0;
-            for (int j = 0; j < r; ++j) {
-                if (usev) xv = fma(sx[j], sx[j], xv);
-                if (useq) xq = fma(sx[r + j], sx[r + j], xq);
-            }
-            const double slack = 2.0 * (bank_norm + M.wq * sqrt(xq) + M.wv * sqrt(xv));
             const double u24 = 5.9604644775390625e-08;   // 2^-24
             double ubmin = INFINITY;
+            double slack = 0.0;
             for (int p0 = tid; p0 < P; p0 += 2 * NT) {
                 const int p1 = p0 + NT;
                 const bool has1 = p1 < P;
-                float q0 = 0.f, q1 = 0.f, v0 = 0.f, v1 = 0.f;
-                if (useq) screen2(qf, P, r, sx + r, p0, has1 ? p1 : p0, has1, q0, q1);
-                if (usev) screen2(vf, P, r, sx, p0, has1 ? p1 : p0, has1, v0, v1);
+                float q0 = 0.f, q1 = 0.f, v0 = 0.f, v1 = 0.f, xq2 = 0.f, xv2 = 0.f;
+                if (useq) screen2(qf, P, r, sxf + r, p0, has1 ? p1 : p0, has1, q0, q1, xq2);
+                if (usev) screen2(vf, P, r, sxf, p0, has1 ? p1 : p0, has1, v0, v1, xv2);
+                // 2 (max point norm + state norm), the FP32 norms padded by 1e-3 relative
+                slack = 2.0 * (bank_norm + 1.001 * (M.wq * (double)sqrtf(xq2) + M.wv * (double)sqrtf(xv2)));
                 const double d0 = M.wq * (double)q0 + M.wv * (double)v0;
                 const double d1 = M.wq * (double)q1 + M.wv * (double)v1;
                 dh[p0] = (float)d0;
-                // (float)d rounds once more: fold that rounding into the bound by using the rounded value + 2 u d
+                // (float)d rounds once more: the candidate test below reads the rounded value and pads the bound for it
                 const double e0 = u24 * (34.0 * d0 + slack) + 1e-14 * d0;
                 ubmin = fmin(ubmin, d0 + e0);
                 if (has1) {
@@ -173,6 +175,7 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
                     ubmin = fmin(ubmin, d1 + e1);
                 }
             }
+            if (lane == 0 && warp == 0) misc[2] = slack;        // thread 0 always owns a point (P >= 1)
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) ubmin = fmin(ubmin, __shfl_xor_sync(0xffffffffu, ubmin, off));
             if (lane == 0) red_d[warp] = ubmin;
@@ -182,9 +185,10 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
 #pragma unroll
             for (int w = 1; w < NW; ++w) U = fmin(U, red_d[w]);
             // candidates: lower bound <= smallest upper bound
+            const double slack_all = misc[2];
             for (int p = tid; p < P; p += NT) {
                 const double d = (double)dh[p];
-                const double e = u24 * (36.0 * d + slack) + 1e-14 * d;
+                const double e = u24 * (36.0 * d + slack_all) + 1e-14 * d;
                 if (d - e <= U) {
                     const int pos = atomicAdd(&cand[0], 1);
                     if (pos < kFwdNNCandCap) cand[2 + pos] = p;
@@ -213,14 +217,14 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
         // ---- phase 2: the linearisation of this step: [A | B | d] of bank entry idx (kept while idx is unchanged)
         if (idx != cur_idx) {
             const LinRef b = MP::bank(M, idx);
-            for (int e = tid; e < n * n; e += NT) Acur[e] = b.A[e];
-            for (int e = tid; e < n * m; e += NT) Acur[n * n + e] = b.B[e];
-            for (int e = tid; e < n; e += NT) Acur[n * n + n * m + e] = b.d[e];
+            for (int e = tid; e < n * n; e += NT) { const int i = e / n; Acur[i * LDA + (e - i * n)] = b.A[e]; }
+            for (int e = tid; e < n * m; e += NT) Acur[n * LDA + e] = b.B[e];
+            for (int e = tid; e < n; e += NT) Acur[n * LDA + n * m + e] = b.d[e];
             cur_idx = idx;
         }
         __syncthreads();                                  // su, se, Acur ready
         if (tid == 0) tr.idx[t] = idx;
-        if (dout) for (int e = tid; e < n; e += NT) dout[(long long)t * n + e] = Acur[n * n + n * m + e];
+        if (dout) for (int e = tid; e < n; e += NT) dout[(long long)t * n + e] = Acur[n * LDA + n * m + e];
         // ---- step cost (ilqr.py:168-175) on the last warp: .5 e^T Q e + .5 du^T R du, row vector times matrix first
         if (warp == NW - 1) {
             double du = 0.0;
@@ -250,23 +254,28 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
             __syncwarp();
             if (lane < m) sup[lane] = su[lane];           // u_{t-1} of the next step
         }
-        // ---- x_{t+1} = (A x + B u) + d  (tpwl.py:231-234): one row per warp at a time, lanes split the sums
+        // ---- x_{t+1} = (A x + B u) + d  (tpwl.py:231-234): four lanes per row, each a strided quarter of the sums
         {
             const double* A = Acur;
-            const double* B = Acur + n * n;
-            const double* d = Acur + n * n + n * m;
-            for (int i = warp; i < n; i += NW) {
+            const double* B = Acur + n * LDA;
+            const double* d = Acur + n * LDA + n * m;
+            const int part = tid & 3;
+            for (int ib = 0; ib < n; ib += NT / 4) {                 // uniform trip count: the shuffles need whole warps
+                const int i = ib + (tid >> 2);
+                const bool act = i < n;
                 double ax = 0.0, bu = 0.0;
-                for (int kk = lane; kk < n; kk += 32) ax = fma(A[i * n + kk], sx[kk], ax);
-                for (int kk = lane; kk < m; kk += 32) bu = fma(B[i * m + kk], su[kk], bu);
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    ax += __shfl_xor_sync(0xffffffffu, ax, off);
-                    bu += __shfl_xor_sync(0xffffffffu, bu, off);
+                if (act) {
+                    for (int kk = part; kk < n; kk += 4) ax = fma(A[i * LDA + kk], sx[kk], ax);
+                    for (int kk = part; kk < m; kk += 4) bu = fma(B[i * m + kk], su[kk], bu);
                 }
-                if (lane == 0) {
+                ax += __shfl_xor_sync(0xffffffffu, ax, 1);
+                bu += __shfl_xor_sync(0xffffffffu, bu, 1);
+                ax += __shfl_xor_sync(0xffffffffu, ax, 2);
+                bu += __shfl_xor_sync(0xffffffffu, bu, 2);
+                if (act && part == 0) {
                     const double v = __dadd_rn(__dadd_rn(ax, bu), d[i]);
                     sxn[i] = v;
+                    sxf[i] = (float)v;
                     tr.x[(long long)(t + 1) * n + i] = v;
                 }
             }

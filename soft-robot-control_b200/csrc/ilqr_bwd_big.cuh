@@ -126,9 +126,13 @@ __device__ __forceinline__ void dmma_blocks(int M, int N, int K, AF a, BF b, ST 
 // concatenation of NSEG segments (len[s] a multiple of 4), each with its own pair of views.
 struct OpView { const double* p; int is, ks, valid; };
 
-template <int NSEG, class ST>
+struct NoAddend { __device__ __forceinline__ double operator()(int, int) const { return 0.0; } };
+
+// `addend(r, c)` is evaluated for the 16 elements a thread owns BEFORE the k loop (its latency -- a global-memory
+// read for the c_xx term -- hides behind the DMMAs) and handed to store(r, c, v0, v1, d0, d1) afterwards.
+template <int NSEG, class ST, class AD>
 __device__ __forceinline__ void dmma_blocks_v(int M, int N, const int (&len)[NSEG], const OpView (&A)[NSEG],
-                                              const OpView (&B)[NSEG], ST store, int nwarps) {
+                                              const OpView (&B)[NSEG], ST store, AD addend, int nwarps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
     const int tm = (M + 7) >> 3, tn = (N + 7) >> 3, bm = (tm + 1) >> 1, bn = (tn + 1) >> 1;
     for (int blk = warp; blk < bm * bn; blk += nwarps) {
@@ -136,6 +140,11 @@ __device__ __forceinline__ void dmma_blocks_v(int M, int N, const int (&len)[NSE
         const int i0 = bi * 16, j0 = (blk - bi * bn) * 16;
         const bool r1 = i0 + 8 < M, c1 = j0 + 8 < N;
         double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0, c20 = 0.0, c21 = 0.0, c30 = 0.0, c31 = 0.0;
+        const int ra = i0 + g, rb = i0 + 8 + g, ca = j0 + 2 * q, cb = j0 + 8 + 2 * q;
+        const double d00 = addend(ra, ca), d01 = addend(ra, ca + 1);
+        const double d10 = c1 ? addend(ra, cb) : 0.0, d11 = c1 ? addend(ra, cb + 1) : 0.0;
+        const double d20 = r1 ? addend(rb, ca) : 0.0, d21 = r1 ? addend(rb, ca + 1) : 0.0;
+        const double d30 = (r1 && c1) ? addend(rb, cb) : 0.0, d31 = (r1 && c1) ? addend(rb, cb + 1) : 0.0;
 #pragma unroll
         for (int s = 0; s < NSEG; ++s) {
             const bool va0 = i0 + g < A[s].valid, va1 = r1 && (i0 + 8 + g < A[s].valid);
@@ -159,14 +168,14 @@ __device__ __forceinline__ void dmma_blocks_v(int M, int N, const int (&len)[NSE
                 if (r1 && c1) dmma_m8n8k4_acc(c30, c31, a1, b1);
             }
         }
-        store(i0 + g, j0 + 2 * q, c00, c01);
-        if (c1) store(i0 + g, j0 + 8 + 2 * q, c10, c11);
-        if (r1) store(i0 + 8 + g, j0 + 2 * q, c20, c21);
-        if (r1 && c1) store(i0 + 8 + g, j0 + 8 + 2 * q, c30, c31);
+        store(ra, ca, c00, c01, d00, d01);
+        if (c1) store(ra, cb, c10, c11, d10, d11);
+        if (r1) store(rb, ca, c20, c21, d20, d21);
+        if (r1 && c1) store(rb, cb, c30, c31, d30, d31);
     }
 }
 
-// One 8 x 8 tile per warp at a time with the K range split over two accumulator chains (short products: 2m x (n+m)).
+// One 8 x 8 tile per warp at a time with the K range dealt round-robin to four accumulator chains (short products: 2m x (n+m)).
 template <class ST>
 __device__ __forceinline__ void dmma_tiles_v(int M, int N, int len, const OpView& A, const OpView& B, ST store, int nwarps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
@@ -178,32 +187,31 @@ __device__ __forceinline__ void dmma_tiles_v(int M, int N, int len, const OpView
         const double* pa = A.p + (va ? (i0 + g) * A.is : 0) + q * A.ks;
         const double* pb = B.p + (vb ? (j0 + g) * B.is : 0) + q * B.ks;
         const int aks = 4 * A.ks, bks = 4 * B.ks;
-        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};     // four chains: DMMA latency, not rate, bounds this
 #pragma unroll
-        for (int k0 = 0; k0 < len; k0 += 8) {
-            const int kk = k0 >> 2;
-            double a0 = pa[kk * aks], b0 = pb[kk * bks];
-            if (!va) a0 = 0.0;
-            if (!vb) b0 = 0.0;
-            dmma_m8n8k4_acc(c0, c1, a0, b0);
-            if (k0 + 4 < len) {
-                double a1 = pa[(kk + 1) * aks], b1 = pb[(kk + 1) * bks];
-                if (!va) a1 = 0.0;
-                if (!vb) b1 = 0.0;
-                dmma_m8n8k4_acc(d0, d1, a1, b1);
+        for (int k0 = 0; k0 < len; k0 += 16) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                if (k0 + 4 * ch < len) {
+                    const int kk = (k0 >> 2) + ch;
+                    double a0 = pa[kk * aks], b0 = pb[kk * bks];
+                    if (!va) a0 = 0.0;
+                    if (!vb) b0 = 0.0;
+                    dmma_m8n8k4_acc(acc[ch][0], acc[ch][1], a0, b0);
+                }
             }
         }
+        const double c0 = acc[0][0] + acc[1][0], d0 = acc[2][0] + acc[3][0];
+        const double c1 = acc[0][1] + acc[1][1], d1 = acc[2][1] + acc[3][1];
         store(i0 + g, j0 + 2 * q, c0 + d0, c1 + d1);
     }
 }
 
-// Cholesky PD test (dpotf2 order, as cholesky_pd<>) and explicit inverse by LU with partial pivoting (as
-// lu_inverse<>) of an MM x MM matrix by ONE thread in registers: the same arithmetic as the cooperative routines
-// without their barriers.  Returns the PD verdict; the inverse is computed when pd or !need_pd.
+// Cholesky PD test (dpotf2 order, as cholesky_pd<>) of an MM x MM matrix by ONE thread in registers: the same arithmetic
+// as the cooperative routine without its barriers.
 template <int MM>
-__device__ __forceinline__ bool small_chol_inv(const double* __restrict__ A, double* __restrict__ inv, bool need_pd) {
+__device__ __forceinline__ bool small_chol(const double* __restrict__ A) {
     double L[MM][MM];
-    bool pd = true;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
 #pragma unroll
@@ -214,12 +222,18 @@ __device__ __forceinline__ bool small_chol_inv(const double* __restrict__ A, dou
             L[i][j] = sacc;
         }
         const double ajj = L[j][j];
-        if (!(ajj > 0.0) || isinf(ajj)) { pd = false; break; }
+        if (!(ajj > 0.0) || isinf(ajj)) return false;
         const double rj = sqrt(ajj);
 #pragma unroll
         for (int i = j; i < MM; ++i) L[i][j] = (i == j) ? rj : L[i][j] / rj;
     }
-    if (!pd && need_pd) return false;
+    return true;
+}
+
+// Column `jcol` of the explicit inverse by LU with partial pivoting (the arithmetic of lu_inverse<>): every calling
+// thread factors its own register copy and solves for one column, so the MM columns come out in parallel.
+template <int MM>
+__device__ __forceinline__ void small_lu_inv_col(const double* __restrict__ A, double* __restrict__ inv, int jcol) {
     double W[MM][MM];
     int piv[MM];
 #pragma unroll
@@ -251,33 +265,29 @@ __device__ __forceinline__ bool small_chol_inv(const double* __restrict__ A, dou
 #pragma unroll
             for (int j = cidx + 1; j < MM; ++j) W[r][j] = fma(-W[r][cidx], W[cidx][j], W[r][j]);
     }
+    int pos = jcol;
 #pragma unroll
-    for (int j = 0; j < MM; ++j) {
-        int pos = j;
-#pragma unroll
-        for (int cidx = 0; cidx < MM; ++cidx) {
-            const int pr = piv[cidx];
-            if (pos == cidx) pos = pr; else if (pos == pr) pos = cidx;
-        }
-        double x[MM];
-#pragma unroll
-        for (int i = 0; i < MM; ++i) {
-            double sacc = (i == pos) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < i; ++k) sacc = fma(-W[i][k], x[k], sacc);
-            x[i] = sacc;
-        }
-#pragma unroll
-        for (int i = MM - 1; i >= 0; --i) {
-            double sacc = x[i];
-#pragma unroll
-            for (int k = i + 1; k < MM; ++k) sacc = fma(-W[i][k], x[k], sacc);
-            x[i] = sacc / W[i][i];
-        }
-#pragma unroll
-        for (int i = 0; i < MM; ++i) inv[i * MM + j] = x[i];
+    for (int cidx = 0; cidx < MM; ++cidx) {
+        const int pr = piv[cidx];
+        if (pos == cidx) pos = pr; else if (pos == pr) pos = cidx;
     }
-    return pd;
+    double x[MM];
+#pragma unroll
+    for (int i = 0; i < MM; ++i) {
+        double sacc = (i == pos) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) sacc = fma(-W[i][k], x[k], sacc);
+        x[i] = sacc;
+    }
+#pragma unroll
+    for (int i = MM - 1; i >= 0; --i) {
+        double sacc = x[i];
+#pragma unroll
+        for (int k = i + 1; k < MM; ++k) sacc = fma(-W[i][k], x[k], sacc);
+        x[i] = sacc / W[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < MM; ++i) inv[i * MM + jcol] = x[i];
 }
 
 template <class MP>
@@ -344,11 +354,20 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
                 if (t > 0) cp_async8(dst + nz + m + i, rc.u + (t - 1) * m + i);
             }
         };
+#ifdef SRCB_PHASE_TIMING
+        long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tk = clock64();
+#define PH(i) do { const long long now_ = clock64(); ph[i] += now_ - tk; tk = now_; } while (0)
+#else
+#define PH(i) do { } while (0)
+#endif
         if (N > 0) prefetch_small(N - 1);
         for (int t = N - 1; t >= 0; --t) {
             // ---- A'_t, e_t, u_t, u_{t-1} have landed and (P | p) of step t+1 is complete; fetch step t-1
+            PH(7);
             cp_async_wait_all();
             cta_sync<NT>();
+            PH(0);
             const double* Ap = sm + ((t & 1) ? G.Ap1 : G.Ap0);
             const double* pf = sm + ((t & 1) ? G.pf1 : G.pf0);
             if (t > 0) {
@@ -387,13 +406,16 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
                 const int len1[1] = {n};
                 const OpView A1[1] = {{Ap, 1, LD, n + m}};
                 const OpView B1[1] = {{Pp, 1, LD, n + 1}};
-                dmma_blocks_v<1>(n + m, n + 1, len1, A1, B1, store1, NW);
+                dmma_blocks_v<1>(n + m, n + 1, len1, A1, B1,
+                                 [&](int r, int cc, double v0, double v1, double, double) { store1(r, cc, v0, v1); }, NoAddend(), NW);
             } else {
                 dmma_blocks(n + m, n + 1, n,
                             [&](int r, int k) { return (r < n + m && k < n) ? Ap[k * LD + r] : 0.0; },
                             [&](int k, int cc) { return (cc <= n && k < n) ? Pp[k * LD + cc] : 0.0; }, store1, NW);
             }
+            PH(1);
             cta_sync<NT>();
+            PH(2);
             // ---- product 2: [B^T P ; B^T (P + rho I)] A' = [Q_ux | Q_uu - R ; Q_ux~ | Q_uu~ - R]; the epilogue adds
             //      c_uu = R (ilqr.py:260-261, 268-271)
             auto put2 = [&](int r, int cc, double v) {
@@ -423,12 +445,20 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
                             [&](int k, int cc) { return (cc < n + m && k < n) ? Ap[k * LD + cc] : 0.0; }, store2, NW);
             }
             cta_sync<NT>();
+            PH(3);
             // ---- PD test by Cholesky (ilqr.py:276-287) and the explicit inverse (ilqr.py:289): m x m, so one thread
             //      (compile-time m) or one warp does it while the others lay out the operands that do not need it:
             //      rows (Q_ux | Q_u) of the right factor and the Q_ux^T block of the left factor
-            if (tid < 32) {
-                if constexpr (MP::CM > 0 && MP::CM <= 8) {
-                    if (tid == 0) *flag = small_chol_inv<(MP::CM > 0 ? MP::CM : 1)>(Quut, inv, c.regularize != 0) ? 1 : 0;
+            constexpr bool small_m = MP::CM > 0 && MP::CM <= 8;
+            constexpr int FILL0 = small_m ? 64 : 32;            // first thread of the operand-layout crew
+            if (tid < FILL0) {
+                if constexpr (small_m) {
+                    // thread 0: Cholesky verdict; lanes 0..m-1 of warp 1: the LU (each its own register copy) and one
+                    // inverse column each.  Two warps, so the two run concurrently; the inverse is only used when
+                    // the verdict allows it, computing it regardless is harmless.
+                    constexpr int MM = MP::CM > 0 ? MP::CM : 1;
+                    if (tid == 0) *flag = small_chol<MM>(Quut) ? 1 : 0;
+                    else if (tid >= 32 && tid < 32 + MM) small_lu_inv_col<MM>(Quut, inv, tid - 32);
                 } else {
                     const bool pd1 = cholesky_pd<32>(Quut, Lc, flag, m);
                     if (pd1 || !c.regularize) {
@@ -438,16 +468,17 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
                     }
                 }
             } else {
-                for (int e = tid - 32; e < m * (n + 1); e += NT - 32) {
+                for (int e = tid - FILL0; e < m * (n + 1); e += NT - FILL0) {
                     const int i = e / (n + 1), j = e - i * (n + 1);
                     R3b[(m + i) * LD + j] = (j < n) ? Q2[i * LD + j] : Qu[i];
                 }
-                for (int e = tid - 32; e < n * m; e += NT - 32) {
+                for (int e = tid - FILL0; e < n * m; e += NT - FILL0) {
                     const int i = e / m, k2 = e - i * m;
                     L3b[i * L3 + 2 * m + k2] = Q2[k2 * LD + i];
                 }
             }
             cta_sync<NT>();
+            PH(4);
             const bool pd = (*flag != 0);
             if (!pd && c.regularize) {
                 rho_update(c, true, rho, drho);
@@ -505,20 +536,24 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
                 }
             }
             cta_sync<NT>();
+            PH(5);
             // ---- product 3: (P | p) = (c_xx | Q_x) + [A^T P | K^T Q_uu | K^T | Q_ux^T] [A|0 ; K|k ; Q_ux|Q_u ; K|k]
-            auto store3 = [&](int r, int cc, double v0, double v1) {
+            auto add3 = [&](int r, int cc) {            // (c_xx | Q_x) element
+                if (r >= n || cc > n) return 0.0;
+                return (cc < n) ? cxx[r * n + cc] : Qx[r];
+            };
+            auto store3d = [&](int r, int cc, double v0, double v1, double d0, double d1) {
                 if (r < n) {
-                    if (cc < n) Pp[r * LD + cc] = __dadd_rn(cxx[r * n + cc], v0);
-                    else if (cc == n) Pp[r * LD + n] = __dadd_rn(Qx[r], v0);
-                    if (cc + 1 < n) Pp[r * LD + cc + 1] = __dadd_rn(cxx[r * n + cc + 1], v1);
-                    else if (cc + 1 == n) Pp[r * LD + n] = __dadd_rn(Qx[r], v1);
+                    if (cc <= n) Pp[r * LD + cc] = __dadd_rn(d0, v0);
+                    if (cc + 1 <= n) Pp[r * LD + cc + 1] = __dadd_rn(d1, v1);
                 }
             };
+            auto store3 = [&](int r, int cc, double v0, double v1) { store3d(r, cc, v0, v1, add3(r, cc), add3(r, cc + 1)); };
             if (aligned4) {
                 const int len3[2] = {n, 3 * m};
                 const OpView A3[2] = {{S1, LD, 1, n}, {L3b, L3, 1, n}};
                 const OpView B3[2] = {{Ap, 1, LD, n}, {R3b, 1, LD, n + 1}};
-                dmma_blocks_v<2>(n, n + 1, len3, A3, B3, store3, NW);
+                dmma_blocks_v<2>(n, n + 1, len3, A3, B3, store3d, add3, NW);
             } else {
                 dmma_blocks(n, n + 1, n + 3 * m,
                             [&](int r, int k) {
@@ -534,6 +569,9 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
             }
         }
         cta_sync<NT>();
+#ifdef SRCB_PHASE_TIMING
+        if (tid == 0 && Quout) for (int i = 0; i < 8; ++i) Quout[i] = (double)ph[i];
+#endif
         if (ok) {
             rho_update(c, false, rho, drho);
             break;

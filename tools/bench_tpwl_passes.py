@@ -30,3 +30,8 @@ torch.cuda.synchronize()
 x2, u2, cost2, *_ = s.forward_pass(x, uu, 1.0, K, k)
 torch.cuda.synchronize()
 print('ok', float(np.mean(cost)), float(np.mean(cost2)))
+if os.environ.get('SRCB_PHASE_TIMING'):
+    q = np.asarray(Qu).reshape(batch, N, 4)
+    ph = q[:, :2, :].reshape(batch, 8)
+    names = ['top wait+sync', 'P1', 'sync', 'P2+sync', 'chol/inv+sync', 'gains+sync', '-', 'P3 (+prologue)']
+    print('cycles per step (mean over CTAs):', {n: round(float(v) / N) for n, v in zip(names, ph.mean(0))})

@@ -12,7 +12,7 @@ batched solve of the whole batch (ONE launch of ilqr_solve_kernel).  Metric: iLQ
   roofline   : algorithmic FP64 flops of the solve kernel / its event time against the measured cuBLAS DGEMM rate.
   cpu_baseline / --impl reference : the CPU port of the reference algorithm (oracle/, pinned bitwise to the
                reference classes) on the box's host cores, bounded sample.
-Other workloads (--workload): tpwl_rollout_nn, tpwl_rollout_weighting, ssm_rollout, pod_gram.
+Other workloads (--workload): ilqr_tpwl, tpwl_rollout_nn, tpwl_rollout_weighting, ssm_rollout, ssm_eval, pod_gram, mpc.
 """
 import argparse
 import json
@@ -522,6 +522,73 @@ def run_mpc(args, rank, world, dev_index):
             "e2e": None, "gpu_launches": steps * 2, "clocks": clk.summary(), "roofline": None}
 
 
+def run_ilqr_tpwl(args, rank, world, dev_index):
+    """Diamond TPWL iLQR (the reference's TPWL controller, tpwl/controllers.py + lqr/ilqr.py): n = 72, m = 4, P = 1000,
+    nearest-neighbour linearisation on the zoh pre-discretised bank, horizon 100, figure-8 targets of random
+    amplitude.  One CTA per problem (generic kernel, Diamond instantiation)."""
+    import torch
+    import torch.distributed as dist
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200 import _lib as L
+    from sofacontrol_b200.tpwl.tpwl import TPWLATV
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost
+    batch = args.batch if args.batch != 4096 else 1184
+    N = args.horizon
+    data, Hf = synth.tpwl_bank()
+    g = TPWLATV(data, params={'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}, Hf=Hf, discr_method='zoh')
+    g.pre_discretize(0.01)
+    Q = np.zeros((6, 6)); Q[3, 3] = Q[4, 4] = 100.0
+    R = 1e-5 * np.eye(4)
+    th = np.linspace(0, 2 * np.pi, N + 1)
+    rng = np.random.default_rng(rank)
+    x0, _ = synth.tpwl_rollout_batch(batch, N=1, seed=21 + rank)
+    amp = rng.uniform(0.3, 1.5, size=batch)
+    zt = np.tile(g.z_ref, (batch, N + 1, 1))
+    zt[:, :, 3] += amp[:, None] * np.sin(th)[None]; zt[:, :, 4] += amp[:, None] * np.sin(2 * th)[None]
+    solver = iLQR(0.01, g, QuadraticCost(Q, R, np.zeros((6, 6))), N)
+    x0d, ztd = L.to_dev(x0), L.to_dev(zt)
+    flush = torch.empty(256 * 1024 * 1024 // 8, device="cuda", dtype=torch.float64)
+    out = None
+    for _ in range(max(1, min(args.warmup, 3))):
+        out = solver.solve_device(x0d, ztd)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(dev_index) as clk:
+        for s_, e_ in ev:
+            flush.fill_(1.0)
+            s_.record()
+            out = solver.solve_device(x0d, ztd)
+            e_.record()
+        torch.cuda.synchronize()
+    t_dev = sum(s_.elapsed_time(e_) for s_, e_ in ev) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt[0])
+    it = out['iterations'].cpu().numpy(); tr = out['trials'].cpu().numpy(); st = out['status'].cpu().numpy()
+    # DMMA work of the backward sweeps: (76x73x72 + 8x76x72 + 72x73x84) fused multiply-adds per step
+    flops = 2.0 * (76 * 73 * 72 + 8 * 76 * 72 + 72 * 73 * 84) * N * float(it.sum())
+    hbm, hsrc, fp64 = measured_peaks()
+    ach = flops * args.steps / t_dev / 1e12
+    return {"metric": "ilqr_solves_per_sec", "value": batch * world * args.steps / t_dev, "unit": "solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Diamond TPWL batched iLQR: %d independent solves per GPU, horizon %d, n=72 m=4 P=1000, nearest-"
+                                   "neighbour linearisation on the zoh bank (dt 0.01), figure-8 tracking of random amplitude"
+                                   % (batch, N),
+                       "batch_per_gpu": batch, "horizon": N, "l2": "256 MB buffer written between timed steps (untimed)",
+                       "converged_frac": float((st & 1).mean()), "mean_iterations": float(it.mean()),
+                       "mean_forward_passes": float((tr + 1).mean())},
+            "e2e": None, "gpu_launches": args.steps, "clocks": clk.summary(),
+            "roofline": {"kernel": "ilqr_solve_kernel<TpwlPolicyT<72,4,6>>", "bound": "tensor", "achieved": ach, "peak": fp64,
+                         "unit": "TFLOP/s", "frac": ach / fp64, "traffic": None,
+                         "note": "flops of the three DMMA products of every backward step only (forward passes and the "
+                                 "nearest-point search not counted) / whole-solve time; peak = measured cuBLAS DGEMM"}}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU port on the host cores, same workload/metric (bounded sample)."""
     t_all = []
@@ -546,7 +613,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ilqr_trunk_ssm",
-                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting", "ssm_rollout", "ssm_eval", "pod_gram", "mpc"])
+                    choices=["ilqr_trunk_ssm", "tpwl_rollout_nn", "tpwl_rollout_weighting", "ssm_rollout", "ssm_eval", "pod_gram", "mpc", "ilqr_tpwl"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--cpu-per-core", type=int, default=2)
@@ -578,6 +645,8 @@ def main():
         res = run_ssm_eval(args, rank, world, local)
     elif args.workload == "pod_gram":
         res = run_pod_gram(args, rank, world, local)
+    elif args.workload == "ilqr_tpwl":
+        res = run_ilqr_tpwl(args, rank, world, local)
     elif args.workload == "mpc":
         res = run_mpc(args, rank, world, local)
     else:

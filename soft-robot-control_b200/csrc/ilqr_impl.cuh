@@ -569,7 +569,14 @@ ilqr_solve_kernel(typename MP::Dev M, IlqrArgs a) {
     const srcb200_ilqr_config& c = a.cfg;
     load_costs<MP>(a, S, sm);
 
-    for (long long b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    // problems differ a lot in iteration count: CTAs take the next unsolved problem from an atomic counter
+    __shared__ long long s_next;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = (long long)atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const long long b = s_next;
+        if (b >= a.batch) break;
         double* wsb = a.ws + b * a.L.total;
         Rec rec[2] = {rec_at(wsb, a.L), rec_at(wsb + a.L.rec, a.L)};
         double* kbuf = wsb + a.L.k;
@@ -776,14 +783,14 @@ static int fill_args(const typename MP::Dev& M, const srcb200_ilqr_config* cfg, 
 }
 
 template <class MP>
-static int grid_size(long long batch, size_t smem) {
+static int grid_size(long long batch, size_t smem, int waves = 4) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long per_sm = (long long)(227 * 1024) / (long long)(smem + 1024);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 32) per_sm = 32;
-    const long long cap = per_sm * sms * 4;
+    const long long cap = per_sm * sms * waves;      // waves = 1: persistent CTAs (the solve kernel's work queue)
     return (int)(batch < cap ? batch : cap);
 }
 
@@ -810,7 +817,8 @@ static int solve_impl(const typename MP::Dev& M, const srcb200_ilqr_config* cfg,
     }
     auto kern = ilqr_solve_kernel<MP>;
     SRCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_size<MP>(a.batch, smem), MP::NT, smem, st>>>(M, a);
+    SRCB_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
+    kern<<<grid_size<MP>(a.batch, smem, 1), MP::NT, smem, st>>>(M, a);
     SRCB_LAUNCH_CHECK("ilqr_solve_kernel");
     return 0;
 }

@@ -359,3 +359,48 @@ def test_branch_paths_max_iter_and_no_linesearch():
     xo, uo, Ko = o.ilqr_computation(x0)
     assert s.info['iterations'] == o.iterations
     assert relerr(x, xo) < TOL and relerr(u, uo) < TOL and relerr(K, Ko) < TOL
+
+
+def test_tpwl_forward_pass_two_stage_search_is_exact_on_ties():
+    """The iLQR forward pass for TPWL-nn picks its linearisation with an FP32-screened search that must return
+    EXACTLY the index of the full FP64 numpy-order search (tpwl.py:160-168), also when stored points coincide
+    (first occurrence wins) or differ by less than FP32 can resolve.  Adversarial bank: duplicated and
+    1e-13-perturbed points, trajectories started on top of them; the indices implied by the pass's A_t are compared
+    with calc_nearest_point (bit-exact vs numpy, tests/test_tpwl_gpu.py) evaluated on the visited states."""
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.tpwl.tpwl import TPWLATV
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost
+    data, Hf = synth.tpwl_bank()
+    q = data['q']
+    q[500] = q[100]                                  # exact tie: index 100 must win
+    q[700] = q[200] * (1.0 + 1e-13)                  # below FP32 resolution: only the FP64 rescoring can tell
+    q[701] = q[200] * (1.0 - 1e-13)
+    q[3] = q[900]                                    # exact tie where the LOWER index is the later-made copy
+    for i in range(1000):                            # make the linearisations distinguishable by A[0, 0]
+        data['A_c'][i][0, 0] = -1.0 - i
+    params = {'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}
+    g = TPWLATV(data, params=params, Hf=Hf, discr_method='fe')
+    g.pre_discretize(0.001)                          # the step's linearisation is then an index into the bank
+    N, Bt = 12, 8
+    rng = np.random.default_rng(5)
+    x0 = np.zeros((Bt, 72))
+    starts = [100, 500, 200, 700, 701, 900, 3, 42]
+    for b, p in enumerate(starts):
+        x0[b, 36:] = q[p] + (0.0 if b % 2 == 0 else 1e-9 * rng.normal(size=36))
+        x0[b, :36] = 0.1 * rng.normal(size=36)
+    Q = np.zeros((6, 6)); Q[3, 3] = Q[4, 4] = 100.0
+    s = iLQR(0.001, g, QuadraticCost(Q, 1e-5 * np.eye(4), np.zeros((6, 6))), N)
+    s.set_target(np.tile(g.z_ref, (Bt, N + 1, 1)))
+    xp = np.zeros((Bt, N + 1, 72)); xp[:, 0] = x0
+    x, u, cost, A, B, d = s.forward_pass(xp, np.zeros((Bt, N, 4)))
+    A = np.asarray(A).reshape(Bt, N, 72, 72)
+    x = np.asarray(x).reshape(Bt, N + 1, 72)
+    idx_pass = np.rint((A[:, :, 0, 0] - 1.0) / 0.001 * -1.0 - 1.0).astype(int)     # fe: A_d[0,0] = 1 + dt * (-1 - i)
+    idx_full = np.asarray(g.calc_nearest_point(x[:, :-1].reshape(-1, 72))).reshape(Bt, N)
+    assert np.array_equal(idx_pass, idx_full)
+    assert idx_full[0, 0] == 100 and idx_full[1, 0] == 100 and idx_full[5, 0] == 3 and idx_full[6, 0] == 3
+    # and against numpy itself on the first states
+    for b in range(Bt):
+        dist = 1.0 * np.linalg.norm(q - x0[b, 36:], axis=1) + 0.0 * np.linalg.norm(data['v'] - x0[b, :36], axis=1)
+        assert idx_pass[b, 0] == int(np.argmin(dist))

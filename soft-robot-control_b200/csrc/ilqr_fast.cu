@@ -792,11 +792,13 @@ __device__ __forceinline__ int queue_pop(int* q, int cap, int lane) {
         const int t = atomicAdd(q + 0, 1);
         volatile int* slot = q + 64 + (t % cap);
         volatile int* remaining = q + 2;
-        while (true) {
+        unsigned ns = 256;                          // back off: an idle warp must not compete with working ones for
+        while (true) {                              // issue slots and L2 bandwidth (an iteration takes ~1 ms)
             const int v = *slot;
             if (v >= 0) { id = v; *slot = -1; break; }
             if (*remaining <= 0) break;
-            __nanosleep(256);
+            __nanosleep(ns);
+            if (ns < 8192) ns <<= 1;
         }
     }
     id = __shfl_sync(FULL, id, 0);

@@ -196,7 +196,9 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
             }
             __syncthreads();
             const int cnt = cand[0];
-            if (cnt >= 1 && cnt <= kFwdNNCandCap && cnt <= NT) {
+            if (cnt == 1) {
+                idx = cand[2];      // the argmin is among the candidates and there is only one: no FP64 evaluation needed
+            } else if (cnt >= 1 && cnt <= kFwdNNCandCap && cnt <= NT) {
                 double best = INFINITY;
                 int bi = 0x7fffffff;
                 if (tid < cnt) {

@@ -293,14 +293,15 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
     n, m, P, r = 72, 4, 1000, 36
     if method == 'nn':
         byt = batch * N * ((n * n + n * m + n) * 8 + (2 * n + m) * 8) + N * P * r * 8
-        ops = batch * N * 3.0 * P * r
-        roof = {"kernel": "tpwl_rollout_nn_multi_kernel<36>", "bound": "hbm", "achieved": byt / (t_dev / args.steps) / 1e9,
+        ops = batch * N * 2.0 * P * r
+        roof = {"kernel": "tpwl_rollout_nn_screen_kernel<36,4>", "bound": "hbm", "achieved": byt / (t_dev / args.steps) / 1e9,
                 "peak": hbm, "unit": "GB/s", "traffic": None,
-                "fp64_ops_tops": ops / (t_dev / args.steps) / 1e12,
+                "fp32_screen_tops": ops / (t_dev / args.steps) / 1e12,
                 "note": "algorithmic bytes per trajectory-step = gathered bank entry 44352 B + state I/O, distance bank "
-                        "288000 B once per time step for the whole batch (SURVEY 8d), of " + hsrc + "; the distance search "
-                        "(3 P r un-fused FP64 ops per step, numpy rounding order) is the actual limiter: fp64_ops_tops "
-                        "against %.1f T pipe slots/s (half the measured DGEMM flop rate)" % (fp64 / 2)}
+                        "288000 B once per time step for the whole batch (SURVEY 8d), of " + hsrc + "; the 44 MB bank is "
+                        "L2 resident, so these bytes move L2 -> SM, not HBM -> L2 (ncu: profiles/ncu_tpwl_screen_r01.txt). "
+                        "The kernel alternates an FP32-issue-bound exact two-stage nearest search (fp32_screen_tops = "
+                        "2 P r FP32 instructions per trajectory-step, T lane-ops/s) with the L2-bandwidth-bound gather"}
     else:
         fl = batch * N * 2.0 * P * (n * n + n * m + n)
         roof = {"kernel": "dgemm_kernel (bank blend)", "bound": "tensor", "achieved": fl / (t_dev / args.steps) / 1e12,

@@ -15,8 +15,8 @@
 // The selected indices are identical to the full search's (tests/test_tpwl_gpu.py compares the index trace with
 // numpy).  A CTA is two independent halves of 256 threads (named barriers), each rolling its own group of
 // trajectories against the shared bank copy: the search is FP32-issue bound, the gathered affine step
-// x+ = A_i x + B_i u + d_i is L2-bandwidth bound (44 KB per trajectory-step), and the halves drift so that one
-// computes while the other gathers.
+// x+ = A_i x + B_i u + d_i is bound by the load path (44 KB gathered from L2 per trajectory-step; ncu: L1/LSU 73 %,
+// L2 16 % of peak), and the halves drift so that one computes while the other gathers.
 #include <cstdlib>
 #include "tpwl.cuh"
 
@@ -279,19 +279,21 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                     const double* x0s = sx + tr0 * n;
                     const double* x1s = sx + tr1 * n;
                     double ax0 = 0.0, ax1 = 0.0, bu0 = 0.0, bu1 = 0.0;
-                    if constexpr (RT > 0) {
-                        constexpr int NK = (2 * RT + 3) / 4;
-                        double v0[NK], v1[NK];
+                    if constexpr (RT > 0 && (2 * RT) % 8 == 0) {
+                        // 16-byte loads: lane `part` takes elements 8 s + 2 part, 8 s + 2 part + 1 (rows are 16-byte
+                        // aligned: n even, bank base from cudaMalloc); half the load instructions / L1 tag lookups
+                        constexpr int NK = (2 * RT) / 8;
+                        double2 v0[NK], v1[NK];
 #pragma unroll
                         for (int s2 = 0; s2 < NK; ++s2) {
-                            const int k = 4 * s2 + part;
-                            v0[s2] = (k < n) ? A0[k] : 0.0;
-                            v1[s2] = (k < n) ? A1[k] : 0.0;
+                            v0[s2] = *reinterpret_cast<const double2*>(A0 + 8 * s2 + 2 * part);
+                            v1[s2] = *reinterpret_cast<const double2*>(A1 + 8 * s2 + 2 * part);
                         }
 #pragma unroll
                         for (int s2 = 0; s2 < NK; ++s2) {
-                            const int k = 4 * s2 + part;
-                            if (k < n) { ax0 = fma(v0[s2], x0s[k], ax0); ax1 = fma(v1[s2], x1s[k], ax1); }
+                            const int k = 8 * s2 + 2 * part;
+                            ax0 = fma(v0[s2].x, x0s[k], ax0); ax0 = fma(v0[s2].y, x0s[k + 1], ax0);
+                            ax1 = fma(v1[s2].x, x1s[k], ax1); ax1 = fma(v1[s2].y, x1s[k + 1], ax1);
                         }
                     } else {
                         for (int k = part; k < n; k += 4) { ax0 = fma(A0[k], x0s[k], ax0); ax1 = fma(A1[k], x1s[k], ax1); }
@@ -337,6 +339,7 @@ int tpwl_rollout_nn_screen_launch(const TpwlDev& M, long long batch, int N, cons
     if (useq == usev) return 0;                                    // both or none
     if ((useq ? M.wq : M.wv) < 0.0) return 0;
     if (M.P > kSPts * kSHalf || M.P < 1 || M.r > 128 || M.m > 32 || M.n != 2 * M.r) return 0;
+    if (reinterpret_cast<uintptr_t>(M.A) & 15) return 0;            // the gather uses 16-byte loads
     const ScreenPlan S = make_screen_plan(M.n, M.m, M.r, M.P);
     if (S.total > 220 * 1024) return 0;
     int dev = 0, sms = 148;

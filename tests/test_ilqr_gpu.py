@@ -404,3 +404,33 @@ def test_tpwl_forward_pass_two_stage_search_is_exact_on_ties():
     for b in range(Bt):
         dist = 1.0 * np.linalg.norm(q - x0[b, 36:], axis=1) + 0.0 * np.linalg.norm(data['v'] - x0[b, :36], axis=1)
         assert idx_pass[b, 0] == int(np.argmin(dist))
+
+
+def test_tpwl_diamond_instantiation_agrees_with_runtime_dimension_kernels():
+    """Compile-time-dimension Diamond instantiation (DMMA views, single-thread factorisation) vs the run-time-dimension
+    instantiation of the same templates (SRCB200_ILQR_GENERIC=1): same iteration counts, 1e-9 on x, u, K."""
+    import os
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.tpwl.tpwl import TPWLATV
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost
+    data, Hf = synth.tpwl_bank()
+    g = TPWLATV(data, params={'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}, Hf=Hf, discr_method='zoh')
+    g.pre_discretize(0.01)
+    N, Bt = 40, 6
+    Q = np.zeros((6, 6)); Q[3, 3] = Q[4, 4] = 100.0
+    th = np.linspace(0, 2 * np.pi, N + 1)
+    x0, _ = synth.tpwl_rollout_batch(Bt, N=1, seed=33)
+    zt = np.tile(g.z_ref, (Bt, N + 1, 1))
+    amp = np.linspace(0.3, 1.5, Bt)
+    zt[:, :, 3] += amp[:, None] * np.sin(th)[None]; zt[:, :, 4] += amp[:, None] * np.sin(2 * th)[None]
+    res = {}
+    for tag, env in (("fixed", "0"), ("runtime", "1")):
+        os.environ["SRCB200_ILQR_GENERIC"] = env
+        s = iLQR(0.01, g, QuadraticCost(Q, 1e-5 * np.eye(4), np.zeros((6, 6))), N)
+        s.set_target(zt)
+        res[tag] = s.ilqr_computation(x0) + (s.info['iterations'],)
+    os.environ["SRCB200_ILQR_GENERIC"] = "0"
+    assert np.array_equal(res["fixed"][3], res["runtime"][3])
+    for a, b in zip(res["fixed"][:3], res["runtime"][:3]):
+        assert relerr(a, b) < 1e-9

@@ -151,7 +151,67 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
         }
         int idx = -1;
         bool full_search = !screen_ok;
-        if (screen_ok) {
+        if (screen_ok && useq != usev && P <= 2 * NT) {
+            // ---- one screened bank (the usual case: one non-zero distance weight).  With eps(d) = c1 d + c0 the smallest
+            //      upper bound is U = (1 + c1) w sqrt(min a^) + c0 and "lower bound <= U" is a^ <= ((U + c0) / (w (1 - c1)))^2:
+            //      per point one float minimum and one float compare on the SQUARED screening distance a^; the bound
+            //      arithmetic runs in double on the reduced minimum, the threshold is rounded UP.
+            const double u24 = 5.9604644775390625e-08;   // 2^-24
+            const float* bk = useq ? qf : vf;
+            const float* xs = useq ? sxf + r : sxf;
+            const double w = useq ? M.wq : M.wv;
+            const int p0 = tid, p1 = tid + NT;
+            const bool has0 = p0 < P, has1 = p1 < P;
+            const float* b0 = bk + (has0 ? p0 : 0);
+            const float* b1 = bk + (has1 ? p1 : 0);
+            float a0 = 0.f, a1 = 0.f, xn2 = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < r; ++j) {
+                const float xj = xs[j];
+                xn2 = fmaf(xj, xj, xn2);
+                const float d0 = b0[j * P] - xj, d1 = b1[j * P] - xj;
+                a0 = fmaf(d0, d0, a0);
+                a1 = fmaf(d1, d1, a1);
+            }
+            float amin = INFINITY;
+            if (has0) amin = a0;
+            if (has1) amin = fminf(amin, a1);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, off));
+            float* red_f = reinterpret_cast<float*>(red_d);
+            if (lane == 0) red_f[warp] = amin;
+            if (tid == 0) cand[0] = 0;
+            __syncthreads();
+            float vmin = red_f[0];
+#pragma unroll
+            for (int k2 = 1; k2 < NW; ++k2) vmin = fminf(vmin, red_f[k2]);
+            const double c1 = 34.0 * u24 + 1e-14;
+            const double c0 = u24 * 2.0 * (bank_norm + w * 1.001 * (double)sqrtf(xn2));
+            const double U = (1.0 + c1) * w * sqrt((double)vmin) + c0;
+            const double T = (U + c0) / (w * (1.0 - c1));
+            const double T2 = T * T * (1.0 + 1e-6);
+            const float thr2 = (T2 < 3.0e38) ? __double2float_ru(T2) : INFINITY;       // NaN compares false: full search
+            if (has0 && a0 <= thr2) { const int pos = atomicAdd(&cand[0], 1); if (pos < kFwdNNCandCap) cand[2 + pos] = p0; }
+            if (has1 && a1 <= thr2) { const int pos = atomicAdd(&cand[0], 1); if (pos < kFwdNNCandCap) cand[2 + pos] = p1; }
+            __syncthreads();
+            const int cnt = cand[0];
+            if (cnt == 1) {
+                idx = cand[2];      // the argmin is among the candidates and there is only one: no FP64 evaluation needed
+            } else if (cnt >= 1 && cnt <= kFwdNNCandCap && cnt <= NT) {
+                double best = INFINITY;
+                int bi = 0x7fffffff;
+                if (tid < cnt) {
+                    const int p = cand[2 + tid];
+                    const double dd = tpwl_distance(M, sx, p);       // bit-exact numpy-order FP64 distance
+                    if (dd < best) { best = dd; bi = p; }
+                }
+                cta_argmin<NT>(best, bi, red_d, red_i);
+                if (bi == 0x7fffffff) full_search = true;            // NaN distances: let the full search decide
+                else idx = bi;
+            } else {
+                full_search = true;
+            }
+        } else if (screen_ok) {
             const double u24 = 5.9604644775390625e-08;   // 2^-24
             double ubmin = INFINITY;
             double slack = 0.0;

@@ -76,11 +76,11 @@ __host__ __device__ inline FwdNNPlan make_fwdnn(int n, int m, int nz, int P, int
     return F;
 }
 
-// Task queue of the fast kernel behind the per-problem scratch: 64 ints of counters + the slot ring.  The ring must be
+// Task queues of the fast kernel behind the per-problem scratch: 64 ints of counters + two slot rings (priority classes).  The ring must be
 // longer than (problems that can be queued) + (warps that can wait on a ticket at the same time), see ilqr_fast.cu.
 constexpr int kIlqrQueueWaiters = 8192;
 inline long long ilqr_queue_cap(long long batch) { return 2 * batch + kIlqrQueueWaiters; }
-inline size_t ilqr_queue_bytes(long long batch) { return 256 + sizeof(int) * (size_t)ilqr_queue_cap(batch); }
+inline size_t ilqr_queue_bytes(long long batch) { return 256 + 2 * sizeof(int) * (size_t)ilqr_queue_cap(batch); }   // two rings
 
 struct IlqrArgs {
     int n, m, nz, N, gn, index_lin, shared_target;

@@ -238,11 +238,11 @@ def run_ilqr(args, rank, world, dev_index):
         "clocks": clocks,
         "roofline": {"kernel": "ilqr_ssm_fast_kernel<8>", "bound": "tensor", "achieved": ach, "peak": fp64,
                      "unit": "TFLOP/s", "frac": ach / fp64,
-                     "traffic": 36.34e9 * batch / 4096.0 if (batch == 4096 and N == 100) else None,
+                     "traffic": 36.12e9 * batch / 4096.0 if (batch == 4096 and N == 100) else None,
                      "note": "FP64 pipe (DMMA + DFMA): algorithmic flops of the executed passes (dense counts, bench.py:"
                              "ilqr_flops, DESIGN.md) / event time of the single launch; peak = cuBLAS DGEMM 8192^3 "
                              "measured on this pool (profiles/fp64_peaks_r01.json), of measured; the kernel is "
-                             "dependent-issue-latency bound (n = 6), see profiles/ncu_ilqr_v5_r01.txt; traffic = "
+                             "dependent-issue-latency bound (n = 6), see profiles/ncu_ilqr_v7_r01.txt; traffic = "
                              "dram read+write bytes of one launch from that ncu capture (trajectory records)"},
     }
     return res

@@ -97,6 +97,79 @@ struct IlqrArgs {
     int queue_cap;
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Task queues of the persistent solve kernels (ilqr_fast.cu: a task = one iteration of one problem on one warp;
+// ilqr_impl.cuh: the same on one CTA).  Two priority classes, one ticket ring each.
+// Counters (ints at q): per ring c in {HIGH = 0, LOW = 1}: head q[4c], tail q[4c+1], avail q[4c+2]; q[8] = problems
+// not finished; q[10..11] = sum of initial costs (double), q[12] = their count.  Rings at q + 64 + c * cap.
+// push: p = tail++, slot[p % cap] = id, fence, avail++.   pop: acquire one unit of `avail` (so a committed entry
+// exists for every ticket), t = head++, wait for slot[t % cap] (its push has at least reserved it), take it.
+// ---------------------------------------------------------------------------------------------------------------
+namespace ilqrq {
+constexpr int Q_REMAINING = 8, Q_CSUM = 10, Q_CCNT = 12;
+constexpr int kStarted = 0x5ca1ab1e;        // marker in a problem's saved state: its first task has run
+
+static __global__ void queue_init_kernel(int* q, int cap, int batch, double* ws, long long total, long long state) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) {
+        q[64 + i] = -1;                         // HIGH ring: empty
+        q[64 + cap + i] = i < batch ? i : -1;   // LOW ring: every problem's first task
+    }
+    if (i < batch) reinterpret_cast<int*>(ws + i * total + state + 3)[5] = 0;      // "not started"
+    if (i == 0) {
+        for (int k = 0; k < 16; ++k) q[k] = 0;
+        q[4 + 1] = batch;                       // LOW tail
+        q[4 + 2] = batch;                       // LOW avail
+        q[Q_REMAINING] = batch;
+    }
+}
+
+__device__ __forceinline__ bool try_acquire(int* avail) {
+    if (*(volatile int*)avail <= 0) return false;
+    if (atomicSub(avail, 1) >= 1) return true;
+    atomicAdd(avail, 1);
+    return false;
+}
+
+// one thread: next task id (HIGH ring first), or -1 when every problem is finished
+__device__ __forceinline__ int pop_one(int* q, int cap) {
+    unsigned ns = 256;                          // back off: an idle warp / CTA must not compete with working ones
+    while (true) {
+        int cls = -1;
+        if (try_acquire(q + 2)) cls = 0;
+        else if (try_acquire(q + 4 + 2)) cls = 1;
+        if (cls >= 0) {
+            const int t = atomicAdd(q + 4 * cls, 1);
+            volatile int* slot = q + 64 + cls * cap + (t % cap);
+            int v;
+            while ((v = *slot) < 0) __nanosleep(64);      // the push that owns this ticket is between tail++ and the store
+            *slot = -1;
+            return v;
+        }
+        if (*(volatile int*)(q + Q_REMAINING) <= 0) return -1;
+        __nanosleep(ns);
+        if (ns < 8192) ns <<= 1;
+    }
+}
+
+// one thread, after the caller's release fence
+__device__ __forceinline__ void push_one(int* q, int cap, int id, int cls) {
+    const int p = atomicAdd(q + 4 * cls + 1, 1);
+    atomicExch(q + 64 + cls * cap + (p % cap), id);
+    __threadfence();
+    atomicAdd(q + 4 * cls + 2, 1);
+}
+
+// one thread: priority class from the initial cost -- above the running mean of the batch: HIGH (0), else LOW (1)
+__device__ __forceinline__ int classify(int* q, double cost) {
+    if (!isfinite(cost)) return 1;
+    double* csum = reinterpret_cast<double*>(q + Q_CSUM);
+    const double sprev = atomicAdd(csum, cost);
+    const int cprev = atomicAdd(q + Q_CCNT, 1);
+    return (cost * (double)(cprev + 1) > sprev + cost) ? 0 : 1;
+}
+}  // namespace ilqrq
+
 // rho schedule (ilqr.py:198-217), including the `dhro` typo: drho is never lowered.
 __device__ __forceinline__ void rho_update(const srcb200_ilqr_config& c, bool increase, double& rho, double& drho) {
     if (increase) {

@@ -781,56 +781,13 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
 // warp serves HIGH first.  (Replaying the measured traces of the bench workload: FIFO 134 pass-times, this rule 119,
 // an oracle that knows every length 118.)  Scheduling only: results do not depend on it.
 //
-// Counters (ints at q): per ring c in {HIGH = 0, LOW = 1}: head q[4c], tail q[4c+1], avail q[4c+2]; q[8] = problems
-// not finished; q[10..11] = sum of initial costs (double), q[12] = their count.  Rings at q + 64 + c * cap.
-// push: p = tail++, slot[p % cap] = id, fence, avail++.   pop: acquire one unit of `avail` (so a committed entry
-// exists for every ticket), t = head++, wait for slot[t % cap] (its push has at least reserved it), take it.
-constexpr int Q_REMAINING = 8, Q_CSUM = 10, Q_CCNT = 12;
-
-__global__ void ilqr_queue_init_kernel(int* q, int cap, int batch, double* ws, long long total, long long state) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cap) {
-        q[64 + i] = -1;                         // HIGH ring: empty
-        q[64 + cap + i] = i < batch ? i : -1;   // LOW ring: every problem's first task
-    }
-    if (i < batch) reinterpret_cast<int*>(ws + i * total + state + 3)[5] = 0;      // "not started"
-    if (i == 0) {
-        for (int k = 0; k < 16; ++k) q[k] = 0;
-        q[4 + 1] = batch;                       // LOW tail
-        q[4 + 2] = batch;                       // LOW avail
-        q[Q_REMAINING] = batch;
-    }
-}
-
-__device__ __forceinline__ bool queue_try_acquire(int* avail) {
-    if (*(volatile int*)avail <= 0) return false;
-    if (atomicSub(avail, 1) >= 1) return true;
-    atomicAdd(avail, 1);
-    return false;
-}
+// The queue primitives (counters, rings, pop / push of one id by one thread) are shared with the generic kernel:
+// ilqr.cuh, namespace ilqrq.
+using namespace ilqrq;
 
 __device__ __forceinline__ int queue_pop(int* q, int cap, int lane) {
     int id = -1;
-    if (lane == 0) {
-        unsigned ns = 256;                          // back off: an idle warp must not compete with working ones for
-        while (true) {                              // issue slots and L2 bandwidth (an iteration takes ~1 ms)
-            int cls = -1;
-            if (queue_try_acquire(q + 2)) cls = 0;
-            else if (queue_try_acquire(q + 4 + 2)) cls = 1;
-            if (cls >= 0) {
-                const int t = atomicAdd(q + 4 * cls, 1);
-                volatile int* slot = q + 64 + cls * cap + (t % cap);
-                int v;
-                while ((v = *slot) < 0) __nanosleep(64);      // the push that owns this ticket is between tail++ and the store
-                *slot = -1;
-                id = v;
-                break;
-            }
-            if (*(volatile int*)(q + Q_REMAINING) <= 0) break;
-            __nanosleep(ns);
-            if (ns < 8192) ns <<= 1;
-        }
-    }
+    if (lane == 0) id = pop_one(q, cap);
     id = __shfl_sync(FULL, id, 0);
     __threadfence();            // acquire: what the previous owner of this problem wrote is visible (L1 invalidated)
     return id;
@@ -839,12 +796,7 @@ __device__ __forceinline__ int queue_pop(int* q, int cap, int lane) {
 __device__ __forceinline__ void queue_push(int* q, int cap, int lane, int id, int cls) {
     __threadfence();            // release: this warp's records / gains / state before the id becomes visible
     __syncwarp();
-    if (lane == 0) {
-        const int p = atomicAdd(q + 4 * cls + 1, 1);
-        atomicExch(q + 64 + cls * cap + (p % cap), id);
-        __threadfence();
-        atomicAdd(q + 4 * cls + 2, 1);
-    }
+    if (lane == 0) push_one(q, cap, id, cls);
 }
 
 template <int M>
@@ -894,12 +846,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
             if (a.ocost0 && lane == 0) a.ocost0[b] = cost;
             // priority class: initial cost above the running mean of the batch -> expected to need many iterations
             cls = 1;
-            if (lane == 0 && isfinite(cost)) {
-                double* csum = reinterpret_cast<double*>(a.work_counter + Q_CSUM);
-                const double sprev = atomicAdd(csum, cost);
-                const int cprev = atomicAdd(a.work_counter + Q_CCNT, 1);
-                if (cost * (double)(cprev + 1) > sprev + cost) cls = 0;
-            }
+            if (lane == 0) cls = classify(a.work_counter, cost);
             cls = __shfl_sync(FULL, cls, 0);
         } else {
             rho = sv[0]; drho = sv[1]; cost = sv[2];
@@ -1408,7 +1355,7 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
     const long long ctas = (a.batch + fast::WARPS - 1) / fast::WARPS;
     int grid = (int)(ctas < 2LL * sms ? ctas : 2LL * sms);   // persistent: 2 CTAs (16 warps) per SM
     if (grid * fast::WARPS > kIlqrQueueWaiters) grid = kIlqrQueueWaiters / fast::WARPS;
-    fast::ilqr_queue_init_kernel<<<(a.queue_cap + 255) / 256, 256, 0, st>>>(a.work_counter, a.queue_cap, (int)a.batch, a.ws,
+    ilqrq::queue_init_kernel<<<(a.queue_cap + 255) / 256, 256, 0, st>>>(a.work_counter, a.queue_cap, (int)a.batch, a.ws,
                                                                                  a.L.total, a.L.state);
     SRCB_LAUNCH_CHECK("ilqr_queue_init_kernel");
     if (M.m == 8) {

@@ -569,14 +569,18 @@ ilqr_solve_kernel(typename MP::Dev M, IlqrArgs a) {
     const srcb200_ilqr_config& c = a.cfg;
     load_costs<MP>(a, S, sm);
 
-    // problems differ a lot in iteration count: CTAs take the next unsolved problem from an atomic counter
-    __shared__ long long s_next;
+    // Problems differ a lot in iteration count (TPWL: 10 .. 51), so the unit of work is ONE iteration: everything a
+    // solve needs between iterations lives in global memory (records, gains) plus 8 doubles of solver state, and a
+    // CTA that finishes an iteration puts the problem back on the task queue (ilqr.cuh, namespace ilqrq: two priority
+    // classes by initial cost) and takes the next task.  Results do not depend on which CTA runs which iteration.
+    __shared__ int s_next, s_cls;
     while (true) {
         __syncthreads();
-        if (threadIdx.x == 0) s_next = (long long)atomicAdd(a.work_counter, 1);
+        if (threadIdx.x == 0) s_next = ilqrq::pop_one(a.work_counter, a.queue_cap);
         __syncthreads();
         const long long b = s_next;
-        if (b >= a.batch) break;
+        if (b < 0) break;
+        __threadfence();                // acquire: what the previous owner of this problem wrote
         double* wsb = a.ws + b * a.L.total;
         Rec rec[2] = {rec_at(wsb, a.L), rec_at(wsb + a.L.rec, a.L)};
         double* kbuf = wsb + a.L.k;
@@ -585,78 +589,102 @@ ilqr_solve_kernel(typename MP::Dev M, IlqrArgs a) {
         const double* ztar = a.z_target + (a.shared_target ? 0 : b * (long long)(N + 1) * nz);
         const double* ulast = a.u_last ? a.u_last + b * m : nullptr;
         double* trace = a.otrace ? a.otrace + b * (long long)(c.max_iter + 1) * 4 : nullptr;
+        double* sv = wsb + a.L.state;   // [rho, drho, cost, (fails, cur), (status, trials), (it, started), (class, -)]
+        int* svi = reinterpret_cast<int*>(sv + 3);
 
-        double rho = c.rho0, drho = c.drho0;
-        int fails = 0, cur = 0, status = 0, trials = 0;
-
-        // initial rollout: x_prev = [x0, 0, ...], u = warm start or zeros, K = k = 0 (ilqr.py:41-49).
-        // With K = 0 the x_prev rows are never used beyond row 0, so the nominal can alias the trial record.
-        {
+        double rho, drho, cost;
+        int fails, cur, status, trials, it, cls;
+        if (svi[5] != ilqrq::kStarted) {
+            rho = c.rho0; drho = c.drho0;
+            fails = 0; cur = 0; status = 0; trials = 0; it = 0;
+            // initial rollout: x_prev = [x0, 0, ...], u = warm start or zeros, K = k = 0 (ilqr.py:41-49).
+            // With K = 0 the x_prev rows are never used beyond row 0, so the nominal can alias the trial record.
             Rec& nom = rec[1];
             for (int i = tid; i < n; i += NT) nom.x[i] = a.x0[b * n + i];
             for (long long e = tid; e < (long long)N * m; e += NT) nom.u[e] = a.u_init ? a.u_init[b * (long long)N * m + e] : 0.0;
             cta_sync<NT>();
+            cost = fwd_pass<MP>(M, a, S, sm, rec[1].x, rec[1].u, 1.0, nullptr, nullptr, rec[0], ztar, ulast, nullptr);
+            if (tid == 0) {
+                if (a.ocost0) a.ocost0[b] = cost;
+                s_cls = ilqrq::classify(a.work_counter, cost);
+            }
+            __syncthreads();
+            cls = s_cls;
+        } else {
+            rho = sv[0]; drho = sv[1]; cost = sv[2];
+            fails = svi[0]; cur = svi[1]; status = svi[2]; trials = svi[3]; it = svi[4]; cls = svi[6];
         }
-        double cost = fwd_pass<MP>(M, a, S, sm, rec[1].x, rec[1].u, 1.0, nullptr, nullptr, rec[0], ztar, ulast, nullptr);
-        if (a.ocost0 && tid == 0) a.ocost0[b] = cost;
-        cur = 0;
 
-        bool conv = false;
-        int it = 0;
-        while (!conv && it <= c.max_iter) {
+        bool conv = false, stop = false;
+        if (it <= c.max_iter) {         // one pass of the `while not converged and nbr_iter <= max_iter` loop
             bool give_up = false;
             const int restarts = bwd_pass<MP>(M, a, S, sm, rec[cur], nullptr, nullptr, ulast, Kbuf, kbuf, ab, nullptr,
                                               nullptr, rho, drho, give_up, wsb + a.L.cxx);
             const double rho_bwd = rho;
-            if (give_up) { status |= SRCB200_ILQR_ST_PD_GIVEUP; break; }
-            const double prev_cost = cost;
-            double alpha = c.alpha0;
-            bool improved = false, failed = false;
-            double cost_t = cost, alpha_acc = 0.0;
-            while (!improved && !failed) {
-                improved = true;
-                cost_t = fwd_pass<MP>(M, a, S, sm, rec[cur].x, rec[cur].u, alpha, Kbuf, kbuf, rec[cur ^ 1], ztar, ulast, nullptr);
-                ++trials;
-                // delta_cost = sum_t alpha k^T Q_u + alpha^2/2 k^T Q_uu k, accumulated in t order (ilqr.py:69-71)
-                double dc = 0.0;
-                const double a2 = __dmul_rn(__dmul_rn(alpha, alpha), 0.5);
-                for (int t = 0; t < N; ++t)
-                    dc = __dadd_rn(dc, __dadd_rn(__dmul_rn(alpha, ab[2 * t]), __dmul_rn(a2, ab[2 * t + 1])));
-                alpha_acc = alpha;
-                if (c.do_linesearch) {
-                    const double ratio = __ddiv_rn(__dsub_rn(cost_t, prev_cost), dc);
-                    if (ratio <= c.improv_lb || ratio > c.improv_ub) {
-                        alpha = __dmul_rn(c.alpha_scaling, alpha);
-                        improved = false;
-                        if (alpha < c.alpha_min) {
-                            rho_update(c, true, rho, drho);
-                            rho = __dadd_rn(rho, c.rho_increase_fp);
-                            failed = true;
+            if (give_up) {
+                status |= SRCB200_ILQR_ST_PD_GIVEUP;
+                stop = true;
+            } else {
+                const double prev_cost = cost;
+                double alpha = c.alpha0;
+                bool improved = false, failed = false;
+                double cost_t = cost, alpha_acc = 0.0;
+                while (!improved && !failed) {
+                    improved = true;
+                    cost_t = fwd_pass<MP>(M, a, S, sm, rec[cur].x, rec[cur].u, alpha, Kbuf, kbuf, rec[cur ^ 1], ztar, ulast, nullptr);
+                    ++trials;
+                    // delta_cost = sum_t alpha k^T Q_u + alpha^2/2 k^T Q_uu k, accumulated in t order (ilqr.py:69-71)
+                    double dc = 0.0;
+                    const double a2 = __dmul_rn(__dmul_rn(alpha, alpha), 0.5);
+                    for (int t = 0; t < N; ++t)
+                        dc = __dadd_rn(dc, __dadd_rn(__dmul_rn(alpha, ab[2 * t]), __dmul_rn(a2, ab[2 * t + 1])));
+                    alpha_acc = alpha;
+                    if (c.do_linesearch) {
+                        const double ratio = __ddiv_rn(__dsub_rn(cost_t, prev_cost), dc);
+                        if (ratio <= c.improv_lb || ratio > c.improv_ub) {
+                            alpha = __dmul_rn(c.alpha_scaling, alpha);
+                            improved = false;
+                            if (alpha < c.alpha_min) {
+                                rho_update(c, true, rho, drho);
+                                rho = __dadd_rn(rho, c.rho_increase_fp);
+                                failed = true;
+                            }
                         }
                     }
                 }
+                if (!failed) {
+                    cur ^= 1;
+                    cost = cost_t;
+                    const double dJ = __dsub_rn(prev_cost, cost);
+                    conv = (dJ < c.epsilon) && (dJ >= 0.0);
+                    if (conv) status |= SRCB200_ILQR_ST_CONVERGED;
+                    fails = 0;
+                } else {
+                    ++fails;
+                    if (fails >= c.counter_limit) { conv = true; status |= SRCB200_ILQR_ST_ABANDONED; }
+                }
+                if (trace && tid == 0) {
+                    trace[it * 4 + 0] = cost;
+                    trace[it * 4 + 1] = failed ? 0.0 : alpha_acc;
+                    trace[it * 4 + 2] = rho_bwd;
+                    trace[it * 4 + 3] = (double)restarts;
+                }
+                ++it;
+                if (!isfinite(cost)) { status |= SRCB200_ILQR_ST_NONFINITE; stop = true; }
             }
-            if (!failed) {
-                cur ^= 1;
-                cost = cost_t;
-                const double dJ = __dsub_rn(prev_cost, cost);
-                conv = (dJ < c.epsilon) && (dJ >= 0.0);
-                if (conv) status |= SRCB200_ILQR_ST_CONVERGED;
-                fails = 0;
-            } else {
-                ++fails;
-                if (fails >= c.counter_limit) { conv = true; status |= SRCB200_ILQR_ST_ABANDONED; }
-            }
-            if (trace && tid == 0) {
-                trace[it * 4 + 0] = cost;
-                trace[it * 4 + 1] = failed ? 0.0 : alpha_acc;
-                trace[it * 4 + 2] = rho_bwd;
-                trace[it * 4 + 3] = (double)restarts;
-            }
-            ++it;
-            if (!isfinite(cost)) { status |= SRCB200_ILQR_ST_NONFINITE; break; }
         }
-        if (!conv && it > c.max_iter) status |= SRCB200_ILQR_ST_MAXITER;
+        if (!conv && !stop && it <= c.max_iter) {
+            // not finished: save the state, hand the problem to whichever CTA is free next
+            if (tid == 0) {
+                sv[0] = rho; sv[1] = drho; sv[2] = cost;
+                svi[0] = fails; svi[1] = cur; svi[2] = status; svi[3] = trials; svi[4] = it; svi[5] = ilqrq::kStarted; svi[6] = cls;
+            }
+            __threadfence();            // release: records / gains / state of every thread
+            __syncthreads();
+            if (tid == 0) ilqrq::push_one(a.work_counter, a.queue_cap, (int)b, cls);
+            continue;
+        }
+        if (!conv && !stop && it > c.max_iter) status |= SRCB200_ILQR_ST_MAXITER;
 
         // results
         const Rec& fin = rec[cur];
@@ -668,6 +696,8 @@ ilqr_solve_kernel(typename MP::Dev M, IlqrArgs a) {
             a.oiter[b] = it;
             a.ostatus[b] = status;
             if (a.otrials) a.otrials[b] = trials;
+            __threadfence();
+            atomicSub(a.work_counter + ilqrq::Q_REMAINING, 1);
         }
         cta_sync<NT>();
     }
@@ -817,7 +847,9 @@ static int solve_impl(const typename MP::Dev& M, const srcb200_ilqr_config* cfg,
     }
     auto kern = ilqr_solve_kernel<MP>;
     SRCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SRCB_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
+    ilqrq::queue_init_kernel<<<(a.queue_cap + 255) / 256, 256, 0, st>>>(a.work_counter, a.queue_cap, (int)a.batch, a.ws,
+                                                                        a.L.total, a.L.state);
+    SRCB_LAUNCH_CHECK("queue_init_kernel");
     kern<<<grid_size<MP>(a.batch, smem, 1), MP::NT, smem, st>>>(M, a);
     SRCB_LAUNCH_CHECK("ilqr_solve_kernel");
     return 0;

@@ -93,6 +93,7 @@ struct IlqrArgs {
     double* ws;
     Layout L;
     int model_scratch;          // doubles of model scratch in shared memory
+    double prio_frac;           // HIGH class: initial cost > prio_frac * running mean
     int* work_counter;          // fast kernel's task queue: ints [head, tail, remaining, pad..64) then `queue_cap` slots
     int queue_cap;
 };
@@ -161,12 +162,12 @@ __device__ __forceinline__ void push_one(int* q, int cap, int id, int cls) {
 }
 
 // one thread: priority class from the initial cost -- above the running mean of the batch: HIGH (0), else LOW (1)
-__device__ __forceinline__ int classify(int* q, double cost) {
+__device__ __forceinline__ int classify(int* q, double cost, double frac = 1.0) {
     if (!isfinite(cost)) return 1;
     double* csum = reinterpret_cast<double*>(q + Q_CSUM);
     const double sprev = atomicAdd(csum, cost);
     const int cprev = atomicAdd(q + Q_CCNT, 1);
-    return (cost * (double)(cprev + 1) > sprev + cost) ? 0 : 1;
+    return (cost * (double)(cprev + 1) > frac * (sprev + cost)) ? 0 : 1;
 }
 }  // namespace ilqrq
 

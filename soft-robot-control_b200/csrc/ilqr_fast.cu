@@ -846,7 +846,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
             if (a.ocost0 && lane == 0) a.ocost0[b] = cost;
             // priority class: initial cost above the running mean of the batch -> expected to need many iterations
             cls = 1;
-            if (lane == 0) cls = classify(a.work_counter, cost);
+            if (lane == 0) cls = classify(a.work_counter, cost, a.prio_frac);
             cls = __shfl_sync(FULL, cls, 0);
         } else {
             rho = sv[0]; drho = sv[1]; cost = sv[2];

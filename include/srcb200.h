@@ -221,6 +221,10 @@ typedef struct srcb200_ilqr_result {
                              failed), rho after the backward pass, number of PD restarts}; NULL allowed */
 } srcb200_ilqr_result;
 
+/* Device scratch of one solve_batch call: per problem two trajectory records (accepted / trial), the feed-forward
+ * gains, the line-search scalars and 8 doubles of saved solver state, plus the task queues of the persistent kernels
+ * (a problem is suspended after every iteration and resumed by the next free warp / CTA).  Contents need not be
+ * initialised or preserved between calls. */
 size_t srcb200_ilqr_workspace_bytes(int32_t model_kind, const void* model, const srcb200_ilqr_problem* prob);
 
 /* Replaces iLQR.ilqr_computation (ilqr.py:27-107) for prob->batch independent problems; one CTA per problem.

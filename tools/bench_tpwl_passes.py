@@ -1,5 +1,8 @@
 """One forward pass and one backward pass of the Diamond TPWL iLQR on a batch (unit entry points), for per-pass timing
-under `ncu --metrics gpu__time_duration.sum`."""
+under `ncu --metrics gpu__time_duration.sum`.
+
+Phase clocks of the backward sweep: compile csrc/ilqr_tpwl_diamond.cu with -DSRCB_PHASE_TIMING (the kernel then writes
+its per-phase clock64 totals into the Q_u output), relink, and run with SRCB_PHASE_TIMING=1 in the environment."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

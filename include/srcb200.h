@@ -227,7 +227,8 @@ typedef struct srcb200_ilqr_result {
  * initialised or preserved between calls. */
 size_t srcb200_ilqr_workspace_bytes(int32_t model_kind, const void* model, const srcb200_ilqr_problem* prob);
 
-/* Replaces iLQR.ilqr_computation (ilqr.py:27-107) for prob->batch independent problems; one CTA per problem.
+/* Replaces iLQR.ilqr_computation (ilqr.py:27-107) for prob->batch independent problems.  Persistent kernel: one
+ * warp (Trunk / Diamond SSM shape) or one CTA (every other model) runs one iteration of one problem at a time.
  * model_kind selects the struct behind `model` (srcb200_ssm_model / srcb200_tpwl_model). */
 int srcb200_ilqr_solve_batch(int32_t model_kind, const void* model, const srcb200_ilqr_config* cfg,
                              const srcb200_ilqr_problem* prob, const srcb200_ilqr_result* res, void* workspace,

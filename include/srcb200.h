@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SRCB200_ABI_VERSION 1
+#define SRCB200_ABI_VERSION 2
 
 /* error codes (<0) */
 #define SRCB200_E_NULL        (-1)  /* required pointer is NULL */
@@ -173,11 +173,11 @@ typedef struct srcb200_ilqr_config {   /* field for field iLQRConfig (lqr/config
     double  epsilon;
     double  alpha0, alpha_scaling, improv_lb, improv_ub, alpha_min;
     double  rho0, drho0, rho_scaling, rho_increase_fp, rho_max, rho_min;
-    int32_t max_pd_restarts;   /* NEW: the reference loops forever when rho saturates and Q_uu~ is still not PD
-                                  (ilqr.py:234,282-287); the kernel gives up after this many restarts of one
-                                  backward pass and flags the problem (status bit SRCB200_ILQR_ST_PD_GIVEUP) */
-    int32_t _pad;
 } srcb200_ilqr_config;
+/* Non-PD Q_uu~ (ilqr.py:276-299), reproduced literally: with `regularize` rho is raised, the backward sweep stops at
+ * that step (K_t = k_t = 0 for every t at or below it), rho is lowered once as after a complete sweep and the line
+ * search runs with those gains -- the reference never restarts the sweep (its comment at ilqr.py:287 says it does;
+ * the `break` only leaves the for loop).  Without `regularize` the non-PD matrix is inverted as it is. */
 
 #define SRCB200_ILQR_MODEL_SSM  0
 #define SRCB200_ILQR_MODEL_TPWL 1
@@ -186,7 +186,7 @@ typedef struct srcb200_ilqr_config {   /* field for field iLQRConfig (lqr/config
 #define SRCB200_ILQR_ST_CONVERGED   1   /* 0 <= J_prev - J < epsilon (ilqr.py:109-115) */
 #define SRCB200_ILQR_ST_MAXITER     2   /* left the loop on nbr_iter > max_iter (ilqr.py:54) */
 #define SRCB200_ILQR_ST_ABANDONED   4   /* counter_limit consecutive line-search failures (ilqr.py:98-103) */
-#define SRCB200_ILQR_ST_PD_GIVEUP   8   /* max_pd_restarts exceeded */
+#define SRCB200_ILQR_ST_NONPD       8   /* some backward sweep met a non-PD Q_uu~ (ilqr.py:282-287) */
 #define SRCB200_ILQR_ST_NONFINITE  16   /* cost became NaN/Inf */
 
 typedef struct srcb200_ilqr_problem {
@@ -218,7 +218,8 @@ typedef struct srcb200_ilqr_result {
     int32_t* status;      /* batch : SRCB200_ILQR_ST_* bits */
     int32_t* trials;      /* batch : total number of line-search forward passes (NULL allowed) */
     double*  trace;       /* optional batch x (max_iter+1) x 4 : per iteration {cost after, alpha accepted (0 if
-                             failed), rho after the backward pass, number of PD restarts}; NULL allowed */
+                             failed), rho after the backward pass, horizon index of the failed PD test of that
+                             backward pass or -1}; NULL allowed */
 } srcb200_ilqr_result;
 
 /* Device scratch of one solve_batch call: per problem two trajectory records (accepted / trial), the feed-forward
@@ -243,11 +244,12 @@ int srcb200_ilqr_forward_pass(int32_t model_kind, const void* model, const srcb2
                               void* stream);
 
 /* Replaces iLQR.dlqr_recursion (ilqr.py:219-300): nominal x,u and its linearisation A,B -> K, k, Q_u, Q_uu and
- * the updated (rho, drho) (batch each, in/out). */
+ * the updated (rho, drho) (batch each, in/out); pd_fail_step (batch, NULL allowed): horizon index at which the PD
+ * test failed and the sweep stopped (K, k zero from there down, Q_u / Q_uu zero below it), -1 if it never failed. */
 int srcb200_ilqr_backward_pass(int32_t model_kind, const void* model, const srcb200_ilqr_config* cfg,
                                const srcb200_ilqr_problem* prob, const double* x, const double* u,
                                const double* A, const double* B, double* K, double* k, double* Q_u, double* Q_uu,
-                               double* rho, double* drho, int32_t* restarts, void* workspace,
+                               double* rho, double* drho, int32_t* pd_fail_step, void* workspace,
                                size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -37,7 +37,7 @@ class Config:
 
 
 class ILQRNP:
-    def __init__(self, dt, model, cost_params, planning_horizon, max_pd_restarts=10000):
+    def __init__(self, dt, model, cost_params, planning_horizon):
         self.params = Config()
         self.dt, self.model, self.cost = dt, model, cost_params
         self.N = planning_horizon
@@ -45,7 +45,6 @@ class ILQRNP:
         self.z_target = None
         self.u_last = np.zeros(self.m)
         self.trace = []
-        self.max_pd_restarts = max_pd_restarts  # the reference loops forever if rho saturates (ilqr.py:234,282-287)
 
     def set_target(self, z_target):
         self.z_target = z_target.copy()
@@ -106,63 +105,62 @@ class ILQRNP:
 
     # ---- backward pass: ilqr.py:219-300
     def dlqr_recursion(self, x, u, A, B, d):
+        """Literal control flow of ilqr.py:236-300.  On a failed Cholesky with `regularize` the reference bumps rho
+        (ilqr.py:286), `break`s out of the `for` (287) and then FALLS THROUGH to the rho decrease (298) and the
+        `break` of the `while` (299): there is no restart (the comment at 287 says otherwise; the code wins).  It
+        returns with K[t] = k[t] = 0 for t <= t_fail, Q_u[t_fail] / Q_uu[t_fail] written, Q_u / Q_uu zero below.
+        With `regularize=False` a non-PD Q_uu is inverted as it is (no break)."""
         N, n, m = self.N, self.n, self.m
         Pm = self.params
-        restarts = 0
-        while True:
-            Q_u = np.zeros((N, m)); Q_uu = np.zeros((N, m, m))
-            K = np.zeros((N, m, n)); k = np.zeros((N, m))
-            # terminal_cost_vectors (ilqr.py:177-182): z first, then model.H is read
-            e = self._zerr(x[-1], -1)
+        self._last_pd_fail = -1                     # horizon index of the failed PD test (-1: none); trace only
+        Q_u = np.zeros((N, m)); Q_uu = np.zeros((N, m, m))
+        K = np.zeros((N, m, n)); k = np.zeros((N, m))
+        # terminal_cost_vectors (ilqr.py:177-182): z first, then model.H is read
+        e = self._zerr(x[-1], -1)
+        H = self.model.H
+        P = H.T @ self.cost.Qf @ H
+        p = H.T @ self.cost.Qf @ e
+        for t in reversed(range(N)):
+            # step_cost_vectors (ilqr.py:186-196)
+            e = self._zerr(x[t], t)
             H = self.model.H
-            P = H.T @ self.cost.Qf @ H
-            p = H.T @ self.cost.Qf @ e
-            ok = True
-            for t in reversed(range(N)):
-                # step_cost_vectors (ilqr.py:186-196)
-                e = self._zerr(x[t], t)
-                H = self.model.H
-                c_xx = H.T @ self.cost.Q @ H
-                c_x = H.T @ self.cost.Q @ e
-                up = self._u_prev(u, t)
-                c_u = self.cost.R @ u[t] if up is None else self.cost.R @ (u[t] - up)
-                c_uu = self.cost.R
-                Q_x = c_x + A[t].T @ p
-                Q_u[t] = c_u + B[t].T @ p
-                Q_xx = c_xx + A[t].T @ P @ A[t]
-                Q_uu[t] = c_uu + B[t].T @ P @ B[t]
-                Q_ux = B[t].T @ P @ A[t]
-                if Pm.regularize:
-                    if Pm.state_regularization:
-                        Preg = P + self.rho * np.eye(n)
-                        Q_uu_t = c_uu + B[t].T @ Preg @ B[t]
-                        Q_ux_t = B[t].T @ Preg @ A[t]
-                    else:
-                        Q_uu_t = Q_uu[t] + self.rho * np.eye(m)
-                        Q_ux_t = Q_ux
+            c_xx = H.T @ self.cost.Q @ H
+            c_x = H.T @ self.cost.Q @ e
+            up = self._u_prev(u, t)
+            c_u = self.cost.R @ u[t] if up is None else self.cost.R @ (u[t] - up)
+            c_uu = self.cost.R
+            Q_x = c_x + A[t].T @ p
+            Q_u[t] = c_u + B[t].T @ p
+            Q_xx = c_xx + A[t].T @ P @ A[t]
+            Q_uu[t] = c_uu + B[t].T @ P @ B[t]
+            Q_ux = B[t].T @ P @ A[t]
+            if Pm.regularize:
+                if Pm.state_regularization:
+                    Preg = P + self.rho * np.eye(n)
+                    Q_uu_t = c_uu + B[t].T @ Preg @ B[t]
+                    Q_ux_t = B[t].T @ Preg @ A[t]
                 else:
-                    Q_uu_t, Q_ux_t = Q_uu[t], Q_ux
-                try:
-                    np.linalg.cholesky(Q_uu_t)
-                    pos_def = True
-                except np.linalg.LinAlgError:
-                    pos_def = False
-                if not pos_def and Pm.regularize:
+                    Q_uu_t = Q_uu[t] + self.rho * np.eye(m)
+                    Q_ux_t = Q_ux
+            else:
+                Q_uu_t, Q_ux_t = Q_uu[t], Q_ux
+            try:
+                np.linalg.cholesky(Q_uu_t)
+                pos_def = True
+            except np.linalg.LinAlgError:
+                pos_def = False
+            if not pos_def:
+                if self._last_pd_fail < 0:
+                    self._last_pd_fail = t
+                if Pm.regularize:
                     self.update_regularization(increase=True)
-                    ok = False
-                    break
-                inv = np.linalg.inv(Q_uu_t)
-                K[t] = - inv @ Q_ux_t
-                k[t] = - inv @ Q_u[t]
-                p = Q_x + K[t].T @ Q_uu[t] @ k[t] + K[t].T @ Q_u[t] + Q_ux.T @ k[t]
-                P = Q_xx + K[t].T @ Q_uu[t] @ K[t] + K[t].T @ Q_ux + Q_ux.T @ K[t]
-            if ok:
-                self.update_regularization(increase=False)
-                break
-            restarts += 1
-            if restarts >= self.max_pd_restarts:
-                raise RuntimeError('rho saturated and Q_uu_tilde still not PD (reference would loop forever)')
-        self._last_restarts = restarts
+                    break                            # ilqr.py:287 -- leaves the for loop only
+            inv = np.linalg.inv(Q_uu_t)
+            K[t] = - inv @ Q_ux_t
+            k[t] = - inv @ Q_u[t]
+            p = Q_x + K[t].T @ Q_uu[t] @ k[t] + K[t].T @ Q_u[t] + Q_ux.T @ k[t]
+            P = Q_xx + K[t].T @ Q_uu[t] @ K[t] + K[t].T @ Q_ux + Q_ux.T @ K[t]
+        self.update_regularization(increase=False)   # ilqr.py:298, reached on BOTH paths
         return K, k, Q_u, Q_uu
 
     # ---- outer loop: ilqr.py:27-115
@@ -182,7 +180,7 @@ class ILQRNP:
         K = None
         while not conv and it <= Pm.max_iter:
             K, k, Q_u, Q_uu = self.dlqr_recursion(x, u, A, B, d)
-            ev = {'it': it, 'pd_restarts': self._last_restarts, 'rho_after_bwd': float(self.rho), 'trials': []}
+            ev = {'it': it, 'pd_fail_t': self._last_pd_fail, 'rho_after_bwd': float(self.rho), 'trials': []}
             prev_cost = cost
             alpha = Pm.alpha0
             improved = failed = False

@@ -12,6 +12,8 @@ Fixtures written
                           recorded outputs z_big.csv and the MSEs of the FP64 restatement (be / fe / discrete).
   ssm_ilqr.npz            reference iLQR class (ilqr.py, unmodified) driving the SSM restatement through the
                           Gauss-Newton H-property adapter: Diamond (m=4) and Trunk (m=8) figure-8 solves.
+  ilqr_nonpd.npz          reference iLQR class on indefinite stage costs: the non-PD branch of dlqr_recursion
+                          (ilqr.py:276-299, no restart) -- full solves + one backward pass.
   tpwl_small.npz          reference TPWLATV (tpwl.py, unmodified) on a small seeded bank: nearest indices, weights,
                           Jacobians (fe/be/bil/zoh), rollouts (nn + weighting), and a reference iLQR solve.
   tpwl_diamond_nn.npz     reference calc_nearest_point on the Diamond-shaped bank (P=1000, r=36): 512 states.
@@ -46,9 +48,64 @@ def small_tpwl_bank(seed=11, r=5, m=3, P=40):
     return synth.tpwl_bank(seed=seed, r=r, m=m, P=P, num_nodes=20, tip_node=7, spread=1.0)
 
 
+NONPD_CASES = [("d4_first_step", 4, 15, 3.0, -5000.0), ("t8_mid", 8, 40, 6.0, -50.0), ("t8_long", 8, 40, 6.0, -500.0),
+               ("d4_mid", 4, 30, 6.0, -200.0)]
+
+
+def nonpd_golden(ref):
+    """Drives the UNMODIFIED reference iLQR class through `Q_uu not PD` (ilqr.py:282-299).  The failing step of each
+    backward sweep is recovered by wrapping (not editing) dlqr_recursion: the first all-zero K row from the top."""
+    import sofacontrol_b200.synth as synth
+    out = {}
+    for tag, m, N, amp, q22 in NONPD_CASES:
+        s = synth.trunk_ssm(m)
+        mdl = ssm_np.GaussNewtonSSM(ssm_np.SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'],
+                                                         params=s['params']))
+        Q, R, Qf = synth.trunk_ilqr_costs(6, m)
+        Q = Q.copy(); Q[2, 2] = q22
+        sol = ref.ilqr.iLQR(0.02, mdl, ref.utils.QuadraticCost(Q, R, Qf), N)
+        sol.set_target(synth.figure8_targets(s['z_ref'], N, amp)[0])
+        fails, calls = [], []
+        inner = sol.dlqr_recursion
+
+        def wrapped(x, u, A, B, d, inner=inner):
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                K, k, Qu, Quu = inner(x, u, A, B, d)
+            tf = -1
+            if 'not PD' in buf.getvalue():
+                # the sweep stopped at t_fail: Q_uu[t_fail] was assigned (non-zero, it contains R), Q_uu below is zero
+                tf = min(t for t in range(N) if Quu[t].any())
+            fails.append(tf)
+            calls.append((x.copy(), u.copy(), A.copy(), B.copy(), d.copy(), K.copy(), k.copy(), Qu.copy(), Quu.copy()))
+            return K, k, Qu, Quu
+        sol.dlqr_recursion = wrapped
+        x, u, K = quiet(sol.ilqr_computation, np.zeros(6))
+        out.update({tag + '_x': x, tag + '_u': u, tag + '_K': K, tag + '_rho': sol.rho, tag + '_iterations': len(fails),
+                    tag + '_pd_fail_t': np.array(fails)})
+        print("nonpd", tag, "iterations", len(fails), "pd_fail_t", fails[:8], "rho", sol.rho)
+        if tag == "t8_long":
+            # unit backward pass: replay the first interrupted sweep from rho = drho = 0
+            i = next(j for j, f in enumerate(fails) if f >= 0)
+            xx, uu, AA, BB, dd = calls[i][:5]
+            sol.dlqr_recursion = inner
+            sol.rho, sol.drho = 0.0, 0.0
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                Kb, kb, Qub, Quub = sol.dlqr_recursion(xx, uu, AA, BB, dd)
+            assert 'not PD' in buf.getvalue()
+            out.update(unit_x=xx, unit_u=uu, unit_A=AA, unit_B=BB, unit_d=dd, unit_K=Kb, unit_k=kb, unit_Qu=Qub,
+                       unit_Quu=Quub, unit_rho=sol.rho, unit_drho=sol.drho,
+                       unit_pd_fail_t=min(t for t in range(N) if Quub[t].any()))
+    return out
+
+
 def main():
     ref = refimport.load()
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'nonpd':
+        np.savez_compressed(os.path.join(GOLD, "ilqr_nonpd.npz"), **nonpd_golden(ref))
+        return
     from scipy.io import loadmat
     from scipy.interpolate import interp1d
     import sofacontrol_b200.synth as synth
@@ -112,6 +169,9 @@ def main():
                     tag + '_bp_k': kb, tag + '_bp_Qu': Qub, tag + '_bp_Quu': Quub, tag + '_bp_rho': solver.rho})
         print("ssm ilqr", tag, "cost", cf)
     np.savez_compressed(os.path.join(GOLD, "ssm_ilqr.npz"), **res)
+
+    # ---------------------------------------------------------------- non-PD branch of the reference class
+    np.savez_compressed(os.path.join(GOLD, "ilqr_nonpd.npz"), **nonpd_golden(ref))
 
     # ---------------------------------------------------------------- small TPWL bank through the reference class
     data, Hf = small_tpwl_bank()

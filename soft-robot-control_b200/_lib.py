@@ -17,7 +17,8 @@ DISCR = {'fe': 0, 'be': 1, 'bil': 2, 'zoh': 3, 'none': 4}
 TPWL_METHOD = {'nn': 0, 'weighting': 1}
 E_NULL, E_DIM, E_METHOD, E_WORKSPACE, E_NOGPU = -1, -2, -3, -4, -5
 ILQR_MODEL_SSM, ILQR_MODEL_TPWL = 0, 1
-ST_CONVERGED, ST_MAXITER, ST_ABANDONED, ST_PD_GIVEUP, ST_NONFINITE = 1, 2, 4, 8, 16
+ABI_VERSION = 2
+ST_CONVERGED, ST_MAXITER, ST_ABANDONED, ST_NONPD, ST_NONFINITE = 1, 2, 4, 8, 16
 SSM_MAX_ORDER = 4
 
 c_dp = C.c_void_p  # device pointers travel as plain addresses
@@ -44,8 +45,7 @@ class IlqrConfig(C.Structure):
                 ("alpha0", C.c_double), ("alpha_scaling", C.c_double), ("improv_lb", C.c_double),
                 ("improv_ub", C.c_double), ("alpha_min", C.c_double),
                 ("rho0", C.c_double), ("drho0", C.c_double), ("rho_scaling", C.c_double),
-                ("rho_increase_fp", C.c_double), ("rho_max", C.c_double), ("rho_min", C.c_double),
-                ("max_pd_restarts", C.c_int32), ("_pad", C.c_int32)]
+                ("rho_increase_fp", C.c_double), ("rho_max", C.c_double), ("rho_min", C.c_double)]
 
 
 class IlqrProblem(C.Structure):
@@ -127,7 +127,7 @@ def lib():
         fn = getattr(L, name)   # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if L.srcb200_abi_version() != 1:
+    if L.srcb200_abi_version() != ABI_VERSION:
         raise RuntimeError("libsrcb200 ABI mismatch")
     _LIB = L
     return L

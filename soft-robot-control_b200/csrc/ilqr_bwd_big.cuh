@@ -295,7 +295,7 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
                             const double* __restrict__ Adense, const double* __restrict__ Bdense,
                             const double* __restrict__ ulast, double* __restrict__ Kout, double* __restrict__ kout,
                             double* __restrict__ ab, double* __restrict__ Quout, double* __restrict__ Quuout,
-                            double& rho, double& drho, bool& give_up, double* __restrict__ cxx) {
+                            double& rho, double& drho, double* __restrict__ cxx) {
     constexpr int NT = MP::NT;
     constexpr int NW = NT / 32;
     const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
@@ -312,8 +312,7 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
     const srcb200_ilqr_config& c = a.cfg;
     const bool sreg = c.regularize && c.state_regularization;
     const bool aligned4 = (n % 4 == 0) && (m % 4 == 0);      // K segments are whole m8n8k4 steps: strided views
-    int restarts = 0;
-    give_up = false;
+    int pd_fail = -1;
 
     auto lin_of = [&](int t) {
         if (a.index_lin) return MP::bank(M, rc.idx[t]);
@@ -328,7 +327,7 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
     mm<NT, false, false>(cxx, n, T1, nz, sHc, n, n, n, nz);
     __threadfence_block();
 
-    while (true) {
+    {
         // terminal_cost_vectors (ilqr.py:177-182): P_N = (H^T Qf) H, p_N = (H^T Qf) e_N
         for (int i = tid; i < nz; i += NT) se[i] = rc.e[N * nz + i];
         for (int e = tid; e < n * LD; e += NT) Pp[e] = 0.0;
@@ -345,7 +344,6 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
         }
         cta_sync<NT>();
 
-        bool ok = true;
         auto prefetch_small = [&](int t) {
             double* dst = sm + ((t & 1) ? G.pf1 : G.pf0);
             for (int i = tid; i < nz; i += NT) cp_async8(dst + i, rc.e + t * nz + i);
@@ -480,9 +478,29 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
             cta_sync<NT>();
             PH(4);
             const bool pd = (*flag != 0);
+            if (!pd && pd_fail < 0) pd_fail = t;
             if (!pd && c.regularize) {
+                // ilqr.py:282-287: raise rho and leave the sweep (no restart -- the code falls through to the decrease
+                // at 298).  Q_u[t], Q_uu[t] are assigned; K, k and the line-search scalars of every s <= t stay zero.
                 rho_update(c, true, rho, drho);
-                ok = false;
+                if (Quout) for (int i = tid; i < m; i += NT) Quout[t * m + i] = Qu[i];
+                if (Quuout) for (int e = tid; e < m * m; e += NT) Quuout[(long long)t * m * m + e] = Quu[e];
+                for (long long e = tid; e < (long long)(t + 1) * m * n; e += NT) Kout[e] = 0.0;
+                for (int e = tid; e < (t + 1) * m; e += NT) kout[e] = 0.0;
+                if (Quout) for (int e = tid; e < t * m; e += NT) Quout[e] = 0.0;
+                if (Quuout) for (long long e = tid; e < (long long)t * m * m; e += NT) Quuout[e] = 0.0;
+                for (int e = tid; e < 2 * t; e += NT) ab[e] = 0.0;
+                if (tid == 0) {
+                    double sacc = 0.0, qq = 0.0;      // k = 0 evaluated literally (0 * inf = nan like numpy)
+                    for (int i = 0; i < m; ++i) sacc = __dadd_rn(sacc, __dmul_rn(0.0, Qu[i]));
+                    for (int j = 0; j < m; ++j) {
+                        double v = 0.0;
+                        for (int i = 0; i < m; ++i) v = __dadd_rn(v, __dmul_rn(0.0, Quu[i * m + j]));
+                        qq = __dadd_rn(qq, __dmul_rn(v, 0.0));
+                    }
+                    ab[2 * t] = sacc;
+                    ab[2 * t + 1] = qq;
+                }
                 break;
             }
             // ---- gains (ilqr.py:289-292): K = -inv Q_ux~, k = -inv Q_u, one column per thread, and with it that
@@ -572,16 +590,11 @@ __device__ int bwd_pass_big(const typename MP::Dev& M, const IlqrArgs& a, const 
 #ifdef SRCB_PHASE_TIMING
         if (tid == 0 && Quout) for (int i = 0; i < 8; ++i) Quout[i] = (double)ph[i];
 #endif
-        if (ok) {
-            rho_update(c, false, rho, drho);
-            break;
-        }
-        cp_async_wait_all();        // a prefetch may still be in flight into the buffers the restart reuses
+        cp_async_wait_all();        // an interrupted sweep may leave a prefetch in flight into buffers the caller reuses
         cta_sync<NT>();
-        ++restarts;
-        if (restarts >= c.max_pd_restarts) { give_up = true; break; }
+        rho_update(c, false, rho, drho);      // ilqr.py:298 -- after a complete AND after an interrupted sweep
     }
-    return restarts;
+    return pd_fail;
 }
 
 }  // namespace srcb

@@ -15,7 +15,7 @@
 //     partial dots are spread over the 32 lanes (4 accumulators each) and read their coefficients from a
 //     conflict-free table built once per CTA.
 //
-// Control flow (line search, rho schedule, PD restarts, convergence) is identical to the generic kernel in ilqr.cu
+// Control flow (line search, rho schedule, interrupted sweep on a non-PD Q_uu~, convergence) is identical to the generic kernel in ilqr.cu
 // and to the reference (ilqr.py:27-107); results agree with it to rounding (tests/test_ilqr_gpu.py).
 #include <cstdlib>
 #include "ilqr.cuh"
@@ -534,7 +534,7 @@ __device__ __noinline__ double fwd_fast(const Ctx c, const IlqrArgs& a, int disc
 // ---------------------------------------------------------------------------------------------------------------
 // Backward pass (ilqr.py:219-300).  The record of step t-1 is fetched into registers while step t computes.
 // ---------------------------------------------------------------------------------------------------------------
-struct BwdResult { double rho, drho; int restarts; int give_up; };
+struct BwdResult { double rho, drho; int pd_fail; };   // pd_fail: horizon index of the failed PD test, -1: none
 
 #define LOAD_STEP(tt)                                                                                        \
     do {                                                                                                     \
@@ -612,11 +612,10 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
     const int bo0 = (lane / M) * LD + lane % M;
     const int bo1 = ((32 + lane) / M) * LD + (32 + lane) % M;
     const int ko0 = (lane / 6) * LD + lane % 6, ko1 = ((32 + lane) / 6) * LD + (32 + lane) % 6;   // K elements lane, 32+lane
-    int restarts = 0;
-    int give_up = 0;
+    int pd_fail = -1;
     double pa0, pa1, ph0, ph1, pb0, pb1, pe, pu, pup;   // record of the next step to process, in registers
 
-    while (true) {
+    {
         for (int t = 0; t < NTILES; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
         __syncwarp();
         // terminal: (P | p) = (H^T Qf) (H | e)                                   (ilqr.py:177-182)
@@ -639,7 +638,6 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
         if (lane == 0) A[6 * LD + 6] = 1.0;
         __syncwarp();
 
-        bool ok = true;
         for (int t = N - 1; t >= 0; --t) {
             // ---- level 0: stage A_t, B_t, (H_t | e_t), du from the prefetched registers; fetch step t-1
             A[c.off0] = pa0;
@@ -715,9 +713,29 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
             __syncwarp();
             // ---- level 3: PD test + gains (K | k) = -Q_uu~^-1 (Q_ux~ | Q_u)         (ilqr.py:276-292)
             const bool pd = gj_solve_spd<M>(QT, RHS, KT, lane);
+            if (!pd && pd_fail < 0) pd_fail = t;
             if (!pd && cf.regularize) {
+                // ilqr.py:282-287: raise rho and LEAVE the sweep -- the reference then falls through to the decrease
+                // of ilqr.py:298 and returns; there is no restart.  K_s = k_s = 0 for every s <= t (their zero
+                // initialisation), hence zero line-search scalars (evaluated literally at t: 0 * inf = nan like numpy).
                 rho_update(cf, true, rho, drho);
-                ok = false;
+                double za = 0.0, zb = 0.0;
+                if (lane < M) {
+                    za = __dmul_rn(0.0, QUX[lane * LD + 6]);
+                    double v = 0.0;
+#pragma unroll
+                    for (int i = 0; i < M; ++i) v = __dadd_rn(v, __dmul_rn(0.0, QUU[i * LD + lane]));
+                    zb = __dmul_rn(v, 0.0);
+                }
+#pragma unroll
+                for (int off = 1; off < 8; off <<= 1) {
+                    za = __dadd_rn(za, __shfl_xor_sync(FULL, za, off));
+                    zb = __dadd_rn(zb, __shfl_xor_sync(FULL, zb, off));
+                }
+                for (int e = lane; e < (t + 1) * M * 6; e += 32) Kout[e] = 0.0;
+                for (int e = lane; e < (t + 1) * M; e += 32) kout[e] = 0.0;
+                for (int e = lane; e < 2 * t; e += 32) ab[e] = 0.0;
+                if (lane == 0) { ab[2 * t] = za; ab[2 * t + 1] = zb; }
                 break;
             }
             __syncwarp();
@@ -754,14 +772,9 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
             store_frag(P, qxx, g, q);
             // the (K | k) tile is W next step: its column 7 must be zero again, rows >= M too (they are: K rows >= M = 0)
         }
-        if (ok) {
-            rho_update(cf, false, rho, drho);
-            break;
-        }
-        ++restarts;
-        if (restarts >= cf.max_pd_restarts) { give_up = 1; break; }
+        rho_update(cf, false, rho, drho);         // ilqr.py:298 -- after a complete AND after an interrupted sweep
     }
-    return BwdResult{rho, drho, restarts, give_up};
+    return BwdResult{rho, drho, pd_fail};
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -858,12 +871,10 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
             const Rec rcur = rec_at(wsb + (cur ? a.L.rec : 0), a.L), rtrial = rec_at(wsb + (cur ? 0 : a.L.rec), a.L);
             const BwdResult br = bwd_fast<M>(c, a, rcur, ulast, Kbuf, kbuf, ab, rho, drho);
             rho = br.rho; drho = br.drho;
-            const int restarts = br.restarts;
+            const int pd_fail = br.pd_fail;
             const double rho_bwd = rho;
-            if (br.give_up) {
-                status |= SRCB200_ILQR_ST_PD_GIVEUP;
-                stop = true;
-            } else {
+            if (pd_fail >= 0) status |= SRCB200_ILQR_ST_NONPD;
+            {
                 __syncwarp();
                 const double prev_cost = cost;
                 double alpha = cf.alpha0;
@@ -906,7 +917,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
                     trace[it * 4 + 0] = cost;
                     trace[it * 4 + 1] = failed ? 0.0 : alpha_acc;
                     trace[it * 4 + 2] = rho_bwd;
-                    trace[it * 4 + 3] = (double)restarts;
+                    trace[it * 4 + 3] = (double)pd_fail;
                 }
                 ++it;
                 if (!isfinite(cost)) { status |= SRCB200_ILQR_ST_NONFINITE; stop = true; }

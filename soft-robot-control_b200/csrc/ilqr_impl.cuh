@@ -1,5 +1,5 @@
 // ilqr_impl.cuh -- batched iLQR (templates, instantiated per model policy in ilqr_ssm.cu / ilqr_tpwl.cu): one CTA per problem walks the reference algorithm (sofacontrol/lqr/ilqr.py:27-300)
-// branch for branch; every per-problem decision (line search, regularisation schedule, PD restarts, convergence)
+// branch for branch; every per-problem decision (line search, regularisation schedule, PD test, convergence)
 // is taken inside the kernel and reported per problem.
 //
 // Structure (Appendix B of SURVEY.md):
@@ -344,19 +344,22 @@ __device__ double fwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const S
 // ---------------------------------------------------------------------------------------------------------------
 // Backward pass (ilqr.py:219-300).  Reads the accepted record `rc`, writes K (N x m x n), k (N x m) and the two
 // line-search scalars per step ab[2t] = k_t . Q_u,t, ab[2t+1] = (k_t^T Q_uu,t) . k_t.  Optional dense Q_u / Q_uu.
-// Returns the number of PD restarts; rho/drho are updated in place.  give_up is set when max_pd_restarts hit.
+// Returns the horizon index of the (first) failed PD test, -1 if every Q_uu~ was PD; rho/drho are updated in place.
+// Control flow of the failed test = the reference's literal code (ilqr.py:282-299): with `regularize` rho is raised,
+// the sweep STOPS at that step (K_t = k_t = 0 for every t <= t_fail, Q_u / Q_uu of t_fail already written), then rho
+// is lowered once like after a complete sweep -- there is no restart.  Without `regularize` the sweep goes on.
 // ---------------------------------------------------------------------------------------------------------------
 template <class MP>
 __device__ int bwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const Smem& S, double* sm, const Rec& rc,
                         const double* __restrict__ Adense, const double* __restrict__ Bdense,
                         const double* __restrict__ ulast, double* __restrict__ Kout, double* __restrict__ kout,
                         double* __restrict__ ab, double* __restrict__ Quout, double* __restrict__ Quuout,
-                        double& rho, double& drho, bool& give_up, double* __restrict__ cxx_global) {
+                        double& rho, double& drho, double* __restrict__ cxx_global) {
     constexpr int NT = MP::NT;
     if constexpr (MP::NT > 32) {
         if (use_big_bwd(NT, MP::CN ? MP::CN : a.n, a.gn))
             return bwd_pass_big<MP>(M, a, S, sm, rc, Adense, Bdense, ulast, Kout, kout, ab, Quout, Quuout, rho, drho,
-                                    give_up, cxx_global);
+                                    cxx_global);
     }
     const int n = MP::CN ? MP::CN : a.n, m = MP::CM ? MP::CM : a.m, nz = MP::CNZ ? MP::CNZ : a.nz, N = a.N, tid = threadIdx.x;
     double* P = sm + S.P;      double* p = sm + S.p;      double* AtP = sm + S.AtP;   double* BtP = sm + S.BtP;
@@ -372,8 +375,7 @@ __device__ int bwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const Smem
     int* piv = reinterpret_cast<int*>(sm + S.ints);
     int* flag = piv + m + 2;
     const srcb200_ilqr_config& c = a.cfg;
-    int restarts = 0;
-    give_up = false;
+    int pd_fail = -1;
 
     // constant-H cost Hessians are computed once per pass (cheap): T1 = H^T Q, cxx = T1 H
     if (!a.gn) {
@@ -383,7 +385,7 @@ __device__ int bwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const Smem
         cta_sync<NT>();
     }
 
-    while (true) {
+    {
         // terminal_cost_vectors (ilqr.py:177-182): P_N = (H^T Qf) H, p_N = (H^T Qf) e_N
         const double* HN = sHc;
         if (a.gn) {
@@ -398,7 +400,6 @@ __device__ int bwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const Smem
         mv<NT, false>(p, T1f, nz, se, n, nz);
         cta_sync<NT>();
 
-        bool ok = true;
         for (int t = N - 1; t >= 0; --t) {
             // ---- stage step data
             LinRef lin;
@@ -466,9 +467,31 @@ __device__ int bwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const Smem
             }
             // ---- PD test by Cholesky (ilqr.py:276-287)
             const bool pd = cholesky_pd<NT>(Quut, Lc, flag, m);
+            if (!pd && pd_fail < 0) pd_fail = t;
             if (!pd && c.regularize) {
+                // ilqr.py:282-287: raise rho and leave the sweep.  Q_u[t], Q_uu[t] are already assigned (258-261);
+                // K, k (and with them the line-search scalars) stay at their zero initialisation for every s <= t.
                 rho_update(c, true, rho, drho);
-                ok = false;
+                if (Quout) for (int i = tid; i < m; i += NT) Quout[t * m + i] = Qu[i];
+                if (Quuout) for (int e = tid; e < m * m; e += NT) Quuout[(long long)t * m * m + e] = Quu[e];
+                for (long long e = tid; e < (long long)(t + 1) * m * n; e += NT) Kout[e] = 0.0;
+                for (int e = tid; e < (t + 1) * m; e += NT) kout[e] = 0.0;
+                if (Quout) for (int e = tid; e < t * m; e += NT) Quout[e] = 0.0;
+                if (Quuout) for (long long e = tid; e < (long long)t * m * m; e += NT) Quuout[e] = 0.0;
+                for (int e = tid; e < 2 * t; e += NT) ab[e] = 0.0;
+                if (tid == 0) {
+                    // alpha * k^T Q_u + alpha^2/2 * k^T Q_uu k with k = 0, evaluated literally (0 * inf = nan)
+                    double s = 0.0, q = 0.0;
+                    for (int i = 0; i < m; ++i) s = __dadd_rn(s, __dmul_rn(0.0, Qu[i]));
+                    for (int j = 0; j < m; ++j) {
+                        double v = 0.0;
+                        for (int i = 0; i < m; ++i) v = __dadd_rn(v, __dmul_rn(0.0, Quu[i * m + j]));
+                        q = __dadd_rn(q, __dmul_rn(v, 0.0));
+                    }
+                    ab[2 * t] = s;
+                    ab[2 * t + 1] = q;
+                }
+                cta_sync<NT>();
                 break;
             }
             // ---- gains (ilqr.py:289-292): explicit inverse, K = -inv Q_ux~, k = -inv Q_u
@@ -536,14 +559,9 @@ __device__ int bwd_pass(const typename MP::Dev& M, const IlqrArgs& a, const Smem
             }
             cta_sync<NT>();
         }
-        if (ok) {
-            rho_update(c, false, rho, drho);
-            break;
-        }
-        ++restarts;
-        if (restarts >= c.max_pd_restarts) { give_up = true; break; }
+        rho_update(c, false, rho, drho);      // ilqr.py:298 -- reached after a complete AND after an interrupted sweep
     }
-    return restarts;
+    return pd_fail;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -619,14 +637,11 @@ ilqr_solve_kernel(typename MP::Dev M, IlqrArgs a) {
 
         bool conv = false, stop = false;
         if (it <= c.max_iter) {         // one pass of the `while not converged and nbr_iter <= max_iter` loop
-            bool give_up = false;
-            const int restarts = bwd_pass<MP>(M, a, S, sm, rec[cur], nullptr, nullptr, ulast, Kbuf, kbuf, ab, nullptr,
-                                              nullptr, rho, drho, give_up, wsb + a.L.cxx);
+            const int pd_fail = bwd_pass<MP>(M, a, S, sm, rec[cur], nullptr, nullptr, ulast, Kbuf, kbuf, ab, nullptr,
+                                             nullptr, rho, drho, wsb + a.L.cxx);
             const double rho_bwd = rho;
-            if (give_up) {
-                status |= SRCB200_ILQR_ST_PD_GIVEUP;
-                stop = true;
-            } else {
+            if (pd_fail >= 0) status |= SRCB200_ILQR_ST_NONPD;
+            {
                 const double prev_cost = cost;
                 double alpha = c.alpha0;
                 bool improved = false, failed = false;
@@ -669,7 +684,7 @@ ilqr_solve_kernel(typename MP::Dev M, IlqrArgs a) {
                     trace[it * 4 + 0] = cost;
                     trace[it * 4 + 1] = failed ? 0.0 : alpha_acc;
                     trace[it * 4 + 2] = rho_bwd;
-                    trace[it * 4 + 3] = (double)restarts;
+                    trace[it * 4 + 3] = (double)pd_fail;
                 }
                 ++it;
                 if (!isfinite(cost)) { status |= SRCB200_ILQR_ST_NONFINITE; stop = true; }
@@ -772,17 +787,16 @@ ilqr_backward_kernel(typename MP::Dev M, IlqrArgs a, const double* __restrict__ 
         cta_sync<NT>();
         __threadfence_block();
         double rho = rho_io[b], drho = drho_io[b];
-        bool give_up = false;
         IlqrArgs a2 = a;
         a2.index_lin = 0;     // dense A/B are supplied by the caller
         const int r = bwd_pass<MP>(M, a2, S, sm, rc, A + b * (long long)N * n * n, B + b * (long long)N * n * m, ulast,
                                    K + b * (long long)N * m * n, k + b * (long long)N * m, wsb + a.L.ab,
                                    Qu ? Qu + b * (long long)N * m : nullptr, Quu ? Quu + b * (long long)N * m * m : nullptr, rho, drho,
-                                   give_up, wsb + a.L.cxx);
+                                   wsb + a.L.cxx);
         if (tid == 0) {
             rho_io[b] = rho;
             drho_io[b] = drho;
-            if (restarts_o) restarts_o[b] = give_up ? -r : r;
+            if (restarts_o) restarts_o[b] = r;          // horizon index of the failed PD test, -1: none
         }
         cta_sync<NT>();
     }

@@ -24,9 +24,6 @@ _OPTIONS = {
     "rho_max": (1e5, ""),
     "rho_min": (1e-3, ""),
     "state_regularization": (True, "rho enters through B^T (P + rho I) B; False: Q_uu + rho I"),
-    # NEW (not in the reference): the reference loops forever when rho saturates at rho_max and Q_uu~ is still not
-    # PD (ilqr.py:234,282-287); the kernel stops after this many restarts of one backward pass and flags the problem.
-    "max_pd_restarts": (200, ""),
 }
 
 

@@ -72,7 +72,7 @@ class iLQR:
                             improv_lb=float(p.improv_lb), improv_ub=float(p.improv_ub), alpha_min=float(p.alpha_min),
                             rho0=float(p.rho0), drho0=float(p.drho0), rho_scaling=float(p.rho_scaling),
                             rho_increase_fp=float(p.rho_increase_fp), rho_max=float(p.rho_max),
-                            rho_min=float(p.rho_min), max_pd_restarts=int(getattr(p, 'max_pd_restarts', 200)))
+                            rho_min=float(p.rho_min))
 
     def _model_handle(self):
         if self._kind == L.ILQR_MODEL_SSM:
@@ -232,14 +232,14 @@ class iLQR:
         Qu, Quu = L.empty((Bt, N, m)), L.empty((Bt, N, m, m))
         rho = L.to_dev(np.broadcast_to(np.asarray(self.rho, dtype=np.float64), (Bt,)))
         drho = L.to_dev(np.broadcast_to(np.asarray(self.drho, dtype=np.float64), (Bt,)))
-        restarts = L.empty((Bt,), torch.int32)
+        pd_fail = L.empty((Bt,), torch.int32)
         L.check(L.lib().srcb200_ilqr_backward_pass(self._kind, C_addr(handle), self._cfg(), pr, L.ptr(xd), L.ptr(ud),
                                                    L.ptr(Ad), L.ptr(Bd), L.ptr(K), L.ptr(k), L.ptr(Qu), L.ptr(Quu),
-                                                   L.ptr(rho), L.ptr(drho), L.ptr(restarts), L.ptr(ws), ws.numel() * 8,
+                                                   L.ptr(rho), L.ptr(drho), L.ptr(pd_fail), L.ptr(ws), ws.numel() * 8,
                                                    L.stream_ptr()))
         rho_h, drho_h = L.to_host(rho), L.to_host(drho)
         self.rho, self.drho = (rho_h[0], drho_h[0]) if single else (rho_h, drho_h)
-        self.info['pd_restarts'] = L.to_host(restarts)
+        self.info['pd_fail_step'] = L.to_host(pd_fail)     # -1: every Q_uu~ was PD
         res = [L.to_host(t) for t in (K, k, Qu, Quu)]
         return tuple(r[0] for r in res) if single else tuple(res)
 
@@ -255,6 +255,31 @@ class iLQR:
         e = z - np.asarray(self.z_target)[step, :]
         du = u if u_prev_step is None else (u - u_prev_step)
         return .5 * e.T @ self.cost_params.Q @ e + .5 * du.T @ self.cost_params.R @ du
+
+    def _H_at(self, x):
+        """The output Jacobian the cost derivatives use: constant model.H (ilqr.py:178,187 as written), or in
+        Gauss-Newton mode H(x) = dC/dx from the model's device evaluation (SURVEY.md App. C.2 adapter)."""
+        if self.gauss_newton:
+            return np.asarray(self.model.get_observer_jacobians(np.asarray(x, dtype=np.float64))[0])
+        return np.asarray(self.model.H)
+
+    def terminal_cost_vectors(self, x):
+        """ilqr.py:177-182 -> (c, c_x, c_xx) with Qf.  Single-state helper like the reference's; the solver kernels
+        form the same quantities per step on the device."""
+        z = self.model.x_to_zfyf(x, zf=True)
+        H = self._H_at(x)
+        e = z - np.asarray(self.z_target)[-1, :]
+        Qf = np.asarray(self.cost_params.Qf)
+        return (.5 * e.T @ Qf @ e, H.T @ Qf @ e, H.T @ Qf @ H)
+
+    def step_cost_vectors(self, x, u, step, u_prev_step=None):
+        """ilqr.py:184-196 -> (c, c_x, c_xx, c_u, c_uu)."""
+        z = self.model.x_to_zfyf(x, zf=True)
+        H = self._H_at(x)
+        e = z - np.asarray(self.z_target)[step, :]
+        Q, R = np.asarray(self.cost_params.Q), np.asarray(self.cost_params.R)
+        du = u if u_prev_step is None else (u - u_prev_step)
+        return (.5 * e.T @ Q @ e + .5 * du.T @ R @ du, H.T @ Q @ e, H.T @ Q @ H, R @ du, R)
 
     def update_regularization(self, increase=True):
         """ilqr.py:198-217 on the host-side scalars (the kernel carries its own per-problem copy); keeps the

@@ -24,14 +24,14 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing symbol %s" % n
     assert sorted(_lib.EXPORTED_SYMBOLS) == names          # the ctypes table binds exactly the header's API
-    assert _lib.lib().srcb200_abi_version() == 1
+    assert _lib.lib().srcb200_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header_sizes():
     from sofacontrol_b200 import _lib
     assert ctypes.sizeof(_lib.SsmModel) == 6 * 4 + 6 * 8
     assert ctypes.sizeof(_lib.TpwlModel) == 6 * 4 + 3 * 8 + 7 * 8
-    assert ctypes.sizeof(_lib.IlqrConfig) == 6 * 4 + 12 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.IlqrConfig) == 6 * 4 + 12 * 8
     assert ctypes.sizeof(_lib.IlqrProblem) == 8 + 4 + 4 + 8 + 8 * 8 + 8
     assert ctypes.sizeof(_lib.IlqrResult) == 10 * 8
 
@@ -128,4 +128,4 @@ def test_ilqr_config_defaults_match_reference_fields():
     a, b = vars(iLQRConfig()), vars(Config())
     for k, v in b.items():
         assert a[k] == v
-    assert set(a) - set(b) == {'max_pd_restarts'}
+    assert set(a) == set(b)

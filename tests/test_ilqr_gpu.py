@@ -95,7 +95,7 @@ def test_branch_trace_matches_oracle():
         tr = s.info['trace'][b]
         for ev in o.trace:
             i = ev['it']
-            assert tr[i, 3] == ev['pd_restarts']
+            assert tr[i, 3] == ev['pd_fail_t']
             assert abs(tr[i, 2] - ev['rho_after_bwd']) <= 1e-12 * max(1.0, ev['rho_after_bwd'])
             assert (tr[i, 1] > 0) == ev['accepted']
             if ev['accepted']:
@@ -289,7 +289,7 @@ def _pair(m, N, tweak, zt, Qscale=1.0, x0=None, Qneg=False):
     if Qneg:
         Q = Q.copy(); Q[2, 2] = -5000.0          # indefinite stage cost: Q_uu~ loses positive definiteness
     s = iLQR(0.02, model, QC(Q, R, Qf), N, trace=True)
-    o = ILQRNP(0.02, _oracle_ssm(m), QuadraticCost(Q, R, Qf), N, max_pd_restarts=60)
+    o = ILQRNP(0.02, _oracle_ssm(m), QuadraticCost(Q, R, Qf), N)
     for obj in (s, o):
         tweak(obj.params)
         obj.set_target(zt)
@@ -319,23 +319,57 @@ def test_branch_paths_line_search_failure_and_abandon():
         assert abs(s.info['trace'][ev['it'], 2] - ev['rho_after_bwd']) <= 1e-12 * max(1.0, ev['rho_after_bwd'])
 
 
-def test_branch_paths_non_pd_restarts():
-    """An indefinite stage cost makes Q_uu~ non-PD: the backward pass restarts with increased rho until the
-    Cholesky test passes (ilqr.py:276-287); restart counts and the rho schedule must match the oracle."""
-    import sofacontrol_b200.synth as synth
-    s_, _ = _ssm(4)
-    zt = synth.figure8_targets(s_['z_ref'], 15, 3.0)[0]
+NONPD_CASES = [("d4_first_step", 4, 15, 3.0, -5000.0), ("t8_mid", 8, 40, 6.0, -50.0), ("t8_long", 8, 40, 6.0, -500.0),
+               ("d4_mid", 4, 30, 6.0, -200.0)]
 
-    def tweak(p):
-        p.max_iter = 2
-    s, o, (x, u, K), x0 = _pair(4, 15, tweak, zt, Qneg=True)
-    xo, uo, Ko = o.ilqr_computation(x0)
-    assert sum(ev['pd_restarts'] for ev in o.trace) > 0                    # the path is really exercised
-    assert s.info['iterations'] == o.iterations
-    for ev in o.trace:
-        assert s.info['trace'][ev['it'], 3] == ev['pd_restarts']
-        assert abs(s.info['trace'][ev['it'], 2] - ev['rho_after_bwd']) <= 1e-12 * max(1.0, ev['rho_after_bwd'])
-    assert relerr(x, xo) < 1e-8 and relerr(u, uo) < 1e-8 and relerr(K, Ko) < 1e-8
+
+@pytest.mark.parametrize("tag,m,N,amp,q22", NONPD_CASES)
+def test_non_pd_branch_matches_reference_golden(golden, tag, m, N, amp, q22):
+    """Indefinite stage cost -> Q_uu~ fails the Cholesky test.  The reference (ilqr.py:282-299) raises rho, LEAVES the
+    backward sweep (K_t = k_t = 0 at and below the failing step), lowers rho once and line-searches with those
+    gains; it never restarts.  Golden = the unmodified reference class (oracle/make_golden.py: ilqr_nonpd.npz);
+    the oracle restatement is pinned bitwise to it (tests/test_oracle_vs_reference.py).  Compared: iteration
+    count, rho, the failing step of every backward sweep, the exact zero pattern of K, and x, u, K at 1e-9."""
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost as QC
+    g = golden("ilqr_nonpd.npz")
+    s_, model = _ssm(m)
+    Q, R, Qf = synth.trunk_ilqr_costs(6, m)
+    Q = Q.copy(); Q[2, 2] = q22
+    zt = synth.figure8_targets(s_['z_ref'], N, amp)[0]
+    s = iLQR(0.02, model, QC(Q, R, Qf), N, trace=True)
+    s.set_target(zt)
+    x, u, K = s.ilqr_computation(np.zeros(6))
+    it = int(g[tag + '_iterations'])
+    assert int(s.info['iterations']) == it
+    assert np.array_equal(s.info['trace'][:it, 3].astype(int), g[tag + '_pd_fail_t'])
+    assert (g[tag + '_pd_fail_t'] >= 0).any() and (s.info['status'] & 8)      # the path is really exercised
+    assert abs(float(s.info['rho']) - float(g[tag + '_rho'])) <= 1e-12 * max(1.0, float(g[tag + '_rho']))
+    assert np.array_equal(K == 0.0, g[tag + '_K'] == 0.0)
+    assert relerr(x, g[tag + '_x']) < TOL and relerr(u, g[tag + '_u']) < TOL and relerr(K, g[tag + '_K']) < TOL
+
+
+def test_non_pd_backward_pass_unit_matches_reference_golden(golden):
+    """dlqr_recursion alone on the non-PD case: K, k, Q_u, Q_uu with the reference's zero pattern (gains zero at and
+    below the failing step, Q_u / Q_uu zero strictly below it), rho raised once then lowered once."""
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost as QC
+    g = golden("ilqr_nonpd.npz")
+    s_, model = _ssm(8)
+    Q, R, Qf = synth.trunk_ilqr_costs(6, 8)
+    Q = Q.copy(); Q[2, 2] = -500.0
+    s = iLQR(0.02, model, QC(Q, R, Qf), 40)
+    s.set_target(synth.figure8_targets(s_['z_ref'], 40, 6.0)[0])
+    s.rho, s.drho = 0.0, 0.0
+    K, k, Qu, Quu = s.dlqr_recursion(g['unit_x'], g['unit_u'], g['unit_A'], g['unit_B'], g['unit_d'])
+    tf = int(g['unit_pd_fail_t'])
+    assert int(s.info['pd_fail_step']) == tf and tf >= 0
+    assert not K[:tf + 1].any() and not k[:tf + 1].any() and not Qu[:tf].any() and not Quu[:tf].any()
+    assert relerr(K, g['unit_K']) < TOL and relerr(k, g['unit_k']) < TOL
+    assert relerr(Qu, g['unit_Qu']) < TOL and relerr(Quu, g['unit_Quu']) < TOL
+    assert float(s.rho) == float(g['unit_rho']) and float(s.drho) == float(g['unit_drho'])
 
 
 def test_branch_paths_max_iter_and_no_linesearch():

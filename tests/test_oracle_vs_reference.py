@@ -99,6 +99,38 @@ def test_ilqr_restatement_bitwise_on_ssm_adapter(ref):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("m,N,amp,q22,max_iter", [(4, 15, 3.0, -5000.0, 2), (8, 40, 6.0, -50.0, 50), (8, 40, 6.0, -500.0, 12),
+                                                  (4, 30, 6.0, -200.0, 50)])
+def test_ilqr_restatement_bitwise_on_the_non_pd_branch(ref, m, N, amp, q22, max_iter):
+    """ilqr.py:276-299 on an indefinite stage cost: the UNMODIFIED reference class prints 'Q_uu not PD', raises rho,
+    leaves the sweep and falls through to the decrease -- no restart, zero gains at and below the failing step.
+    The restatement must follow it bit for bit (x, u, K, rho) and report the same number of failed PD tests."""
+    import sofacontrol_b200.synth as synth
+    from oracle.ssm_np import SSMDynamicsNP, GaussNewtonSSM
+    from oracle.ilqr_np import ILQRNP
+    from oracle.utils_np import QuadraticCost
+    s = synth.trunk_ssm(m)
+    zt = synth.figure8_targets(s['z_ref'], N, amp)[0]
+    Q, R, Qf = synth.trunk_ilqr_costs(6, m)
+    Q = Q.copy(); Q[2, 2] = q22
+    out, counts = [], []
+    for cls, qc in ((ref.ilqr.iLQR, ref.utils.QuadraticCost), (ILQRNP, QuadraticCost)):
+        mdl = GaussNewtonSSM(SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params']))
+        sol = cls(0.02, mdl, qc(Q, R, Qf), N)
+        sol.params.max_iter = max_iter
+        sol.set_target(zt)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf), np.errstate(all='ignore'):
+            out.append(sol.ilqr_computation(np.zeros(6)) + (sol.rho,))
+        if cls is ILQRNP:
+            counts.append((sum(1 for ev in sol.trace if ev['pd_fail_t'] >= 0), sol.iterations))
+        else:
+            counts.append((buf.getvalue().count('not PD'), buf.getvalue().count('Iteration')))
+    assert counts[0] == counts[1] and counts[0][0] > 0
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+
+
 def test_pod_restatement(ref):
     import sofacontrol_b200.synth as synth
     from oracle import pod_np

@@ -26,5 +26,5 @@ print('oracle iters', o.iterations, 'cost', o.final_cost)
 tr = sol.info['trace']
 for ev in o.trace:
     i = ev['it']
-    print(i, 'oracle: acc', ev['accepted'], 'ntr', len(ev['trials']), 'cost %.12g' % ev['cost'], 'rho %.6g' % ev['rho_after_bwd'], 'restarts', ev['pd_restarts'],
+    print(i, 'oracle: acc', ev['accepted'], 'ntr', len(ev['trials']), 'cost %.12g' % ev['cost'], 'rho %.6g' % ev['rho_after_bwd'], 'pd_fail_t', ev['pd_fail_t'],
           '| gpu: alpha', tr[i, 1], 'cost %.12g' % tr[i, 0], 'rho %.6g' % tr[i, 2], 'restarts', tr[i, 3], ' ratios', [('%.3g' % t[2]) for t in ev['trials']])

@@ -9,9 +9,12 @@ Fixtures written
                           output z_eq = linearModel([1354],1628).evaluate(x_eq, qv=True) from rest_qv.pkl
                           (examples/hardware/diamond_SSM.py:88-102).  Model INPUT data for every SSM test/bench.
   ssm_module_test.npz     the reference's manual module_test (diamond_SSM.py:83-140): recorded inputs u_big.csv,
-                          recorded outputs z_big.csv and the MSEs of the FP64 restatement (be / fe / discrete).
-  ssm_ilqr.npz            reference iLQR class (ilqr.py, unmodified) driving the SSM restatement through the
-                          Gauss-Newton H-property adapter: Diamond (m=4) and Trunk (m=8) figure-8 solves.
+                          recorded outputs z_big.csv, rollouts and MSEs of the reference SSMDynamics class
+                          (ssm.py UNMODIFIED, run on oracle/jax_shim.py) for be / fe / bil / discrete.
+  ssm_units.npz           reference SSMDynamics on 64 seeded states: f, C, W, (A, B, d) continuous / fe / be / bil /
+                          discrete, (H, c), update_state -- Diamond (m=4) and Trunk (m=8) models.
+  ssm_ilqr.npz            reference iLQR class (ilqr.py, unmodified) driving the reference SSMDynamics class through
+                          the Gauss-Newton H-property adapter: Diamond (m=4) and Trunk (m=8) figure-8 solves.
   ilqr_nonpd.npz          reference iLQR class on indefinite stage costs: the non-PD branch of dlqr_recursion
                           (ilqr.py:276-299, no restart) -- full solves + one backward pass.
   tpwl_small.npz          reference TPWLATV (tpwl.py, unmodified) on a small seeded bank: nearest indices, weights,
@@ -138,9 +141,10 @@ def main():
     u_int = interp1d(t_orig, u_true, axis=0)(t_int)
     z_qv = interp1d(t_orig, np.hstack((zq, zv)), axis=0)(t_int)
     out = dict(u=u_int, z_true_qv=z_qv, dt=dt)
+    rssm = refimport.load_ssm()        # sofacontrol/SSM/ssm.py UNMODIFIED, on the jax stand-in of oracle/jax_shim.py
     for name, kw in (('be', dict(discrete=False, discr_method='be')), ('fe', dict(discrete=False, discr_method='fe')),
                      ('bil', dict(discrete=False, discr_method='bil')), ('disc', dict(discrete=True, discr_method='be'))):
-        m = ssm_np.SSMDynamicsNP(z_eq, model=mdl, params=prm, **kw)
+        m = rssm.SSMDynamics(z_eq, model=mdl, params=prm, **kw)
         x, z = m.rollout(np.zeros(6), u_int, dt)
         err = z_qv - z[:-1]
         out['x_' + name] = x
@@ -149,11 +153,40 @@ def main():
         print("module_test", name, out['mse_' + name])
     np.savez_compressed(os.path.join(GOLD, "ssm_module_test.npz"), **out)
 
+    # ---------------------------------------------------------------- unit evaluations of the reference SSM class
+    units = {}
+    for tag, mm in (('diamond', 4), ('trunk', 8)):
+        sm = synth.trunk_ssm(mm)
+        rng = np.random.default_rng(100 + mm)
+        xs = rng.normal(size=(64, 6)) * np.array([3.0, 3.0, 3.0, 30.0, 30.0, 30.0])
+        us = rng.uniform(0, 800, size=(64, mm))
+        zs = sm['z_ref'] + rng.normal(size=(64, 6)) * np.array([3.0, 3.0, 3.0, 20.0, 20.0, 20.0])
+        units[tag + '_x'], units[tag + '_u'], units[tag + '_z'] = xs, us, zs
+        c = rssm.SSMDynamics(sm['z_ref'], discrete=False, discr_method='fe', model=sm['model'], params=sm['params'])
+        units[tag + '_f'] = np.array([c.reduced_dynamics(x, u) for x, u in zip(xs, us)])
+        units[tag + '_C'] = np.array([c.C_map(x) for x in xs])
+        units[tag + '_zf'] = np.asarray(c.x_to_zfyf(xs))
+        units[tag + '_W'] = np.array([c.compute_RO_state(z) for z in zs])
+        J = [c.get_continuous_jacobians(x, u) for x, u in zip(xs, us)]
+        for i, nm in enumerate('ABd'):
+            units[tag + '_c' + nm] = np.array([np.asarray(j[i]) for j in J])
+        O = [c.get_observer_jacobians(x) for x in xs]
+        units[tag + '_H'] = np.array([np.asarray(o[0]) for o in O])
+        units[tag + '_c'] = np.array([np.asarray(o[1]) for o in O])
+        for meth, kw in (('fe', dict(discrete=False, discr_method='fe')), ('be', dict(discrete=False, discr_method='be')),
+                         ('bil', dict(discrete=False, discr_method='bil')), ('disc', dict(discrete=True, discr_method='be'))):
+            mdl_ = rssm.SSMDynamics(sm['z_ref'], model=sm['model'], params=sm['params'], **kw)
+            J = [mdl_.get_jacobians(x, u, 0.02) for x, u in zip(xs, us)]
+            for i, nm in enumerate('ABd'):
+                units['%s_%s_%s' % (tag, meth, nm)] = np.array([np.asarray(j[i]) for j in J])
+            units['%s_%s_next' % (tag, meth)] = np.array([mdl_.update_state(x, u, 0.02) for x, u in zip(xs, us)])
+    np.savez_compressed(os.path.join(GOLD, "ssm_units.npz"), **units)
+
     # ---------------------------------------------------------------- SSM iLQR through the unmodified reference class
     res = {}
     for tag, mm in (('diamond', 4), ('trunk', 8)):
         s = synth.trunk_ssm(mm)
-        m = ssm_np.SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
+        m = rssm.SSMDynamics(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
         Nh = 100
         zt = synth.figure8_targets(s['z_ref'], Nh, 5.0)[0]
         Q, R, Qf = synth.trunk_ilqr_costs(6, mm)

@@ -5,7 +5,8 @@ numpy restatements in oracle/*.py against the real reference.  Never imported by
 
 `sofacontrol/utils.py:5` does `import osqp` at module top; osqp is absent here and only
 `Polyhedron(with_reproject=True)` touches it, so an empty stub module is injected.
-`sofacontrol/SSM/ssm.py` needs jax and is NOT importable; see oracle/ssm_np.py.
+`sofacontrol/SSM/ssm.py` needs jax (absent here): `load_ssm()` registers the stand-in of oracle/jax_shim.py (numpy
+float64 for `jax.numpy`, identity `jit`, exact forward-mode dual-number `jacobian`) and imports the file UNMODIFIED.
 """
 import os
 import sys
@@ -37,3 +38,14 @@ def load():
         import sofacontrol.measurement_models as measurement_models
     return types.SimpleNamespace(utils=utils, pod=pod, tpwl=tpwl, ilqr=ilqr, config=config,
                                  measurement_models=measurement_models, root=REFERENCE_ROOT)
+
+
+def load_ssm():
+    """The reference's sofacontrol.SSM.ssm module, imported unmodified on top of oracle/jax_shim.py."""
+    load()
+    from oracle import jax_shim
+    jax_shim.install()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import sofacontrol.SSM.ssm as ssm
+    return ssm

@@ -1,9 +1,11 @@
-"""FP64 numpy restatement of sofacontrol/SSM/ssm.py (the reference needs jax, absent here: "parity unpinned").
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+"""FP64 numpy restatement of sofacontrol/SSM/ssm.py.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+PINNED against the reference file itself, imported unmodified on oracle/jax_shim.py
+(tests/test_oracle_vs_reference.py::test_ssm_restatement_vs_unmodified_reference_class, golden ssm_units.npz /
+ssm_module_test.npz / ssm_ilqr.npz produced by the reference class).
 
 Monomial order (ssm.py:158-164): sympy `itermonomials(vars, order)` sorted by grevlex on reversed variables with the
 constant dropped == for d = 1..order: itertools.combinations_with_replacement(range(dim), d)
-(verified against sympy in tests/test_oracle_ssm.py).  Jacobians (ssm.py:198-235, jax.jacobian in the reference)
+(verified against sympy and against the reference's lambdified basis in tests/test_oracle_vs_reference.py).  Jacobians (ssm.py:198-235, jax.jacobian in the reference)
 are the analytic  coeff @ dphi/dx.
 """
 import itertools

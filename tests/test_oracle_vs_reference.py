@@ -131,6 +131,102 @@ def test_ilqr_restatement_bitwise_on_the_non_pd_branch(ref, m, N, amp, q22, max_
         assert np.array_equal(a, b)
 
 
+@pytest.fixture(scope="module")
+def ref_ssm():
+    return refimport.load_ssm()
+
+
+@pytest.mark.parametrize("m", [4, 8])
+@pytest.mark.parametrize("kw", [dict(discrete=False, discr_method='fe'), dict(discrete=False, discr_method='be'),
+                                dict(discrete=False, discr_method='bil'), dict(discrete=True, discr_method='be')])
+def test_ssm_restatement_vs_unmodified_reference_class(ref_ssm, m, kw):
+    """sofacontrol/SSM/ssm.py imported UNMODIFIED (jax replaced by oracle/jax_shim.py: numpy float64 + exact
+    forward-mode dual-number jacobian) vs oracle/ssm_np.py.  Maps, Jacobians and A_d agree to 1e-14 of their scale (bitwise on most
+    inputs: the only difference in arithmetic is x**3 by libm pow in the lambdified basis vs (x*x)*x in the
+    restatement, which is also how XLA lowers integer_pow); the cancellation residue d (ssm.py:203) within a few
+    ulp of its largest term."""
+    import sofacontrol_b200.synth as synth
+    from oracle.ssm_np import SSMDynamicsNP
+    s = synth.trunk_ssm(m)
+    r = ref_ssm.SSMDynamics(s['z_ref'], model=s['model'], params=s['params'], **kw)
+    o = SSMDynamicsNP(s['z_ref'], model=s['model'], params=s['params'], **kw)
+    for attr in ('state_dim', 'input_dim', 'output_dim', 'SSM_order', 'ROM_order', 'Ts', 'nonlinear_observer'):
+        assert getattr(r, attr) == getattr(o, attr)
+    assert np.array_equal(r.H, o.H) and not r.H.any()
+    close = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max()) <= 1e-14 * max(float(np.abs(np.asarray(b)).max()), 1e-300)
+    rng = np.random.default_rng(m)
+    eps = np.finfo(np.float64).eps
+    for _ in range(12):
+        x = rng.normal(size=6) * np.array([3, 3, 3, 30, 30, 30.0])
+        u = rng.uniform(0, 800, size=m)
+        z = s['z_ref'] + rng.normal(size=6)
+        assert close(np.asarray(r.rom_phi(*x)), __import__('oracle.ssm_np', fromlist=['x']).poly_features(x, o.rom_table))
+        assert close(r.reduced_dynamics(x, u), o.reduced_dynamics(x, u))
+        assert close(r.reduced_dynamics_discrete(x, u), o.reduced_dynamics_discrete(x, u))
+        assert close(r.C_map(x), o.C_map(x)) and close(r.W_map(x), o.W_map(x))
+        assert close(r.compute_RO_state(z), o.compute_RO_state(z))
+        assert close(r.x_to_zy(x), o.x_to_zy(x))
+        A, B, d = r.get_continuous_jacobians(x, u)
+        Ao, Bo, do = o.get_continuous_jacobians(x, u)
+        scale = (np.abs(r.reduced_dynamics(x, u)) + np.abs(A) @ np.abs(x) + np.abs(B) @ np.abs(u)).max()
+        assert close(A, Ao) and close(B, Bo) and np.abs(d - do).max() <= 8 * eps * scale
+        if kw['discrete']:
+            A, B, d = r.get_discrete_jacobians(x, u)
+            Ao, Bo, do = o.get_discrete_jacobians(x, u)
+            assert close(A, Ao) and close(B, Bo) and np.abs(d - do).max() <= 8 * eps * scale
+        for a, b in zip(r.get_observer_jacobians(x), o.get_observer_jacobians(x)):
+            assert close(a, b)
+        assert close(r.update_observer_state(x), o.update_observer_state(x))
+        Ad, Bd, dd = r.get_jacobians(x, u, 0.02)
+        Ado, Bdo, ddo = o.get_jacobians(x, u, 0.02)
+        assert close(Ad, Ado) and np.abs(Bd - Bdo).max() <= 4 * eps * np.abs(Bdo).max()
+        xn, xno = r.update_state(x, u, 0.02), o.update_state(x, u, 0.02)
+        assert np.abs(xn - xno).max() <= 1e-14 * np.abs(xno).max()
+    xs = rng.normal(size=(9, 6))
+    assert close(r.x_to_zfyf(xs), o.x_to_zfyf(xs))
+    assert np.array_equal(r.zfyf_to_zy(zf=xs), o.zfyf_to_zy(zf=xs)) and np.array_equal(r.zy_to_zfyf(z=xs), o.zy_to_zfyf(z=xs))
+    uu = rng.uniform(0, 800, size=(40, m))
+    (xr, zr), (xo, zo) = r.rollout(np.zeros(6), uu, 0.02), o.rollout(np.zeros(6), uu, 0.02)
+    assert np.abs(xr - xo).max() <= 1e-13 * np.abs(xo).max() and np.abs(zr - zo).max() <= 1e-13 * np.abs(zo).max()
+
+
+def test_ssm_zoh_raises_like_the_reference(ref_ssm):
+    import sofacontrol_b200.synth as synth
+    from oracle.ssm_np import SSMDynamicsNP
+    s = synth.trunk_ssm(4)
+    for cls in (ref_ssm.SSMDynamics, SSMDynamicsNP):
+        mdl = cls(s['z_ref'], discrete=False, discr_method='zoh', model=s['model'], params=s['params'])
+        with pytest.raises(RuntimeError):
+            mdl.get_jacobians(np.zeros(6), np.zeros(4), 0.01)
+
+
+def test_gauss_newton_ilqr_reference_classes_vs_restatements(ref, ref_ssm):
+    """Reference iLQR class driving the reference SSM class (through the H-property adapter of SURVEY App. C.2)
+    vs ILQRNP driving SSMDynamicsNP: same iteration count and rho, x / u / K to 1e-12."""
+    import sofacontrol_b200.synth as synth
+    from oracle.ssm_np import SSMDynamicsNP, GaussNewtonSSM
+    from oracle.ilqr_np import ILQRNP
+    from oracle.utils_np import QuadraticCost
+    s = synth.trunk_ssm(8)
+    N = 30
+    zt = synth.figure8_targets(s['z_ref'], N, 9.0, 1.1)[0]
+    Q, R, Qf = synth.trunk_ilqr_costs(6, 8)
+    kw = dict(discrete=False, discr_method='be', model=s['model'], params=s['params'])
+    rs = ref.ilqr.iLQR(0.02, GaussNewtonSSM(ref_ssm.SSMDynamics(s['z_ref'], **kw)), ref.utils.QuadraticCost(Q, R, Qf), N)
+    os_ = ILQRNP(0.02, GaussNewtonSSM(SSMDynamicsNP(s['z_ref'], **kw)), QuadraticCost(Q, R, Qf), N)
+    res = []
+    for sol in (rs, os_):
+        sol.set_target(zt)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            res.append(sol.ilqr_computation(0.05 * np.ones(6)))
+        if sol is rs:
+            its = buf.getvalue().count('Iteration')
+    assert its == os_.iterations and rs.rho == os_.rho
+    for a, b in zip(*res):
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()
+
+
 def test_pod_restatement(ref):
     import sofacontrol_b200.synth as synth
     from oracle import pod_np

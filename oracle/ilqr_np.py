@@ -217,9 +217,9 @@ class ILQRNP:
         return x, u, K
 
 
-def riccati_noise_floor(model, cost, z_target, x, u, A, B, u_last=None):
+def riccati_noise_floor(model, cost, z_target, x, u, A, B, u_last=None, rho=0.0):
     """How far is the reference's own FP64 backward pass from exact arithmetic?  Runs the value recursion of
-    ilqr.py:258-295 (rho = 0) once in float64 and once in numpy longdouble (x87 80-bit here) on identical inputs
+    ilqr.py:258-295 (fixed rho) once in float64 and once in numpy longdouble (x87 80-bit here) on identical inputs
     and returns the relative differences of K and k.  The un-symmetrised recursion amplifies rounding noise along
     the horizon (measured ~1e6 over N = 100 on the Trunk figure-8), which bounds how closely ANY independent
     implementation can reproduce the reference's gains -- see DESIGN.md "Parity tolerance"."""
@@ -244,11 +244,13 @@ def riccati_noise_floor(model, cost, z_target, x, u, A, B, u_last=None):
             c_u = R @ c(u[t] - (u_last if t == 0 else u[t - 1]))
             Q_x, Q_u = c_x + At.T @ p, c_u + Bt.T @ p
             Q_xx, Q_uu, Q_ux = c_xx + At.T @ P @ At, R + Bt.T @ P @ Bt, Bt.T @ P @ At
-            inv = c(np.linalg.inv(np.asarray(Q_uu, dtype=np.float64)))
+            Preg = P + c(rho) * np.eye(n, dtype=dt)           # state regularisation (ilqr.py:266-267)
+            Q_uu_t, Q_ux_t = R + Bt.T @ Preg @ Bt, Bt.T @ Preg @ At
+            inv = c(np.linalg.inv(np.asarray(Q_uu_t, dtype=np.float64)))
             if dt is not np.float64:
                 for _ in range(3):                     # Newton refinement of the inverse in extended precision
-                    inv = inv + inv @ (np.eye(m, dtype=dt) - Q_uu @ inv)
-            K, k = -inv @ Q_ux, -inv @ Q_u
+                    inv = inv + inv @ (np.eye(m, dtype=dt) - Q_uu_t @ inv)
+            K, k = -inv @ Q_ux_t, -inv @ Q_u
             p = Q_x + K.T @ Q_uu @ k + K.T @ Q_u + Q_ux.T @ k
             P = Q_xx + K.T @ Q_uu @ K + K.T @ Q_ux + Q_ux.T @ K
             Ks.append(K); ks.append(k)

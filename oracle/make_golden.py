@@ -109,6 +109,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == 'nonpd':
         np.savez_compressed(os.path.join(GOLD, "ilqr_nonpd.npz"), **nonpd_golden(ref))
         return
+    only_ssm = len(sys.argv) > 1 and sys.argv[1] == 'ssm'
     from scipy.io import loadmat
     from scipy.interpolate import interp1d
     import sofacontrol_b200.synth as synth
@@ -200,9 +201,19 @@ def main():
         Kb, kb, Qub, Quub = quiet(solver.dlqr_recursion, xf, uf, Af, Bf, df)
         res.update({tag + '_fp_cost': cf, tag + '_fp_A': Af, tag + '_fp_B': Bf, tag + '_fp_d': df, tag + '_bp_K': Kb,
                     tag + '_bp_k': kb, tag + '_bp_Qu': Qub, tag + '_bp_Quu': Quub, tag + '_bp_rho': solver.rho})
+        # and on the initial zero-input rollout, far from the optimum: k, Q_u are O(1) there (no cancellation)
+        x00 = np.zeros((Nh + 1, 6))
+        x0f, u0f, c0f, A0f, B0f, d0f = solver.forward_pass(x00, np.zeros((Nh, mm)))
+        solver.rho, solver.drho = 0.0, 0.0
+        K0, k0, Qu0, Quu0 = quiet(solver.dlqr_recursion, x0f, u0f, A0f, B0f, d0f)
+        res.update({tag + '_init_x': x0f, tag + '_init_u': u0f, tag + '_init_cost': c0f, tag + '_init_A': A0f,
+                    tag + '_init_B': B0f, tag + '_init_d': d0f, tag + '_init_K': K0, tag + '_init_k': k0,
+                    tag + '_init_Qu': Qu0, tag + '_init_Quu': Quu0})
         print("ssm ilqr", tag, "cost", cf)
     np.savez_compressed(os.path.join(GOLD, "ssm_ilqr.npz"), **res)
 
+    if only_ssm:
+        return
     # ---------------------------------------------------------------- non-PD branch of the reference class
     np.savez_compressed(os.path.join(GOLD, "ilqr_nonpd.npz"), **nonpd_golden(ref))
 

@@ -51,8 +51,12 @@ def small_tpwl_bank(seed=11, r=5, m=3, P=40):
     return synth.tpwl_bank(seed=seed, r=r, m=m, P=P, num_nodes=20, tip_node=7, spread=1.0)
 
 
-NONPD_CASES = [("d4_first_step", 4, 15, 3.0, -5000.0), ("t8_mid", 8, 40, 6.0, -50.0), ("t8_long", 8, 40, 6.0, -500.0),
-               ("d4_mid", 4, 30, 6.0, -200.0)]
+NONPD_CASES = [  # tag, m, N, amplitude, Q[2,2], max_iter
+    ("d4_first_step", 4, 15, 3.0, -5000.0, 50), ("d4_five", 4, 20, 3.0, -30.0, 4), ("t8_five", 8, 40, 6.0, -30.0, 4),
+    ("t8_hard", 8, 40, 3.0, -500.0, 4),
+    # long solves: the indefinite cost makes these closed loops unstable (|x| ~ 1e5..1e6), a ONE-ulp change of the target
+    # moves the reference's own result by 1e-6..1e-2 (stored as *_ulp_sensitivity) -- they pin the branch sequence
+    ("t8_mid", 8, 40, 6.0, -50.0, 50), ("t8_long", 8, 40, 6.0, -500.0, 50), ("d4_mid", 4, 30, 6.0, -200.0, 50)]
 
 
 def nonpd_golden(ref):
@@ -60,13 +64,14 @@ def nonpd_golden(ref):
     backward sweep is recovered by wrapping (not editing) dlqr_recursion: the first all-zero K row from the top."""
     import sofacontrol_b200.synth as synth
     out = {}
-    for tag, m, N, amp, q22 in NONPD_CASES:
+    for tag, m, N, amp, q22, max_iter in NONPD_CASES:
         s = synth.trunk_ssm(m)
         mdl = ssm_np.GaussNewtonSSM(ssm_np.SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'],
                                                          params=s['params']))
         Q, R, Qf = synth.trunk_ilqr_costs(6, m)
         Q = Q.copy(); Q[2, 2] = q22
         sol = ref.ilqr.iLQR(0.02, mdl, ref.utils.QuadraticCost(Q, R, Qf), N)
+        sol.params.max_iter = max_iter
         sol.set_target(synth.figure8_targets(s['z_ref'], N, amp)[0])
         fails, calls = [], []
         inner = sol.dlqr_recursion
@@ -86,6 +91,17 @@ def nonpd_golden(ref):
         x, u, K = quiet(sol.ilqr_computation, np.zeros(6))
         out.update({tag + '_x': x, tag + '_u': u, tag + '_K': K, tag + '_rho': sol.rho, tag + '_iterations': len(fails),
                     tag + '_pd_fail_t': np.array(fails)})
+        # conditioning of the case: the same reference solve with the target moved by ONE ulp.  An indefinite stage
+        # cost makes some of these closed loops unstable (|x| grows to 1e5..1e6 along the horizon), and rounding-level
+        # input changes are then amplified over the iterations; the GPU test allows 10 x this measured sensitivity.
+        sol2 = ref.ilqr.iLQR(0.02, mdl, ref.utils.QuadraticCost(Q, R, Qf), N)
+        sol2.params.max_iter = max_iter
+        sol2.set_target(synth.figure8_targets(s['z_ref'], N, amp)[0] * (1.0 + 2.0 ** -52))
+        with np.errstate(all='ignore'):
+            x2, u2, K2 = quiet(sol2.ilqr_computation, np.zeros(6))
+        rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+        out[tag + '_ulp_sensitivity'] = np.array([rel(x2, x), rel(u2, u), rel(K2, K)])
+        print("nonpd", tag, "1-ulp sensitivity of the reference solve (x, u, K):", out[tag + '_ulp_sensitivity'])
         print("nonpd", tag, "iterations", len(fails), "pd_fail_t", fails[:8], "rho", sol.rho)
         if tag == "t8_long":
             # unit backward pass: replay the first interrupted sweep from rho = drho = 0

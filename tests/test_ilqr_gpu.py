@@ -359,17 +359,24 @@ def test_branch_paths_line_search_failure_and_abandon():
         assert abs(s.info['trace'][ev['it'], 2] - ev['rho_after_bwd']) <= 1e-12 * max(1.0, ev['rho_after_bwd'])
 
 
-NONPD_CASES = [("d4_first_step", 4, 15, 3.0, -5000.0), ("t8_mid", 8, 40, 6.0, -50.0), ("t8_long", 8, 40, 6.0, -500.0),
-               ("d4_mid", 4, 30, 6.0, -200.0)]
+NONPD_CASES = [  # tag, m, N, amplitude, Q[2,2], max_iter
+    ("d4_first_step", 4, 15, 3.0, -5000.0, 50), ("d4_five", 4, 20, 3.0, -30.0, 4), ("t8_five", 8, 40, 6.0, -30.0, 4),
+    ("t8_hard", 8, 40, 3.0, -500.0, 4),
+    # long solves: the indefinite cost makes these closed loops unstable (|x| ~ 1e5..1e6), a ONE-ulp change of the target
+    # moves the reference's own result by 1e-6..1e-2 (stored as *_ulp_sensitivity) -- they pin the branch sequence
+    ("t8_mid", 8, 40, 6.0, -50.0, 50), ("t8_long", 8, 40, 6.0, -500.0, 50), ("d4_mid", 4, 30, 6.0, -200.0, 50)]
 
 
-@pytest.mark.parametrize("tag,m,N,amp,q22", NONPD_CASES)
-def test_non_pd_branch_matches_reference_golden(golden, tag, m, N, amp, q22):
+@pytest.mark.parametrize("tag,m,N,amp,q22,max_iter", NONPD_CASES)
+def test_non_pd_branch_matches_reference_golden(golden, tag, m, N, amp, q22, max_iter, capsys):
     """Indefinite stage cost -> Q_uu~ fails the Cholesky test.  The reference (ilqr.py:282-299) raises rho, LEAVES the
     backward sweep (K_t = k_t = 0 at and below the failing step), lowers rho once and line-searches with those
     gains; it never restarts.  Golden = the unmodified reference class (oracle/make_golden.py: ilqr_nonpd.npz);
-    the oracle restatement is pinned bitwise to it (tests/test_oracle_vs_reference.py).  Compared: iteration
-    count, rho, the failing step of every backward sweep, the exact zero pattern of K, and x, u, K at 1e-9."""
+    the oracle restatement is pinned bitwise to it (tests/test_oracle_vs_reference.py).
+    Exact on every case: iteration count, final rho, the failing step of every backward sweep, the zero pattern of K.
+    x, u, K: 1e-9 on the well-conditioned cases (<= 5 iterations).  The long cases are unstable closed loops: the
+    reference's OWN result moves by `ulp_sensitivity` (1e-6 .. 1e-2, measured in make_golden.py) when its target is
+    changed by one ulp, so there the values are held to 10 x that measured sensitivity (printed)."""
     import sofacontrol_b200.synth as synth
     from sofacontrol_b200.lqr.ilqr import iLQR
     from sofacontrol_b200.utils import QuadraticCost as QC
@@ -379,6 +386,7 @@ def test_non_pd_branch_matches_reference_golden(golden, tag, m, N, amp, q22):
     Q = Q.copy(); Q[2, 2] = q22
     zt = synth.figure8_targets(s_['z_ref'], N, amp)[0]
     s = iLQR(0.02, model, QC(Q, R, Qf), N, trace=True)
+    s.params.max_iter = max_iter
     s.set_target(zt)
     x, u, K = s.ilqr_computation(np.zeros(6))
     it = int(g[tag + '_iterations'])
@@ -387,7 +395,15 @@ def test_non_pd_branch_matches_reference_golden(golden, tag, m, N, amp, q22):
     assert (g[tag + '_pd_fail_t'] >= 0).any() and (s.info['status'] & 8)      # the path is really exercised
     assert abs(float(s.info['rho']) - float(g[tag + '_rho'])) <= 1e-12 * max(1.0, float(g[tag + '_rho']))
     assert np.array_equal(K == 0.0, g[tag + '_K'] == 0.0)
-    assert relerr(x, g[tag + '_x']) < TOL and relerr(u, g[tag + '_u']) < TOL and relerr(K, g[tag + '_K']) < TOL
+    e = [relerr(x, g[tag + '_x']), relerr(u, g[tag + '_u']), relerr(K, g[tag + '_K'])]
+    sens = g[tag + '_ulp_sensitivity']
+    tol = [max(TOL, 10.0 * float(v)) for v in sens]
+    with capsys.disabled():
+        print("\n[non-PD %s] %d iterations: x %.1e u %.1e K %.1e | 1-ulp sensitivity of the reference %s -> tol %s"
+              % (tag, it, *e, np.array2string(sens, precision=1), ["%.1e" % t for t in tol]))
+    if it <= 5:
+        assert max(tol) == TOL                                                 # the short cases ARE held to 1e-9
+    assert e[0] < tol[0] and e[1] < tol[1] and e[2] < tol[2]
 
 
 def test_non_pd_backward_pass_unit_matches_reference_golden(golden):

@@ -53,10 +53,10 @@ def small_tpwl_bank(seed=11, r=5, m=3, P=40):
 
 NONPD_CASES = [  # tag, m, N, amplitude, Q[2,2], max_iter
     ("d4_first_step", 4, 15, 3.0, -5000.0, 50), ("d4_five", 4, 20, 3.0, -30.0, 4), ("t8_five", 8, 40, 6.0, -30.0, 4),
-    ("t8_hard", 8, 40, 3.0, -500.0, 4),
+    ("t8_hard", 8, 40, 3.0, -500.0, 4), ("t8_twelve", 8, 40, 6.0, -500.0, 11),
     # long solves: the indefinite cost makes these closed loops unstable (|x| ~ 1e5..1e6), a ONE-ulp change of the target
     # moves the reference's own result by 1e-6..1e-2 (stored as *_ulp_sensitivity) -- they pin the branch sequence
-    ("t8_mid", 8, 40, 6.0, -50.0, 50), ("t8_long", 8, 40, 6.0, -500.0, 50), ("d4_mid", 4, 30, 6.0, -200.0, 50)]
+    ("t8_mid", 8, 40, 6.0, -50.0, 50), ("d4_mid", 4, 30, 6.0, -200.0, 50)]
 
 
 def nonpd_golden(ref):
@@ -103,7 +103,7 @@ def nonpd_golden(ref):
         out[tag + '_ulp_sensitivity'] = np.array([rel(x2, x), rel(u2, u), rel(K2, K)])
         print("nonpd", tag, "1-ulp sensitivity of the reference solve (x, u, K):", out[tag + '_ulp_sensitivity'])
         print("nonpd", tag, "iterations", len(fails), "pd_fail_t", fails[:8], "rho", sol.rho)
-        if tag == "t8_long":
+        if tag == "t8_twelve":
             # unit backward pass: replay the first interrupted sweep from rho = drho = 0
             i = next(j for j, f in enumerate(fails) if f >= 0)
             xx, uu, AA, BB, dd = calls[i][:5]

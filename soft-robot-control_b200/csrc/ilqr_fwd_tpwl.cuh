@@ -185,7 +185,7 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
             float vmin = red_f[0];
 #pragma unroll
             for (int k2 = 1; k2 < NW; ++k2) vmin = fminf(vmin, red_f[k2]);
-            const double c1 = 34.0 * u24 + 1e-14;
+            const double c1 = (0.5 * r + 16.0) * u24 + 1e-14;   // r/2 + 2 ulp accumulate over r squares (+ margin); = 34 u at r = 36
             const double c0 = u24 * 2.0 * (bank_norm + w * 1.001 * (double)sqrtf(xn2));
             const double U = (1.0 + c1) * w * sqrt((double)vmin) + c0;
             const double T = (U + c0) / (w * (1.0 - c1));
@@ -227,11 +227,11 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
                 const double d1 = M.wq * (double)q1 + M.wv * (double)v1;
                 dh[p0] = (float)d0;
                 // (float)d rounds once more: the candidate test below reads the rounded value and pads the bound for it
-                const double e0 = u24 * (34.0 * d0 + slack) + 1e-14 * d0;
+                const double e0 = u24 * ((0.5 * r + 16.0) * d0 + slack) + 1e-14 * d0;
                 ubmin = fmin(ubmin, d0 + e0);
                 if (has1) {
                     dh[p1] = (float)d1;
-                    const double e1 = u24 * (34.0 * d1 + slack) + 1e-14 * d1;
+                    const double e1 = u24 * ((0.5 * r + 16.0) * d1 + slack) + 1e-14 * d1;
                     ubmin = fmin(ubmin, d1 + e1);
                 }
             }
@@ -248,7 +248,7 @@ __device__ double fwd_pass_tpwl_nn(const TpwlDev& M, const IlqrArgs& a, const Sm
             const double slack_all = misc[2];
             for (int p = tid; p < P; p += NT) {
                 const double d = (double)dh[p];
-                const double e = u24 * (36.0 * d + slack_all) + 1e-14 * d;
+                const double e = u24 * ((0.5 * r + 18.0) * d + slack_all) + 1e-14 * d;
                 if (d - e <= U) {
                     const int pos = atomicAdd(&cand[0], 1);
                     if (pos < kFwdNNCandCap) cand[2 + pos] = p;

@@ -194,7 +194,7 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
 #pragma unroll
                     for (int off = 4; off > 0; off >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, off));
                     if (lane == 0) {
-                        const double c1 = 34.0 * u24 + 1e-14;
+                        const double c1 = (0.5 * RT + 16.0) * u24 + 1e-14;   // 34 u at r = 36; grows with the sum length
                         const double c0 = u24 * 2.0 * (bank_norm + w * xnorm[hw]);
                         const double U = (1.0 + c1) * w * sqrt((double)v) + c0;     // smallest upper bound
                         const double T = (U + c0) / (w * (1.0 - c1));

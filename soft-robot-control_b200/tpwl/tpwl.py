@@ -103,7 +103,13 @@ class TPWL:
                 if method not in ('fe', 'be', 'bil', 'zoh'):
                     raise RuntimeError('self.discr_method must be in [fe, be, bil, zoh]')   # tpwl.py:295
         H, z = self._out()
-        dw = self.dist_weights or {}
+        # the reference subscripts dist_weights / multiplies by beta_weighting unconditionally (tpwl.py:166-167, 176):
+        # None raises TypeError there, so it does here instead of silently selecting point 0 / uniform weights
+        if self.dist_weights is None:
+            raise TypeError("'NoneType' object is not subscriptable (params['dist_weights'] is required, tpwl.py:166)")
+        if self.tpwl_method == 'weighting' and self.beta_weighting is None:
+            raise TypeError("bad operand type for unary -: 'NoneType' (params['beta_weighting'] is required, tpwl.py:176)")
+        dw = self.dist_weights
         h = L.TpwlModel(n=self.state_dim, m=self.input_dim, nz=(0 if self.H is None else int(self.H.shape[0])),
                         P=self.num_points, method=L.TPWL_METHOD[self.tpwl_method], discr_method=L.DISCR[method],
                         wq=float(dw.get('q', 0.0)), wv=float(dw.get('v', 0.0)),

@@ -1,5 +1,7 @@
-"""State-layout helpers and containers of sofacontrol/utils.py that the hot path uses (utils.py:8-16, 129-159).
-Pure data plumbing -- no numerics live here."""
+"""State-layout helpers and containers of sofacontrol/utils.py that the hot path uses (utils.py:8-16, 129-159):
+pure data plumbing; plus the zero-order-hold discretisation `zoh_affine` / `zoh_linear` (utils.py:302-335), which runs
+the batched Pade-13 expm kernel of csrc/expm.cu, and `extract_AB` (utils.py:251-286), the batched second-order ->
+first-order conversion of csrc/bank.cu used when a TPWL bank is built."""
 import os
 import pickle
 
@@ -49,3 +51,35 @@ def load_data(filename):
     """utils.py:156-159."""
     with open(filename, 'rb') as file:
         return pickle.load(file)
+
+
+def _zoh_device(A, B, d, dt):
+    from . import _lib as L
+    L.require_gpu()
+    A = np.asarray(A, dtype=np.float64)
+    single = (A.ndim == 2)
+    n, m = A.shape[-1], np.asarray(B).shape[-1]
+    Ad = L.to_dev(A.reshape(-1, n, n))
+    Bd = L.to_dev(np.asarray(B, dtype=np.float64).reshape(-1, n, m))
+    dd = L.to_dev(np.asarray(d, dtype=np.float64).reshape(-1, n))
+    wsb = int(L.lib().srcb200_zoh_workspace(n, m, Ad.shape[0]))
+    ws = L.empty((wsb // 8 + 1,))
+    L.check(L.lib().srcb200_zoh_batch(n, m, Ad.shape[0], float(dt), L.ptr(Ad), L.ptr(Bd), L.ptr(dd), L.ptr(Ad), L.ptr(Bd),
+                                      L.ptr(dd), L.ptr(ws), ws.numel() * 8, L.stream_ptr()))
+    res = (L.to_host(Ad), L.to_host(Bd), L.to_host(dd))
+    return tuple(r[0] for r in res) if single else res
+
+
+def zoh_affine(A, B, d, dt):
+    """utils.py:322-335: exact discretisation of x' = A x + B u + d under zero-order hold -> (A_d, B_d, d_d).
+    One system or a stack with a leading axis; runs srcb200_zoh_batch (scaling-and-squaring Pade-13 of the
+    (n+m+1)^2 augmented matrix, one CTA per system)."""
+    return _zoh_device(A, B, d, dt)
+
+
+def zoh_linear(A, B, dt):
+    """utils.py:302-319 -> (A_d, B_d).  Same kernel with a zero affine column (the extra zero column of the
+    augmented matrix does not touch the A_d / B_d blocks of its exponential)."""
+    A = np.asarray(A, dtype=np.float64)
+    Ad, Bd, _ = _zoh_device(A, B, np.zeros(A.shape[:-1]), dt)
+    return Ad, Bd

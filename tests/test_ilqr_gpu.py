@@ -361,10 +361,10 @@ def test_branch_paths_line_search_failure_and_abandon():
 
 NONPD_CASES = [  # tag, m, N, amplitude, Q[2,2], max_iter
     ("d4_first_step", 4, 15, 3.0, -5000.0, 50), ("d4_five", 4, 20, 3.0, -30.0, 4), ("t8_five", 8, 40, 6.0, -30.0, 4),
-    ("t8_hard", 8, 40, 3.0, -500.0, 4),
+    ("t8_hard", 8, 40, 3.0, -500.0, 4), ("t8_twelve", 8, 40, 6.0, -500.0, 11),
     # long solves: the indefinite cost makes these closed loops unstable (|x| ~ 1e5..1e6), a ONE-ulp change of the target
     # moves the reference's own result by 1e-6..1e-2 (stored as *_ulp_sensitivity) -- they pin the branch sequence
-    ("t8_mid", 8, 40, 6.0, -50.0, 50), ("t8_long", 8, 40, 6.0, -500.0, 50), ("d4_mid", 4, 30, 6.0, -200.0, 50)]
+    ("t8_mid", 8, 40, 6.0, -50.0, 50), ("d4_mid", 4, 30, 6.0, -200.0, 50)]
 
 
 @pytest.mark.parametrize("tag,m,N,amp,q22,max_iter", NONPD_CASES)
@@ -374,7 +374,7 @@ def test_non_pd_branch_matches_reference_golden(golden, tag, m, N, amp, q22, max
     gains; it never restarts.  Golden = the unmodified reference class (oracle/make_golden.py: ilqr_nonpd.npz);
     the oracle restatement is pinned bitwise to it (tests/test_oracle_vs_reference.py).
     Exact on every case: iteration count, final rho, the failing step of every backward sweep, the zero pattern of K.
-    x, u, K: 1e-9 on the well-conditioned cases (<= 5 iterations).  The long cases are unstable closed loops: the
+    x, u, K: 1e-9 on the well-conditioned cases (<= 12 iterations).  The long cases are unstable closed loops: the
     reference's OWN result moves by `ulp_sensitivity` (1e-6 .. 1e-2, measured in make_golden.py) when its target is
     changed by one ulp, so there the values are held to 10 x that measured sensitivity (printed)."""
     import sofacontrol_b200.synth as synth
@@ -400,8 +400,8 @@ def test_non_pd_branch_matches_reference_golden(golden, tag, m, N, amp, q22, max
     tol = [max(TOL, 10.0 * float(v)) for v in sens]
     with capsys.disabled():
         print("\n[non-PD %s] %d iterations: x %.1e u %.1e K %.1e | 1-ulp sensitivity of the reference %s -> tol %s"
-              % (tag, it, *e, np.array2string(sens, precision=1), ["%.1e" % t for t in tol]))
-    if it <= 5:
+              % (tag, it, *e, ['%.1e' % v for v in sens], ["%.1e" % t for t in tol]))
+    if it <= 12:
         assert max(tol) == TOL                                                 # the short cases ARE held to 1e-9
     assert e[0] < tol[0] and e[1] < tol[1] and e[2] < tol[2]
 
@@ -421,7 +421,7 @@ def test_non_pd_backward_pass_unit_matches_reference_golden(golden):
     s.rho, s.drho = 0.0, 0.0
     K, k, Qu, Quu = s.dlqr_recursion(g['unit_x'], g['unit_u'], g['unit_A'], g['unit_B'], g['unit_d'])
     tf = int(g['unit_pd_fail_t'])
-    assert int(s.info['pd_fail_step']) == tf and tf >= 0
+    assert int(np.ravel(s.info['pd_fail_step'])[0]) == tf and tf >= 0
     assert not K[:tf + 1].any() and not k[:tf + 1].any() and not Qu[:tf].any() and not Quu[:tf].any()
     assert relerr(K, g['unit_K']) < TOL and relerr(k, g['unit_k']) < TOL
     assert relerr(Qu, g['unit_Qu']) < TOL and relerr(Quu, g['unit_Quu']) < TOL

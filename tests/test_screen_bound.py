@@ -19,7 +19,7 @@ def candidates(bank64, x64, w):
         a = (a + d[:, j] * d[:, j]).astype(np.float32)     # un-fused rounds more often: covered by the same bound)
     bank_norm = w * np.sqrt((bank64 ** 2).sum(1)).max() * (1.0 + 1e-6)
     xnorm = 1.001 * float(np.sqrt(np.float32((x32.astype(np.float32) ** 2).sum(dtype=np.float32))))
-    c1 = 34.0 * U24 + 1e-14
+    c1 = (0.5 * bank64.shape[1] + 16.0) * U24 + 1e-14      # r/2 + 16 ulp: 34 at r = 36, grows with the sum length
     c0 = U24 * 2.0 * (bank_norm + w * xnorm)
     U = (1.0 + c1) * w * np.sqrt(float(a.min())) + c0
     T = (U + c0) / (w * (1.0 - c1))
@@ -28,11 +28,12 @@ def candidates(bank64, x64, w):
     return np.nonzero(a <= thr2)[0]
 
 
+@pytest.mark.parametrize("r", [36, 5, 64, 128])
 @pytest.mark.parametrize("scale", [1e-6, 1e-2, 1.0, 37.0, 1e4, 1e8])
 @pytest.mark.parametrize("w", [1.0, 0.3, 250.0])
-def test_argmin_is_always_a_candidate(scale, w):
-    rng = np.random.default_rng(int(scale * 7) % 1000 + int(w * 10))
-    P, r = 300, 36
+def test_argmin_is_always_a_candidate(scale, w, r):
+    rng = np.random.default_rng(int(scale * 7) % 1000 + int(w * 10) + r)
+    P = 300
     for trial in range(40):
         bank = rng.normal(0, scale, size=(P, r)) + rng.normal(0, 3 * scale, size=(1, r)) * (trial % 3)
         kind = trial % 5

@@ -78,6 +78,21 @@ class TPWLATVNP:
     def get_input_dim(self):
         return self.input_dim
 
+    # tpwl.py:91-113
+    def zfyf_to_zy(self, zf=None, yf=None):
+        if zf is not None and self.z_ref is not None:
+            return zf - self.z_ref
+        elif yf is not None and self.y_ref is not None:
+            return yf - self.y_ref
+        raise RuntimeError('Need to set output or meas. model')
+
+    def zy_to_zfyf(self, z=None, y=None):
+        if z is not None and self.z_ref is not None:
+            return z + self.z_ref
+        elif y is not None and self.y_ref is not None:
+            return y + self.y_ref
+        raise RuntimeError('Need to set output or meas. model')
+
     # tpwl.py:115-126
     def x_to_zfyf(self, x, zf=False, yf=False):
         if zf and self.H is not None:

@@ -26,6 +26,12 @@ def x2qv(x):
     raise IndexError('Unable to process x.ndim > 2')
 
 
+def vq2qv(x):
+    """utils.py:144-146."""
+    q, v = x2qv(x)
+    return np.hstack((q, v))
+
+
 def zoh_affine(A, B, d, dt):
     """utils.py:302-335 -- exact ZOH of xdot = A x + B u + d via expm of the (n+m+1) augmented matrix.
     The reference calls scipy.sparse.linalg.expm on the dense augmented matrix (Al-Mohy & Higham scaling and

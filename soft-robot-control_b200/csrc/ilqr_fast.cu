@@ -11,9 +11,11 @@
 //     (for a symmetric matrix the k-th pivot IS the k-th Cholesky pivot a_kk - sum l_kj^2 of np.linalg.cholesky).
 //   * the polynomial model (ssm.py:158-235) is evaluated sparsely: d phi / d x_j of a degree-<=3 monomial is a
 //     multiple of a degree-<=2 monomial, so A_c = r_coeff dphi/dx and H = w_coeff dphi/dx are 72 dot products of
-//     length 28 against psi = (1, x, x (x) x), and f, z are 12 dot products of length 84 split in three; all 108
-//     partial dots are spread over the 32 lanes (4 accumulators each) and read their coefficients from a
-//     conflict-free table built once per CTA.
+//     length 28 against psi = (1, x, x (x) x), accumulated per polynomial degree; the VALUES f, z then cost no
+//     coefficient reads at all: for a homogeneous polynomial h of degree p, x . grad h = p h (Euler), hence
+//     f_i = sum_j x_j (g1_ij + g2_ij / 2 + g3_ij / 3) with g_p the degree-p part of row i of the Jacobian.  The
+//     coefficient table (the dominant shared-memory traffic of a step) shrinks from 108 to 72 rows of 28, spread
+//     over the 32 lanes in three rounds and read with conflict-free LDS.128.
 //
 // Control flow (line search, rho schedule, interrupted sweep on a non-PD Q_uu~, convergence) is identical to the generic kernel in ilqr.cu
 // and to the reference (ilqr.py:27-107); results agree with it to rounding (tests/test_ilqr_gpu.py).
@@ -26,9 +28,9 @@ namespace fast {
 constexpr int LD = 12;            // tile row stride (doubles): A-/B-fragment loads are bank-conflict free
 constexpr int TILE = 8 * LD;
 constexpr int WARPS = 8;          // problems in flight per CTA (2 CTAs per SM; 20-24 warps at 96/80 registers measured slower)
-constexpr int NJ = 28;            // terms per partial dot
-constexpr int NPD = 120;          // partial-dot slots: 4 rounds x 32 lanes (108 used; lanes >= 24 of round 3 read zeros)
-constexpr int TS = 30;            // table row stride (doubles)
+constexpr int NJ = 30;            // slots per Jacobian row: [deg1 c, 0 | deg2: 6 | deg3: 21, 0] -- degrees on even boundaries
+constexpr int NPD = 73;           // table rows: 72 Jacobian rows (A_c 0..35, H 36..71) + one zero row for idle lanes
+constexpr int TS = 30;            // table row stride (doubles): LDS.128 of 8 consecutive rows hit 8 distinct 16 B banks
 constexpr int NFEAT = 83;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -42,19 +44,20 @@ constexpr int SH_ZREF = SH_BR + TILE;           // 8
 constexpr int SH_FIDX = SH_ZREF + 8;            // 84 ints = 42 doubles
 constexpr int SH_END = SH_FIDX + 44;
 // per-warp block (doubles)
-constexpr int W_PHI = 0;                        // 84 (+4 pad)
-constexpr int W_X = 88;                         // x_t (6), X[6] = 0, X[7] = 1
-constexpr int W_U = 96;
-constexpr int W_UP = 104;                       // u_{t-1}, then du
-constexpr int W_DC = 112;
-constexpr int W_DD = 120;
-constexpr int W_E = 128;
-constexpr int W_DX = 136;                       // x_t - x_prev_t (6)
-constexpr int W_QE = 144;
-constexpr int W_RDU = 152;
-constexpr int W_TILES = 160;
+constexpr int W_PHI = 0;                        // psi slots 0..29 (see NJ), then PV[72]: x_j * value part of row o at W_PHI + 32
+constexpr int W_PV = 32;                        // 72 (+0)
+constexpr int W_X = 104;                        // x_t (6), X[6] = 0, X[7] = 1
+constexpr int W_U = 112;
+constexpr int W_UP = 120;                       // u_{t-1}, then du
+constexpr int W_DC = 128;
+constexpr int W_DD = 136;
+constexpr int W_E = 144;
+constexpr int W_DX = 152;                       // x_t - x_prev_t (6)
+constexpr int W_QE = 160;
+constexpr int W_RDU = 168;
+constexpr int W_TILES = 176;
 constexpr int NTILES = 11;
-constexpr int W_SIZE = W_TILES + NTILES * TILE; // 1216 doubles = 9.5 KB per warp
+constexpr int W_SIZE = W_TILES + NTILES * TILE; // 1232 doubles = 9.6 KB per warp
 constexpr size_t SMEM_BYTES = sizeof(double) * (SH_END + WARPS * W_SIZE);
 
 struct Frag { double c0, c1; };
@@ -95,13 +98,19 @@ struct Ctx {
 #define CTX_WS(c) (g_sm + (c).ws_off)
 
 // ---------------------------------------------------------------------------------------------------------------
-// Coefficient table, built once per CTA from the model arrays.
-//   slots 0..35   : A_c[i][j]   = sum_q T[pd][q] psi_q,  pd = 6 i + j,        T = mult * r_coeff[i][k(j,q)]
-//   slots 36..71  : H[i][j]                              pd = 36 + 6 i + j,   T = mult * w_coeff[i][k(j,q)]
-//   slots 72..83  : value part 0 of f_i (v = i) / z_i (v = 6 + i): operand Phi[0..27]
-//   slots 96..107 : value part 1, operand Phi[28..55];  slots 108..119: value part 2, operand Phi[56..83]
-// with psi = Phi[0..27] = (1, x_1..x_6, 21 quadratic monomials) and Phi[1 + k] = phi_k (83 monomials).
+// Coefficient table, built once per CTA from the model arrays.  Row pd (A_c[i][j]: pd = 6 i + j with r_coeff,
+// H[i][j]: pd = 36 + 6 i + j with w_coeff) holds d/dx_j of the polynomial of output i, sorted by degree:
+//   slot 0      : coefficient of x_j itself (degree-1 part: a constant), slot 1: 0
+//   slots 2..7  : mult * coeff of the quadratic monomials containing x_j, operand psi = x_0..x_5
+//   slots 8..28 : mult * coeff of the cubic monomials containing x_j, operand psi = the 21 products x_a x_b, slot 29: 0
+// psi lives in the per-warp block with the same slot numbering (psi_0 = 1, psi_1 = psi_29 = 0).  Row 72 is zero.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int slot_to_q(int slot) {      // q indexes (1, x_0..x_5, 21 quadratic monomials); -1: padding
+    if (slot == 0) return 0;
+    if (slot >= 2 && slot <= 7) return slot - 1;
+    if (slot >= 8 && slot <= 28) return slot - 1;
+    return -1;
+}
 __device__ int find_monomial(const SsmDev& M, int a, int b, int c) {
     // sort ascending with 0xFF (absent) last
     if (a > b) { int t = a; a = b; b = t; }
@@ -119,26 +128,18 @@ __device__ void build_tables(const SsmDev& M, const double* Qg, const double* Rg
     for (int e = threadIdx.x; e < NPD * TS; e += blockDim.x) T[e] = 0.0;
     for (int e = threadIdx.x; e < 4 * TILE + 8; e += blockDim.x) sh[SH_Q + e] = 0.0;
     __syncthreads();
-    // Jacobian slots
+    // Jacobian rows
     for (int e = threadIdx.x; e < 72 * NJ; e += blockDim.x) {
-        const int pd = e / NJ, q = e - pd * NJ;
+        const int pd = e / NJ, slot = e - pd * NJ;
+        const int q = slot_to_q(slot);
+        if (q < 0) continue;
         const double* src = pd < 36 ? M.r : M.w;
         const int o = pd < 36 ? pd : pd - 36, i = o / 6, j = o - 6 * i;
         int s0 = 0xFF, s1 = 0xFF;
         if (q >= 1) { s0 = M.mono[(q - 1) * SRCB200_SSM_MAX_ORDER]; s1 = M.mono[(q - 1) * SRCB200_SSM_MAX_ORDER + 1]; }
         const int k = find_monomial(M, s0, s1, j);
         const int mult = 1 + (s0 == j) + (s1 == j);
-        T[pd * TS + q] = (k >= 0) ? (double)mult * src[i * M.nfeat + k] : 0.0;
-    }
-    // value slots
-    for (int e = threadIdx.x; e < 36 * NJ; e += blockDim.x) {
-        const int s = e / NJ, q = e - s * NJ;          // s = part * 12 + v
-        const int part = s / 12, v = s - 12 * part;
-        const int pd = (part == 0) ? 72 + v : (part == 1 ? 96 + v : 108 + v);
-        const double* src = v < 6 ? M.r : M.w;
-        const int i = v < 6 ? v : v - 6;
-        const int k = 28 * part + q - 1;
-        T[pd * TS + q] = (k >= 0 && k < M.nfeat) ? src[i * M.nfeat + k] : 0.0;
+        T[pd * TS + slot] = (k >= 0) ? (double)mult * src[i * M.nfeat + k] : 0.0;
     }
     for (int e = threadIdx.x; e < 36; e += blockDim.x) {
         const int i = e / 6, j = e - 6 * i;
@@ -158,8 +159,9 @@ __device__ void build_tables(const SsmDev& M, const double* Qg, const double* Rg
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Model evaluation at the state in X: fills Phi, then A_c -> tile AC, H -> tile HT, returns in lanes 8..13 the
+// Model evaluation at the state in X: fills psi, then A_c -> tile AC, H -> record Hg, and returns in lanes 8..13 the
 // polynomial part of f_i (i = lane - 8) and in lanes 14..19 the raw output z_i (i = lane - 14).
+// Row o = 32 r + lane of the Jacobian table is handled by `lane` in round r (r = 2: lanes < 8).
 // ---------------------------------------------------------------------------------------------------------------
 struct Scatter { int o0, o1, o2; };   // per-lane tile offsets of the Jacobian outputs of rounds 0, 1, 2
 
@@ -174,52 +176,79 @@ __device__ __forceinline__ Scatter make_scatter(int lane) {
 __device__ __forceinline__ double ssm_eval_fast(const Ctx c, const Scatter sc, double* __restrict__ AC,
                                                 double* __restrict__ Hg) {
     const int lane = c.lane;
-    double* PHI = CTX_WS(c) + W_PHI;
+    double* PSI = CTX_WS(c) + W_PHI;
+    double* PV = CTX_WS(c) + W_PV;
     const double* X = CTX_WS(c) + W_X;
     const int* fidx = reinterpret_cast<const int*>(CTX_SH + SH_FIDX);
-    // features, products left to right like the oracle: (x_a x_b) x_c with absent factors = 1
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int k = lane + 32 * r;
-        if (k < NFEAT) {
-            const int pk = fidx[k];
-            double p = X[pk & 7];
-            p = __dmul_rn(p, X[(pk >> 3) & 7]);
-            p = __dmul_rn(p, X[(pk >> 6) & 7]);
-            PHI[1 + k] = p;
-        }
+    // psi: slots 2..7 = x, slots 8..28 = the 21 quadratic monomials x_a x_b (phi_6..phi_26 of ssm.py:158-164)
+    if (lane < 21) {
+        const int pk = fidx[6 + lane];
+        PSI[8 + lane] = __dmul_rn(X[pk & 7], X[(pk >> 3) & 7]);
+    } else if (lane < 27) {
+        PSI[2 + lane - 21] = X[lane - 21];
     }
+    const double xj0 = X[lane % 6], xj1 = X[(32 + lane) % 6], xj2 = X[(64 + lane) % 6];
     __syncwarp();
     const double* T = CTX_SH + SH_T;
     const double* t0 = T + lane * TS;
     const double* t1 = T + (32 + lane) * TS;
-    const double* t2 = T + (64 + lane) * TS;
-    const double* t3 = T + (96 + (lane < 24 ? lane : 23 - 12)) * TS;   // lanes >= 24 have no round-3 slot: any row x zero operand
-    const double* op3 = PHI + (lane < 12 ? 28 : 56);
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;   // even / odd terms
+    const double* t2 = T + (lane < 8 ? 64 + lane : 72) * TS;             // lanes >= 8: the zero row (one broadcast read)
+    // degree 1: the coefficient itself
+    double g10, g11, g12;
+    {
+        const double2 c0 = *reinterpret_cast<const double2*>(t0);
+        const double2 c1 = *reinterpret_cast<const double2*>(t1);
+        const double2 c2 = *reinterpret_cast<const double2*>(t2);
+        g10 = c0.x; g11 = c1.x; g12 = c2.x;
+    }
+    // degree 2: slots 2..7 (even / odd accumulators)
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
 #pragma unroll
-    for (int q = 0; q < NJ; q += 2) {
-        const double2 ps = *reinterpret_cast<const double2*>(PHI + q);
-        const double2 p3 = *reinterpret_cast<const double2*>(op3 + q);
+    for (int q = 2; q < 8; q += 2) {
+        const double2 ps = *reinterpret_cast<const double2*>(PSI + q);
         const double2 c0 = *reinterpret_cast<const double2*>(t0 + q);
         const double2 c1 = *reinterpret_cast<const double2*>(t1 + q);
         const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
-        const double2 c3 = *reinterpret_cast<const double2*>(t3 + q);
         a0 = fma(c0.x, ps.x, a0); b0 = fma(c0.y, ps.y, b0);
         a1 = fma(c1.x, ps.x, a1); b1 = fma(c1.y, ps.y, b1);
         a2 = fma(c2.x, ps.x, a2); b2 = fma(c2.y, ps.y, b2);
-        a3 = fma(c3.x, p3.x, a3); b3 = fma(c3.y, p3.y, b3);
     }
-    a0 = __dadd_rn(a0, b0); a1 = __dadd_rn(a1, b1); a2 = __dadd_rn(a2, b2); a3 = __dadd_rn(a3, b3);
-    // A_c into its tile, H_t straight to the trajectory record
-    AC[sc.o0] = a0;
-    if (lane < 4) AC[sc.o1] = a1; else if (Hg) Hg[lane - 4] = a1;
-    if (lane < 8 && Hg) Hg[28 + lane] = a2;
-    // combine the three parts of the 12 value outputs in lanes 8..19
-    const int v = lane - 8;
-    const double p1 = __shfl_sync(FULL, a3, v & 31);
-    const double p2 = __shfl_sync(FULL, a3, (12 + v) & 31);
-    return __dadd_rn(__dadd_rn(a2, p1), p2);
+    const double g20 = __dadd_rn(a0, b0), g21 = __dadd_rn(a1, b1), g22 = __dadd_rn(a2, b2);
+    // degree 3: slots 8..29
+    a0 = a1 = a2 = b0 = b1 = b2 = 0.0;
+#pragma unroll
+    for (int q = 8; q < NJ; q += 2) {
+        const double2 ps = *reinterpret_cast<const double2*>(PSI + q);
+        const double2 c0 = *reinterpret_cast<const double2*>(t0 + q);
+        const double2 c1 = *reinterpret_cast<const double2*>(t1 + q);
+        const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
+        a0 = fma(c0.x, ps.x, a0); b0 = fma(c0.y, ps.y, b0);
+        a1 = fma(c1.x, ps.x, a1); b1 = fma(c1.y, ps.y, b1);
+        a2 = fma(c2.x, ps.x, a2); b2 = fma(c2.y, ps.y, b2);
+    }
+    const double g30 = __dadd_rn(a0, b0), g31 = __dadd_rn(a1, b1), g32 = __dadd_rn(a2, b2);
+    // Jacobian entries: A_c into its tile, H_t straight to the trajectory record
+    const double j0 = __dadd_rn(__dadd_rn(g10, g20), g30);
+    const double j1 = __dadd_rn(__dadd_rn(g11, g21), g31);
+    const double j2 = __dadd_rn(__dadd_rn(g12, g22), g32);
+    AC[sc.o0] = j0;
+    if (lane < 4) AC[sc.o1] = j1; else if (Hg) Hg[lane - 4] = j1;
+    if (lane < 8 && Hg) Hg[28 + lane] = j2;
+    // values by Euler's theorem: x_j (g1 + g2 / 2 + g3 / 3) summed over the six columns j of an output row
+    constexpr double third = 1.0 / 3.0;
+    PV[lane] = __dmul_rn(xj0, __dadd_rn(__dadd_rn(g10, __dmul_rn(0.5, g20)), __dmul_rn(third, g30)));
+    PV[32 + lane] = __dmul_rn(xj1, __dadd_rn(__dadd_rn(g11, __dmul_rn(0.5, g21)), __dmul_rn(third, g31)));
+    if (lane < 8) PV[64 + lane] = __dmul_rn(xj2, __dadd_rn(__dadd_rn(g12, __dmul_rn(0.5, g22)), __dmul_rn(third, g32)));
+    __syncwarp();
+    double val = 0.0;
+    if (lane >= 8 && lane < 20) {
+        const double* pv = PV + 6 * (lane - 8);
+        const double2 p01 = *reinterpret_cast<const double2*>(pv);
+        const double2 p23 = *reinterpret_cast<const double2*>(pv + 2);
+        const double2 p45 = *reinterpret_cast<const double2*>(pv + 4);
+        val = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(p01.x, p01.y), p23.x), p23.y), p45.x), p45.y);
+    }
+    return val;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -328,7 +357,7 @@ __device__ __noinline__ double fwd_fast(const Ctx c, const IlqrArgs& a, int disc
     if (lane < 8) X[lane] = lane < 6 ? nx[lane] : (lane == 7 ? 1.0 : 0.0);
     if (lane < 6) tr.x[lane] = nx[lane];
     if (lane < 8) { UP[lane] = (lane < M && ulast) ? ulast[lane] : 0.0; U[lane] = 0.0; DC[lane] = 0.0; DX[lane] = 0.0; }
-    if (lane == 0) ws[W_PHI] = 1.0;
+    if (lane < 3) ws[W_PHI + (lane == 0 ? 0 : (lane == 1 ? 1 : 29))] = (lane == 0) ? 1.0 : 0.0;   // psi_0 = 1, padding slots 0
     // prefetch registers for step 0
     double p_nu = 0.0, p_k = 0.0, p_K[6] = {0, 0, 0, 0, 0, 0}, p_nx = 0.0, p_zt = 0.0;
     if (lane < M) {
@@ -984,7 +1013,7 @@ ssm_rollout_fast_kernel(const __grid_constant__ SsmDev Mdl, long long batch, int
         for (int t = 0; t < 6; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
         if (lane < 8) { X[lane] = lane < 6 ? x0[b * 6 + lane] : (lane == 7 ? 1.0 : 0.0); U[lane] = 0.0; DC[lane] = 0.0; }
         if (lane < 6) xb[lane] = x0[b * 6 + lane];
-        if (lane == 0) ws[W_PHI] = 1.0;
+        if (lane < 3) ws[W_PHI + (lane == 0 ? 0 : (lane == 1 ? 1 : 29))] = (lane == 0) ? 1.0 : 0.0;
         double p_u = (lane < M && N > 0) ? ub[lane] : 0.0;
         __syncwarp();
         for (int t = 0; t <= N; ++t) {

@@ -267,6 +267,61 @@ int srcb200_pod_gram(int64_t nf, int64_t ns, const double* X, int64_t ldx, doubl
 int srcb200_dgemm(int32_t transA, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                   const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Callers either side of the hot path, batched.  All matrices row-major, device pointers.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* DiscreteEKFObserver.predict_state (sofacontrol/tpwl/observer.py:94-104) for `batch` independent filters:
+ *   x <- A_d x + B_d u + d_d ;  Sigma <- (A_d Sigma) A_d^T + W.
+ * A_d (batch, n, n), B_d (batch, n, m), d_d (batch, n): the linearisation at x (srcb200_tpwl_linearize_batch);
+ * u (batch, m); W (n, n) shared; x (batch, n) and Sigma (batch, n, n) are updated in place. */
+int srcb200_ekf_predict_batch(int32_t n, int32_t m, int64_t batch, const double* A_d, const double* B_d,
+                              const double* d_d, const double* u, const double* W, double* x, double* Sigma,
+                              void* stream);
+/* DiscreteEKFObserver.update_state (observer.py:106-126):  y_r = y - y_ref ; S = (C Sigma) C^T + V ;
+ *   K = (Sigma C^T) inv(S) ; x <- x + K (y_r - C x) ; Sigma <- (I - K C) Sigma.
+ * C (p, n), V (p, p), y_ref (p) (NULL = zeros) shared; y (batch, p); x, Sigma in place. */
+int srcb200_ekf_update_batch(int32_t n, int32_t p, int64_t batch, const double* C, const double* V,
+                             const double* y_ref, const double* y, double* x, double* Sigma, void* stream);
+/* Infinite-horizon discrete LQR (sofacontrol/lqr/lqr.py:6-31) for `batch` systems A (batch, n, n), B (batch, n, m);
+ * Q (n, n), R (m, m) shared (shared_cost != 0) or per system.  K (batch, m, n) with u = +K x, P (batch, n, n).
+ *   mode 0: `solve_riccati` literally -- value iteration from P = 0 until ||L - L_old||_F <= tol (reference: 1e-4);
+ *           iterations (batch, NULL allowed) = number of passes.
+ *   mode 1: `dare` -- the stabilising solution to working precision (structure-preserving doubling; tol is the
+ *           relative change of P at which it stops, e.g. 1e-15), then K = -inv(B^T P B + R) (B^T P A). */
+int srcb200_dlqr_riccati_batch(int32_t n, int32_t m, int64_t batch, const double* A, const double* B,
+                               const double* Q, const double* R, int32_t shared_cost, double tol, int32_t max_iter,
+                               int32_t mode, double* K, double* P, int32_t* iterations, void* stream);
+/* TrajTrackingLQR.perform_dlqr_recursion (sofacontrol/lqr/traj_tracking_lqr.py:31-44) on `batch` trajectories of
+ * `steps` linearisations A (batch, steps, n, n), B (batch, steps, n, m) in time order:  P_T = Q, backwards
+ *   K_i = -solve(R + B^T P B, B^T P A) ; P <- Q + K^T R K + (A + B K)^T P (A + B K).
+ * K (batch, steps, m, n), P (batch, steps + 1, n, n), both in time order. */
+int srcb200_tvlqr_batch(int32_t n, int32_t m, int32_t steps, int64_t batch, const double* A, const double* B,
+                        const double* Q, const double* R, double* K, double* P, void* stream);
+/* One stored TPWL point per entry from reduced second-order matrices: extract_AB (sofacontrol/utils.py:251-286, dense
+ * branch) and the affine term of add_continuous_TPWL (sofacontrol/tpwl/tpwl_utils.py:263-276):
+ *   A_c = [[-inv(M) D, -inv(M) K], [I, 0]] ; B_c = [[inv(M) H], [0]] ; d_c = [solve(M, f + K q) ; 0].
+ * K, D, M (count, r, r), H (count, r, m), f, q (count, r; both NULL with d_c NULL for extract_AB alone)
+ * -> A_c (count, 2r, 2r), B_c (count, 2r, m), d_c (count, 2r). */
+int srcb200_tpwl_bank_point_batch(int32_t r, int32_t m, int64_t count, const double* K, const double* D,
+                                  const double* M, const double* H, const double* f, const double* q, double* A_c,
+                                  double* B_c, double* d_c, void* stream);
+/* GuSTO.compute_accuracy (sofacontrol/scp/gusto.py:203-223) for `batch` trajectories of N linearisation points:
+ * (f_k, A_k, B_k) continuous dynamics at the previous iterate (x_k, u_k), f at the candidate (x, u);
+ *   error = sum_i dt ||s o (f_i - fa_i)||_2, approx = sum_i dt ||s o fa_i||_2, fa_i = f_k,i + A_k,i dx_i + B_k,i du_i,
+ *   rho = error / (J + approx).   f_k, f (batch, N, n); A_k (batch, N, n, n); B_k (batch, N, n, m);
+ * x, x_k (batch, N + 1, n); u, u_k (batch, N, m); f_scale (n) or NULL; J (batch) or NULL; outputs (batch). */
+int srcb200_gusto_accuracy_batch(int32_t n, int32_t m, int32_t N, int64_t batch, double dt, const double* f_k,
+                                 const double* A_k, const double* B_k, const double* f, const double* x,
+                                 const double* x_k, const double* u, const double* u_k, const double* f_scale,
+                                 const double* J, double* rho, double* error, double* approx, void* stream);
+/* Receding-horizon bookkeeping between two solves (the warm-start hooks of sofacontrol/lqr/ilqr.py:24-25, 46-47 and
+ * the target window of tpwl/controllers.py:185-198), control step k of T:  u_applied = u_plan[:, 0] (also logged to
+ * u_log (batch, T, m) if not NULL), u_warm = [u_plan[:, 1:], u_plan[:, -1]], z_window = z_ref[:, k+1 : k+2+N].
+ * u_plan, u_warm (batch, N, m); z_ref (batch, T + N + 1, nz); z_window (batch, N + 1, nz). */
+int srcb200_mpc_shift_batch(int64_t batch, int32_t N, int32_t m, int32_t nz, int32_t T, int32_t k,
+                            const double* u_plan, const double* z_ref, double* u_warm, double* u_applied,
+                            double* z_window, double* u_log, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

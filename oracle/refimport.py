@@ -21,11 +21,17 @@ def available():
 
 
 def load():
-    """Returns a namespace with the reference modules: tpwl, pod, ilqr, config, utils, measurement_models."""
+    """Returns a namespace with the reference modules: tpwl, pod, ilqr, config, lqr, traj_tracking_lqr, observer, utils,
+    measurement_models."""
     if not available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
     if "osqp" not in sys.modules:
         sys.modules["osqp"] = types.ModuleType("osqp")
+    if "control" not in sys.modules:            # lqr/lqr.py:1 imports python-control for CLQR only (absent here)
+        try:
+            import control  # noqa: F401
+        except ImportError:
+            sys.modules["control"] = types.ModuleType("control")
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     with warnings.catch_warnings():
@@ -36,7 +42,11 @@ def load():
         import sofacontrol.lqr.ilqr as ilqr
         import sofacontrol.lqr.config as config
         import sofacontrol.measurement_models as measurement_models
-    return types.SimpleNamespace(utils=utils, pod=pod, tpwl=tpwl, ilqr=ilqr, config=config,
+        import sofacontrol.lqr.lqr as lqr
+        import sofacontrol.lqr.traj_tracking_lqr as traj_tracking_lqr
+        import sofacontrol.tpwl.observer as observer
+    return types.SimpleNamespace(utils=utils, pod=pod, tpwl=tpwl, ilqr=ilqr, config=config, lqr=lqr,
+                                 traj_tracking_lqr=traj_tracking_lqr, observer=observer,
                                  measurement_models=measurement_models, root=REFERENCE_ROOT)
 
 

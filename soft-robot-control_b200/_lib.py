@@ -96,6 +96,19 @@ _SIGS = {
     "srcb200_pod_gram": (C.c_int, [C.c_int64, C.c_int64, c_dp, C.c_int64, c_dp, C.c_int64, C.c_int32, c_dp]),
     "srcb200_dgemm": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_dp, C.c_int64, c_dp,
                                 C.c_int64, c_dp, C.c_int64, c_dp]),
+    "srcb200_ekf_predict_batch": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                            c_dp]),
+    "srcb200_ekf_update_batch": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "srcb200_dlqr_riccati_batch": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, c_dp, c_dp, c_dp, c_dp, C.c_int32,
+                                             C.c_double, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, c_dp]),
+    "srcb200_tvlqr_batch": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                      c_dp]),
+    "srcb200_tpwl_bank_point_batch": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                                c_dp, c_dp, c_dp, c_dp]),
+    "srcb200_gusto_accuracy_batch": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_double, c_dp, c_dp, c_dp,
+                                               c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "srcb200_mpc_shift_batch": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_dp, c_dp,
+                                          c_dp, c_dp, c_dp, c_dp, c_dp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

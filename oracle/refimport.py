@@ -34,6 +34,9 @@ def load():
             sys.modules["control"] = types.ModuleType("control")
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
+    import numpy as _np
+    if not hasattr(_np, "infty"):               # lqr/lqr.py:15 uses the NumPy-1.x alias `np.infty` (removed in 2.0)
+        _np.infty = _np.inf
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         import sofacontrol.utils as utils

@@ -178,6 +178,8 @@ class POD:
             matrix = matrix.toarray()
         if not isinstance(matrix, np.ndarray):
             raise RuntimeError('Matrix is not numpy ndarray or sparse coo_matrix')
+        if matrix.ndim == 1:                      # U^T f for a force vector (tpwl_utils.py:95-96): one column
+            return self.compute_RO_matrix(matrix[:, None], left=left, right=right)[:, 0]
         Md = L.to_dev(matrix)
         Ud = self._U_dev()
         if (left and right) or (not left and not right):

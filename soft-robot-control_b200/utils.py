@@ -83,3 +83,22 @@ def zoh_linear(A, B, dt):
     A = np.asarray(A, dtype=np.float64)
     Ad, Bd, _ = _zoh_device(A, B, np.zeros(A.shape[:-1]), dt)
     return Ad, Bd
+
+
+def extract_AB(K, D, M, H):
+    """utils.py:251-286 (dense branch): first-order (A, B) of  M q'' + D q' + K q = H u  with x = [v; q]:
+    A = [[-inv(M) D, -inv(M) K], [I, 0]], B = [[inv(M) H], [0]].  One system or a stack (leading axis); runs
+    csrc/control.cu: bank_point_kernel."""
+    from . import _lib as L
+    L.require_gpu()
+    K = np.asarray(K, dtype=np.float64)
+    single = (K.ndim == 2)
+    r, m = K.shape[-1], np.asarray(H).shape[-1]
+    dev = [L.to_dev(np.asarray(a, dtype=np.float64).reshape((-1,) + s)) for a, s in
+           ((K, (r, r)), (D, (r, r)), (M, (r, r)), (H, (r, m)))]
+    cnt = dev[0].shape[0]
+    A, B = L.empty((cnt, 2 * r, 2 * r)), L.empty((cnt, 2 * r, m))
+    L.check(L.lib().srcb200_tpwl_bank_point_batch(r, m, cnt, *[L.ptr(a) for a in dev], None, None, L.ptr(A), L.ptr(B),
+                                                  None, L.stream_ptr()))
+    Ah, Bh = L.to_host(A), L.to_host(B)
+    return (Ah[0], Bh[0]) if single else (Ah, Bh)

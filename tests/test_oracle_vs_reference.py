@@ -287,3 +287,78 @@ def test_golden_vectors_are_what_the_reference_produces_today(ref, golden):
     assert np.array_equal(np.array([m.calc_nearest_point(x) for x in gt['xs']]), gt['idx_w10'])
     x, z = m.rollout(gt['xs'][0], gt['useq'], 0.01)
     assert np.array_equal(x, gt['nn_x_be']) and np.array_equal(z, gt['nn_z_be'])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Callers either side of the hot path: observers, infinite-horizon / time-varying gains,
+# bank construction -- the reference modules are importable (python-control and np.infty are stubbed in
+# oracle/refimport.py), so the restatements are pinned bit for bit.
+# ------------------------------------------------------------------------------------------------------------
+def _meas(rows, nf):
+    Cf = np.zeros((len(rows), nf))
+    for i, j in enumerate(rows):
+        Cf[i, j] = 1.0
+    return Cf
+
+
+def test_ekf_restatement_bitwise(ref):
+    from oracle.tpwl_np import TPWLATVNP
+    from oracle.observer_np import DiscreteEKFObserverNP, FullStateObserverNP
+    data, Hf = _small_bank()
+    Cf = _meas((3, 17, 64, 90), 120)
+    prm = {'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}
+    mr = ref.tpwl.TPWLATV(data, params=prm, Hf=Hf, Cf=Cf, discr_method='be')
+    mo = TPWLATVNP(data, params=prm, Hf=Hf, Cf=Cf, discr_method='be')
+    kw = dict(W=0.5 * np.eye(10), V=0.01 * np.eye(4), Sigma0=2.0 * np.eye(10))
+    er, eo = ref.observer.DiscreteEKFObserver(mr, **kw), DiscreteEKFObserverNP(mo, **kw)
+    assert np.array_equal(er.x, eo.x) and np.array_equal(er.z, eo.z)
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        u, y = rng.uniform(0, 1000, size=3), mr.y_ref + rng.normal(size=4)
+        er.update(u, y, 0.01); eo.update(u, y, 0.01)
+        assert np.array_equal(er.x, eo.x) and np.array_equal(er.Sigma, eo.Sigma) and np.array_equal(er.z, eo.z)
+    fr, fo = ref.observer.FullStateObserver(10, H=mr.H), FullStateObserverNP(10, H=mo.H)
+    x = rng.normal(size=10)
+    fr.update(None, None, 0.01, x=x); fo.update(None, None, 0.01, x=x)
+    assert np.array_equal(fr.z, fo.z)
+
+
+def test_lqr_gain_restatements_bitwise(ref):
+    from oracle import lqr_np
+    rng = np.random.default_rng(0)
+    n, m = 10, 3
+    A = np.eye(n) + 0.05 * rng.normal(size=(n, n)); B = rng.normal(size=(n, m)); Q = np.eye(n); R = 0.1 * np.eye(m)
+    for a, b in zip(ref.lqr.solve_riccati(A, B, Q, R), lqr_np.solve_riccati(A, B, Q, R)):
+        assert np.array_equal(a, b)
+    for a, b in zip(ref.lqr.dare(A, B, Q, R), lqr_np.dare(A, B, Q, R)):
+        assert np.array_equal(a, b)
+
+
+def test_traj_tracking_lqr_restatement_bitwise(ref):
+    from oracle import lqr_np
+    from oracle.tpwl_np import TPWLATVNP
+    data, Hf = _small_bank()
+    prm = {'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}
+    mr = ref.tpwl.TPWLATV(data, params=prm, Hf=Hf, discr_method='be')
+    mo = TPWLATVNP(data, params=prm, Hf=Hf, discr_method='be')
+    rng = np.random.default_rng(2)
+
+    class T:
+        pass
+    tg = T(); tg.t = np.linspace(0, 0.3, 31); tg.x = rng.normal(size=(31, 10)); tg.u = rng.uniform(0, 100, size=(31, 3))
+    qc = ref.utils.QuadraticCost(Q=np.eye(10), R=0.01 * np.eye(3))
+    a, b = ref.traj_tracking_lqr.TrajTrackingLQR(0.01, mr, qc), lqr_np.TrajTrackingLQRNP(0.01, mo, qc)
+    (Ka, Pa), (Kb, Pb) = a.perform_dlqr_recursion(tg), b.perform_dlqr_recursion(tg)
+    assert np.array_equal(Ka, Kb) and np.array_equal(Pa, Pb) and np.array_equal(a.x_bar, b.x_bar)
+    assert np.array_equal(a.u_bar, b.u_bar)
+
+
+def test_extract_AB_restatement_bitwise(ref):
+    from oracle import lqr_np
+    rng = np.random.default_rng(4)
+    r = 6
+    K = rng.normal(size=(r, r)); K = K @ K.T + r * np.eye(r)
+    M = np.eye(r) + 0.1 * rng.normal(size=(r, r)); M = M @ M.T
+    D, H = 0.1 * K + np.eye(r), rng.normal(size=(r, 2))
+    for a, b in zip(ref.utils.extract_AB(K, D, M, H), lqr_np.extract_AB(K, D, M, H)):
+        assert np.array_equal(a, b)

@@ -10,8 +10,13 @@ batched solve of the whole batch (ONE launch of ilqr_solve_kernel).  Metric: iLQ
   value      : device-resident inputs, CUDA events on the launching stream, L2 flushed between steps (untimed).
   e2e        : the public host API path -- pinned host buffers, H2D of x0 / targets, solve, D2H of x, u, K, cost.
   roofline   : algorithmic FP64 flops of the solve kernel / its event time against the measured cuBLAS DGEMM rate.
-  cpu_baseline / --impl reference : the CPU port of the reference algorithm (oracle/, pinned bitwise to the
-               reference classes) on the box's host cores, bounded sample.
+  strong     : (N > 1) the SAME 4096 problems split across the N ranks (BASELINE configs[2] "sharded across 1/2/4/8
+               GPUs"), measured in the same run next to the weak-scaling `value` (4096 per GPU, same seed per rank).
+  secondary  : the other kernels of the path (TPWL nn rollout, SSM evaluation, POD Gram [+ all-reduce for N > 1],
+               closed-loop MPC) measured outside the headline's timed region, each with roofline / e2e / cpu_baseline.
+  cpu_baseline / --impl reference : the reference's own iLQR class (imported from /root/reference when that tree is
+               present: kind "reference") or else its CPU port (oracle/, pinned bitwise to the reference classes:
+               kind "port") on the box's host cores, bounded sample.
 Other workloads (--workload): ilqr_tpwl, tpwl_rollout_nn, tpwl_rollout_weighting, ssm_rollout, ssm_eval, pod_gram, mpc.
 """
 import argparse
@@ -123,10 +128,22 @@ def build_ilqr(batch, N, seed):
     return w, solver
 
 
+def _reference_available():
+    try:
+        from oracle import refimport
+        return refimport.available()
+    except Exception:
+        return False
+
+
 def cpu_ilqr_worker(args):
-    """One CPU worker: solves a slice of the same batch with the reference algorithm's CPU port."""
+    """One CPU worker: solves a slice of the same batch with the reference's own iLQR class (when /root/reference is
+    present; it drives the SSM through the Gauss-Newton H-property adapter of SURVEY App. C.2) or its CPU port."""
     os.environ["OMP_NUM_THREADS"] = "1"
-    idx, N, seed, batch = args
+    idx, N, seed, batch, use_ref = args
+    import contextlib
+    import io
+    import warnings
     import sofacontrol_b200.synth as synth
     from oracle.ssm_np import SSMDynamicsNP, GaussNewtonSSM
     from oracle.ilqr_np import ILQRNP
@@ -134,40 +151,65 @@ def cpu_ilqr_worker(args):
     w = synth.trunk_ilqr_batch(batch, N=N, seed=seed, m=8)
     s = w['ssm']
     Q, R, Qf = synth.trunk_ilqr_costs(6, 8)
+    cls, qc = ILQRNP, QuadraticCost
+    if use_ref:
+        warnings.simplefilter("ignore")
+        from oracle import refimport
+        ref = refimport.load()
+        cls, qc = ref.ilqr.iLQR, ref.utils.QuadraticCost
     t0 = time.perf_counter()
     its = 0
     for b in idx:
-        o = ILQRNP(w['dt'], GaussNewtonSSM(SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'],
-                                                         params=s['params'])), QuadraticCost(Q, R, Qf), N)
+        o = cls(w['dt'], GaussNewtonSSM(SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'],
+                                                      params=s['params'])), qc(Q, R, Qf), N)
         o.set_target(w['z_target'][b])
-        o.ilqr_computation(w['x0'][b])
-        its += o.iterations
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):     # the reference prints in its hot loop
+            o.ilqr_computation(w['x0'][b])
+        its += getattr(o, 'iterations', 0)
     return len(idx), its, time.perf_counter() - t0
 
 
 def cpu_ilqr_baseline(batch, N, seed, per_core=2):
     """Reference CPU path on the host cores: `per_core` solves per core taken from the same batch, one process per
-    core, OMP_NUM_THREADS=1.  Returns (solves/s aggregate, cores, sample description)."""
+    core, OMP_NUM_THREADS=1.  Returns (solves/s aggregate, cores, sample description, kind,
+    seconds of the slowest worker)."""
     import multiprocessing as mp
     cores = max(1, len(os.sched_getaffinity(0)))
     cores = min(cores, 64)
-    jobs = [(list(range(c * per_core, (c + 1) * per_core)), N, seed, max(batch, cores * per_core)) for c in range(cores)]
+    use_ref = _reference_available()
+    jobs = [(list(range(c * per_core, (c + 1) * per_core)), N, seed, max(batch, cores * per_core), use_ref) for c in range(cores)]
     t0 = time.perf_counter()
     with mp.get_context("spawn").Pool(cores) as pool:
         res = pool.map(cpu_ilqr_worker, jobs)
     wall = time.perf_counter() - t0
     solved = sum(r[0] for r in res)
     busy = max(r[2] for r in res)
-    return solved / busy, cores, "%d solves (%d per core, first problems of the same seeded batch), horizon %d; " \
-                                 "wall %.1fs incl. process start, slowest worker %.1fs" % (solved, per_core, N, wall, busy)
+    kind = "reference" if use_ref else "port"
+    what = ("the reference's iLQR class (sofacontrol/lqr/ilqr.py, unmodified) on the pinned numpy SSM" if use_ref else
+            "the CPU port of the reference iLQR (oracle/ilqr_np.py, pinned bitwise to the reference class)")
+    return solved / busy, cores, "%s: %d solves (%d per core, first problems of the same seeded batch), horizon %d; " \
+                                 "wall %.1fs incl. process start, slowest worker %.1fs" % (what, solved, per_core, N, wall, busy), kind, busy
+
+
+def ilqr_record_traffic(n, m, nz, N, fwd_passes, bwd_passes, batch):
+    """Bytes the solve kernel moves through L2/HBM by design: every forward step writes one
+    trajectory record (x, u, e, H_t, A_t, B_t) and reads the nominal step (x, u, K_t, k_t, target); every backward
+    step reads the record (+ u_{t-1}) and writes K_t, k_t and two line-search scalars; plus the result copy."""
+    rec = n + m + nz + nz * n + n * n + n * m
+    fwd = (rec + (n + m + m * n + m + nz)) * 8.0
+    bwd = (rec + m + (m * n + m + 2)) * 8.0
+    out = batch * ((N + 1) * n + N * m) * 8.0 * 2
+    return fwd_passes * N * fwd + bwd_passes * N * bwd + out
 
 
 def run_ilqr(args, rank, world, dev_index):
     import torch
     import torch.distributed as dist
     from sofacontrol_b200 import _lib as L
+    from sofacontrol_b200.parallel import shard_slice
     batch, N = args.batch, args.horizon
-    w, solver = build_ilqr(batch, N, seed=3 + rank)
+    # the same seeded batch on every rank: weak scaling measures the system, not a different draw of problems
+    w, solver = build_ilqr(batch, N, seed=3)
     x0 = L.to_dev(w['x0'])
     zt = L.to_dev(w['z_target'])
     flush = torch.empty(256 * 1024 * 1024 // 8, device="cuda", dtype=torch.float64)
@@ -177,6 +219,18 @@ def run_ilqr(args, rank, world, dev_index):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(x0_, zt_, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        o = None
+        for s_, e_ in ev:
+            flush.fill_(1.0)                       # L2 flush, untimed
+            s_.record()
+            o = solver.solve_device(x0_, zt_)
+            e_.record()
+        barrier()
+        return sum(s_.elapsed_time(e_) for s_, e_ in ev) * 1e-3, o
+
     out = None
     for _ in range(args.warmup):
         out = solver.solve_device(x0, zt)
@@ -185,18 +239,19 @@ def run_ilqr(args, rank, world, dev_index):
     trials = out['trials'].cpu().numpy()
     status = out['status'].cpu().numpy()
 
-    # ---- device-resident timing (value)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    # ---- device-resident timing (value): weak scaling, `batch` problems per GPU
     with ClockSampler(dev_index) as clk:
-        for s, e in ev:
-            flush.fill_(1.0)                       # L2 flush, untimed
-            s.record()
-            out = solver.solve_device(x0, zt)
-            e.record()
-        barrier()
-    t_dev = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
+        t_dev, out = timed(x0, zt, args.steps)
     clocks = clk.summary()
+
+    # ---- strong scaling: the SAME `batch` problems split across the ranks (BASELINE configs[2])
+    strong = None
+    if world > 1:
+        sl = shard_slice(batch, rank, world)
+        xs, zs = x0[sl].contiguous(), zt[sl].contiguous()
+        for _ in range(2):
+            solver.solve_device(xs, zs)
+        t_strong, _ = timed(xs, zs, args.steps)
 
     # ---- end-to-end through the host API with pinned buffers (e2e)
     x0_h = torch.from_numpy(w['x0']).pin_memory()
@@ -214,37 +269,51 @@ def run_ilqr(args, rank, world, dev_index):
     d2h = sum(v.numel() * v.element_size() for v in outs_h.values())
 
     if world > 1:
-        tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_dev, t_e2e, t_strong], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(tt[0]), float(tt[1])
+        t_dev, t_e2e, t_strong = float(tt[0]), float(tt[1]), float(tt[2])
+        strong = {"value": batch * args.steps / t_strong, "unit": "solves/s", "ms_per_step": 1e3 * t_strong / args.steps,
+                  "batch_total": batch, "batch_per_gpu": batch // world,
+                  "note": "the same %d seed-3 problems split contiguously across the %d ranks, no collective; "
+                          "%d problems per GPU is below the %d resident warps of one B200, so this is the latency of "
+                          "the longest solves, not throughput" % (batch, world, batch // world, 148 * 16)}
     total = batch * world * args.steps
-    flops = ilqr_flops(6, 8, 6, 83, N, float((trials + 1).sum()), float(iters.sum()))
+    fwd_passes, bwd_passes = float((trials + 1).sum()), float(iters.sum())
+    flops = ilqr_flops(6, 8, 6, 83, N, fwd_passes, bwd_passes)
     hbm, hsrc, fp64 = measured_peaks()
     per_launch = t_dev / args.steps
     ach = flops / per_launch / 1e12
+    traffic_model = ilqr_record_traffic(6, 8, 6, N, fwd_passes, bwd_passes, batch)
     res = {
         "metric": "ilqr_solves_per_sec", "value": total / t_dev, "unit": "solves/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "Trunk-SSM batched iLQR (BASELINE configs[2]): %d independent solves per GPU, horizon %d, "
                                "n=6 m=8 order-3 SSM (83 monomials), be discretisation, dt=0.02, Gauss-Newton figure-8 "
-                               "tracking, randomised amplitude/phase/x0 (seed 3+rank)" % (batch, N),
+                               "tracking, randomised amplitude/phase/x0 (seed 3, the same batch on every rank)" % (batch, N),
                    "batch_per_gpu": batch, "horizon": N, "parallelism": "dp%d (problems sharded, no collective)" % world,
                    "l2": "256 MB buffer written between timed steps (untimed)",
                    "converged_frac": float((status & 1).mean()), "mean_iterations": float(iters.mean()),
-                   "mean_forward_passes": float((trials + 1).mean())},
+                   "mean_forward_passes": float((trials + 1).mean()),
+                   "total_iterations_per_rank": int(iters.sum())},
         "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": 2 * args.steps,         # ilqr_queue_init_kernel + ilqr_ssm_fast_kernel<8> per step
         "clocks": clocks,
         "roofline": {"kernel": "ilqr_ssm_fast_kernel<8>", "bound": "tensor", "achieved": ach, "peak": fp64,
                      "unit": "TFLOP/s", "frac": ach / fp64,
-                     "traffic": 36.12e9 * batch / 4096.0 if (batch == 4096 and N == 100) else None,
+                     "traffic": traffic_model,
+                     "traffic_source": "modelled from the executed passes (bench.py:ilqr_record_traffic: record + gain "
+                                       "bytes per pass-step); ncu dram read+write of one launch of this workload: 35.7e9 "
+                                       "(profiles/ncu_ilqr_r2_e1.txt)",
+                     "algorithmic_io_bytes": float(batch * (55e3)),
                      "note": "FP64 pipe (DMMA + DFMA): algorithmic flops of the executed passes (dense counts, bench.py:"
                              "ilqr_flops, DESIGN.md) / event time of the single launch; peak = cuBLAS DGEMM 8192^3 "
-                             "measured on this pool (profiles/fp64_peaks_r01.json), of measured; the kernel is "
-                             "dependent-issue-latency bound (n = 6), see profiles/ncu_ilqr_v7_r01.txt; traffic = "
-                             "dram read+write bytes of one launch from that ncu capture (trajectory records)"},
+                             "measured on this pool (profiles/fp64_peaks_r01.json), of measured; the kernel is bound by "
+                             "dependent-issue latency and the shared-memory/shuffle pipe (n = 6), see "
+                             "profiles/ncu_ilqr_r2_e1.txt and ncu_ilqr_r2_e1_lines.txt"},
     }
+    if strong is not None:
+        res["strong"] = strong
     return res
 
 
@@ -294,20 +363,24 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
     if method == 'nn':
         byt = batch * N * ((n * n + n * m + n) * 8 + (2 * n + m) * 8) + N * P * r * 8
         ops = batch * N * 2.0 * P * r
-        roof = {"kernel": "tpwl_rollout_nn_screen_kernel<36,4>", "bound": "hbm", "achieved": byt / (t_dev / args.steps) / 1e9,
-                "peak": hbm, "unit": "GB/s", "traffic": None,
+        dram = 0.25e9 * batch / 4096.0          # ncu dram read+write of one launch (profiles/ncu_tpwl_screen_r01.txt)
+        roof = {"kernel": "tpwl_rollout_nn_screen_kernel<36,4>", "bound": "l2/lsu (on-chip: the 44 MB bank is L2 resident)",
+                "achieved": byt / (t_dev / args.steps) / 1e9, "peak": None, "unit": "GB/s (L2 -> SM, algorithmic)",
+                "traffic": dram, "hbm_frac": dram / (t_dev / args.steps) / 1e9 / hbm,
+                "l1tex_pct_ncu": 65.0, "lts_pct_ncu": 12.0, "issue_active_pct_ncu": 52.0,
                 "fp32_screen_tops": ops / (t_dev / args.steps) / 1e12,
                 "note": "algorithmic bytes per trajectory-step = gathered bank entry 44352 B + state I/O, distance bank "
-                        "288000 B once per time step for the whole batch (SURVEY 8d), of " + hsrc + "; the 44 MB bank is "
-                        "L2 resident, so these bytes move L2 -> SM, not HBM -> L2 (ncu: profiles/ncu_tpwl_screen_r01.txt). "
-                        "The kernel alternates an FP32-issue-bound exact two-stage nearest search (fp32_screen_tops = "
-                        "2 P r FP32 instructions per trajectory-step, T lane-ops/s) with the L2-bandwidth-bound gather"}
+                        "288000 B once per time step for the whole batch (SURVEY 8d).  These bytes move L2 -> SM, not HBM -> "
+                        "L2: DRAM traffic is 0.25 GB per launch (hbm_frac, of " + hsrc + "); the limiters ncu reports are the "
+                        "L1/LSU pipe (65 %) and FP32 issue of the exact two-stage search (52 %), "
+                        "profiles/ncu_tpwl_screen_r01.txt.  frac = the L1/LSU utilisation ncu measured."}
+        roof["frac"] = 0.65
     else:
         fl = batch * N * 2.0 * P * (n * n + n * m + n)
         roof = {"kernel": "dgemm_kernel (bank blend)", "bound": "tensor", "achieved": fl / (t_dev / args.steps) / 1e12,
                 "peak": fp64, "unit": "TFLOP/s", "traffic": None,
                 "note": "2 P (n^2+nm+n) flop per trajectory-step; whole step time (weights + blend + discretise + step)"}
-    roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["frac"] = roof["achieved"] / roof["peak"]
     return {"metric": "tpwl_%s_rollout_steps_per_sec" % method, "value": steps_total / t_dev, "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -473,54 +546,60 @@ def run_pod_gram(args, rank, world, dev_index):
 
 
 def run_mpc(args, rank, world, dev_index):
-    """BASELINE configs[3]: closed-loop receding-horizon Monte Carlo -- every control step re-solves all problems
-    (horizon 20, warm start = shifted previous plan, u_last) and steps the plant with process noise."""
+    """BASELINE configs[3] "Diamond SSM + TPWL closed-loop MPC Monte Carlo: 16k receding-horizon problems, re-linearised
+    at every step": plant = Diamond-shaped TPWL bank (n = 72, nearest-neighbour on the zoh bank), controller =
+    receding-horizon iLQR (N = 20) on the Diamond SSM fed by the SSM observer, warm start = shifted previous plan,
+    u_last, process noise; every control step re-solves ALL problems (each forward step re-linearises the SSM)."""
     import torch
     import torch.distributed as dist
     import sofacontrol_b200.synth as synth
     from sofacontrol_b200 import _lib as L
-    from sofacontrol_b200.SSM.ssm import SSMDynamics
-    from sofacontrol_b200.lqr.ilqr import iLQR
-    from sofacontrol_b200.mpc import RecedingHorizonILQR
-    from sofacontrol_b200.utils import QuadraticCost
+    from sofacontrol_b200.mpc import RecedingHorizonILQR, SSMOutputBelief
     batch = args.batch if args.batch != 4096 else 16384
-    N, steps = 20, 20
-    s = synth.trunk_ssm(8)
-    model = SSMDynamics(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
-    Q, R, Qf = synth.trunk_ilqr_costs(6, 8)
-    solver = iLQR(0.02, model, QuadraticCost(Q, R, Qf), N)
-    rng = np.random.default_rng(4 + rank)
-    amp, ph = rng.uniform(2, 15, size=batch), rng.uniform(0, 2 * np.pi, size=batch)
-    T = steps + N
-    th = np.linspace(0, 2 * np.pi * T / 100.0, T + 1)[None, :] + ph[:, None]
-    zref = np.tile(s['z_ref'], (batch, T + 1, 1))
-    zref[:, :, 0] += -amp[:, None] * np.sin(th); zref[:, :, 1] += amp[:, None] * np.sin(2 * th)
-    x0 = np.zeros((batch, 6)); x0[:, :3] = rng.uniform(-0.5, 0.5, size=(batch, 3))
-    mpc = RecedingHorizonILQR(solver, process_noise_std=1e-3, seed=4 + rank)
-    x0d, zd = L.to_dev(x0), L.to_dev(zref)
-    mpc.run_device(x0d, zd, 2)                                   # warm-up
+    N, steps = 20, args.mpc_steps
+    w = synth.mpc_ssm_tpwl_workload(batch, steps=steps, N=N, seed=4)
+    mpc = RecedingHorizonILQR(w['solver'], plant=w['plant'], observer=SSMOutputBelief(w['ssm']), process_noise_std=1e-3,
+                              seed=4 + rank)
+    xb, xp, zd = L.to_dev(w['x0_belief']), L.to_dev(w['x0_plant']), L.to_dev(w['z_ref'])
+    mpc.run_device(xb, zd, 3, xp)                                # warm-up
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     with ClockSampler(dev_index) as clk:
         s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s_.record()
-        out = mpc.run_device(x0d, zd, steps)
+        out = mpc.run_device(xb, zd, steps, xp)
         e_.record()
         torch.cuda.synchronize()
     t_dev = s_.elapsed_time(e_) * 1e-3
+    # e2e: host arrays in, closed-loop record out
+    t0 = time.perf_counter()
+    outh = mpc.run(w['x0_belief'], w['z_ref'], steps, x0_plant=w['x0_plant'])
+    t_e2e = time.perf_counter() - t0
     if world > 1:
-        tt = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev = float(tt[0])
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
     its = out['iterations'].float().mean().item()
+    h2d = (w['x0_belief'].size + w['x0_plant'].size + w['z_ref'].size) * 8
+    d2h = sum(v.size * v.itemsize for v in outh.values())
     return {"metric": "mpc_problem_steps_per_sec", "value": batch * steps * world / t_dev, "unit": "receding-horizon solves/s",
-            "n_gpus": world, "steps": steps, "warmup": 2, "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True,
+            "n_gpus": world, "steps": steps, "warmup": 3, "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "closed-loop receding-horizon iLQR Monte Carlo (BASELINE configs[3], SSM plant): %d problems per "
-                                   "GPU x %d control steps, horizon %d, warm start + u_last, process noise 1e-3" % (batch, steps, N),
-                       "mean_iterations_per_solve": its, "converged_frac": float((out['status'] & 1).float().mean().item())},
-            "e2e": None, "gpu_launches": steps * 2, "clocks": clk.summary(), "roofline": None}
+            "config": {"workload": "closed-loop receding-horizon iLQR Monte Carlo (BASELINE configs[3]): %d problems per GPU x %d "
+                                   "control steps; plant = Diamond TPWL bank (n=72, P=1000, nn, zoh), controller = Diamond-SSM "
+                                   "iLQR horizon %d with SSM observer, warm start + u_last, process noise 1e-3"
+                                   % (batch, steps, N),
+                       "mean_iterations_per_solve": its, "converged_frac": float((out['status'] & 1).float().mean().item()),
+                       "launches_per_control_step": "2 solver + 1 plant step + 1 observer map + 1 glue (mpc_shift) + 1 index_select"},
+            "e2e": {"value": batch * steps * world / t_e2e, "unit": "receding-horizon solves/s", "h2d_bytes_per_step": int(h2d // steps),
+                    "d2h_bytes_per_step": int(d2h // steps)},
+            "gpu_launches": steps * 5, "clocks": clk.summary(),
+            "roofline": {"kernel": "ilqr_ssm_fast_kernel<4> (per control step)", "bound": "tensor", "achieved": None, "peak": None,
+                         "unit": "TFLOP/s", "frac": None, "traffic": None,
+                         "note": "launch- and latency-bound loop of short solves (horizon 20, warm-started: a few iterations); "
+                                 "the per-step kernels are the headline iLQR kernel and the nn rollout kernel, whose rooflines "
+                                 "are reported by their own workloads"}}
 
 
 def run_ilqr_tpwl(args, rank, world, dev_index):
@@ -591,20 +670,93 @@ def run_ilqr_tpwl(args, rank, world, dev_index):
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm's CPU port on the host cores, same workload/metric (bounded sample)."""
-    t_all = []
-    val = cores = sample = None
-    for i in range(max(1, min(args.steps, 2))):
-        val, cores, sample = cpu_ilqr_baseline(args.batch, args.horizon, seed=3, per_core=args.cpu_per_core)
-        t_all.append(val)
-    val = max(t_all)
+    """--impl reference: the reference's own iLQR class on the host cores (imported from /root/reference when present,
+    else its CPU port), same workload/metric, bounded sample per step."""
+    steps = max(1, min(args.steps, 3))
+    vals, busys = [], []
+    cores = sample = kind = None
+    for i in range(steps):
+        val, cores, sample, kind, busy = cpu_ilqr_baseline(args.batch, args.horizon, seed=3, per_core=args.cpu_per_core)
+        vals.append(val); busys.append(busy)
+    val = max(vals)
     return {"impl": "reference", "metric": "ilqr_solves_per_sec", "value": val, "unit": "solves/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": 0, "ms_per_step": 1e3 * min(busys), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "Trunk-SSM batched iLQR (BASELINE configs[2]), horizon %d -- reference algorithm on CPU" % args.horizon},
-            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "Trunk-SSM batched iLQR (BASELINE configs[2]): horizon %d, n=6 m=8 order-3 SSM, be "
+                                   "discretisation, dt=0.02, seed 3 -- the reference algorithm on the host cores; one step = "
+                                   "%d solves per core of the same batch" % (args.horizon, args.cpu_per_core),
+                       "batch_per_gpu": args.batch, "horizon": args.horizon},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baselines of the secondary workloads (rank 0, N = 1): the oracle ports on the host cores, bounded samples
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_tpwl_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    idx, N = args
+    import sofacontrol_b200.synth as synth
+    from oracle.tpwl_np import TPWLATVNP
+    data, Hf = synth.tpwl_bank()
+    o = TPWLATVNP(data, params={'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}, Hf=Hf, discr_method='fe')
+    o.pre_discretize(0.01)          # fe bank: the per-step work (nearest point + affine step) does not depend on the method
+    x0, u = synth.tpwl_rollout_batch(max(idx) + 1, N=N, seed=2)
+    t0 = time.perf_counter()
+    for b in idx:
+        o.rollout(x0[b], u[b], 0.01)
+    return len(idx) * N, time.perf_counter() - t0
+
+
+def _cpu_ssm_eval_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    count, seed = args
+    import sofacontrol_b200.synth as synth
+    from oracle.ssm_np import SSMDynamicsNP
+    s = synth.trunk_ssm(8)
+    o = SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
+    rng = np.random.default_rng(seed)
+    X, U = rng.normal(size=(count, 6)), rng.uniform(0, 800, size=(count, 8))
+    t0 = time.perf_counter()
+    for x, u in zip(X, U):
+        o.get_continuous_jacobians(x, u)
+        o.get_observer_jacobians(x)
+        o.x_to_zfyf(x)
+    return count, time.perf_counter() - t0
+
+
+def _cpu_pool(worker, jobs):
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(len(jobs)) as pool:
+        res = pool.map(worker, jobs)
+    return sum(r[0] for r in res) / max(r[1] for r in res)
+
+
+def secondary_cpu_baseline(name):
+    cores = min(64, max(1, len(os.sched_getaffinity(0))))
+    if name == "tpwl_rollout_nn":
+        v = _cpu_pool(_cpu_tpwl_worker, [(list(range(c * 2, c * 2 + 2)), 100) for c in range(cores)])
+        return {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                "sample": "2 trajectories x 100 steps per core of the same seeded batch (oracle/tpwl_np.py, numpy)"}
+    if name == "ssm_eval":
+        v = _cpu_pool(_cpu_ssm_eval_worker, [(400, c) for c in range(cores)])
+        return {"value": v, "unit": "states/s", "cores": cores, "kind": "port",
+                "sample": "400 states per core: continuous Jacobians + observer Jacobians + output (oracle/ssm_np.py)"}
+    if name == "pod_gram":
+        nf, ns = 16384, 2048
+        X = np.random.default_rng(5).normal(size=(nf, ns))
+        t0 = time.perf_counter()
+        X.T @ X
+        dt = time.perf_counter() - t0
+        return {"value": 2.0 * nf * ns * ns / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                "sample": "numpy X^T X (multi-threaded BLAS) on a %d x %d slice" % (nf, ns)}
+    return None
+
+
+def _trim(res):
+    keep = ("metric", "value", "unit", "ms_per_step", "steps", "config", "e2e", "roofline", "gpu_launches", "cpu_baseline")
+    return {k: res[k] for k in keep if k in res}
 
 
 def main():
@@ -618,7 +770,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--cpu-per-core", type=int, default=2)
+    ap.add_argument("--mpc-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -638,23 +792,33 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     args.warmup = max(args.warmup, 3)
-    if args.workload == "ilqr_trunk_ssm":
-        res = run_ilqr(args, rank, world, local)
-    elif args.workload == "ssm_rollout":
-        res = run_ssm_rollout(args, rank, world, local)
-    elif args.workload == "ssm_eval":
-        res = run_ssm_eval(args, rank, world, local)
-    elif args.workload == "pod_gram":
-        res = run_pod_gram(args, rank, world, local)
-    elif args.workload == "ilqr_tpwl":
-        res = run_ilqr_tpwl(args, rank, world, local)
-    elif args.workload == "mpc":
-        res = run_mpc(args, rank, world, local)
-    else:
-        res = run_tpwl_rollout(args, rank, world, local, "nn" if args.workload.endswith("nn") else "weighting")
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "ilqr_trunk_ssm":
-        v, cores, sample = cpu_ilqr_baseline(args.batch, args.horizon, seed=3, per_core=args.cpu_per_core)
-        res["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample}
+    runners = {"ilqr_trunk_ssm": run_ilqr, "ssm_rollout": run_ssm_rollout, "ssm_eval": run_ssm_eval, "pod_gram": run_pod_gram,
+               "ilqr_tpwl": run_ilqr_tpwl, "mpc": run_mpc,
+               "tpwl_rollout_nn": lambda a, r, w_, l: run_tpwl_rollout(a, r, w_, l, "nn"),
+               "tpwl_rollout_weighting": lambda a, r, w_, l: run_tpwl_rollout(a, r, w_, l, "weighting")}
+    res = runners[args.workload](args, rank, world, local)
+    headline = (args.workload == "ilqr_trunk_ssm")
+    if headline and not args.no_secondary:
+        # the other kernels of the path, outside the headline's timed region (their own events, warm-up and L2 policy)
+        import copy
+        sec = {}
+        for name, steps in (("tpwl_rollout_nn", 5), ("ssm_eval", 5), ("pod_gram", 2), ("mpc", 1)):
+            a2 = copy.copy(args)
+            a2.batch, a2.steps, a2.warmup, a2.horizon = 4096, steps, 3, 100
+            a2.mpc_steps = 25
+            try:
+                r2 = runners[name](a2, rank, world, local)
+                if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                    cb = secondary_cpu_baseline(name)
+                    if cb is not None:
+                        r2["cpu_baseline"] = cb
+                sec[name] = _trim(r2)
+            except Exception as e:                      # a secondary workload must never take the headline down
+                sec[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        res["secondary"] = sec
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and headline:
+        v, cores, sample, kind, _ = cpu_ilqr_baseline(args.batch, args.horizon, seed=3, per_core=args.cpu_per_core)
+        res["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": cores, "kind": kind, "sample": sample}
     elif rank == 0:
         res.setdefault("cpu_baseline", None)
     if world > 1:

@@ -184,3 +184,59 @@ def pod_snapshots(nf, ns, seed=5, rank=None):
     Vo, _ = np.linalg.qr(rng.normal(size=(ns, k)))
     s = pod_spectrum(k)
     return (Uo * s) @ Vo.T, Uo, s
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Closed-loop Monte Carlo (config 4): "Diamond SSM + TPWL"
+# ------------------------------------------------------------------------------------------------------------
+def mpc_ssm_tpwl_workload(batch, steps=100, N=20, seed=4, dt=0.02):
+    """Plant = the Diamond-shaped TPWL bank (config 2; nearest-neighbour, zoh pre-discretised at the control period),
+    controller = receding-horizon iLQR on the Diamond SSM (m = 4) fed by the SSM observer (tip output [v; q] ->
+    [q; v] -> W_map).  The plant's reference configuration is placed so that its tip output at rest equals the SSM's
+    equilibrium output (the two synthetic models then describe the same operating point).  Returns the model
+    objects, the solver and seeded initial conditions / figure-8 references."""
+    from .SSM.ssm import SSMDynamics
+    from .tpwl.tpwl import TPWLATV
+    from .lqr.ilqr import iLQR
+    from .utils import QuadraticCost
+    rng = np.random.default_rng(seed)
+    s = trunk_ssm(4)
+    ssm = SSMDynamics(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
+    data, Hf = tpwl_bank()
+    tip = 1354
+    data['rom_info']['q_ref'] = data['rom_info']['q_ref'].copy()
+    data['rom_info']['q_ref'][3 * tip:3 * tip + 3] = s['z_ref'][:3]
+    plant = TPWLATV(data, params={'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}, Hf=Hf, discr_method='zoh')
+    plant.pre_discretize(dt)
+    Q, R, Qf = trunk_ilqr_costs(6, 4)
+    solver = iLQR(dt, ssm, QuadraticCost(Q, R, Qf), N)
+    T = steps + N
+    amp, ph = rng.uniform(1.0, 4.0, size=batch), rng.uniform(0, 2 * np.pi, size=batch)
+    th = np.linspace(0, 2 * np.pi * T / 100.0, T + 1)[None, :] + ph[:, None]
+    z_ref = np.tile(s['z_ref'], (batch, T + 1, 1))
+    z_ref[:, :, 0] += -amp[:, None] * np.sin(th)
+    z_ref[:, :, 1] += amp[:, None] * np.sin(2 * th)
+    x0_plant = np.concatenate((rng.normal(0, 0.05, size=(batch, 36)), rng.normal(0, 1.0, size=(batch, 36))), axis=1)
+    zp = plant_output_host(plant, x0_plant)
+    x0_belief = ssm_belief_host(s, zp)
+    solver.set_target(z_ref[:, :N + 1])
+    return dict(ssm=ssm, plant=plant, solver=solver, z_ref=z_ref, x0_plant=x0_plant, x0_belief=x0_belief, dt=dt)
+
+
+def plant_output_host(plant, x):
+    """z = H x + z_ref of a TPWL model on host arrays (workload construction only)."""
+    return x @ np.asarray(plant.H).T + np.asarray(plant.z_ref)
+
+
+def ssm_belief_host(s, z_vq):
+    """Initial belief of the SSM controller from a tip output in [v; q] order: W_map(vq2qv(z) - z_ref) on the host
+    (workload construction only; in the loop this is the batched map kernel)."""
+    f = diamond_ssm_fixture()
+    h = z_vq.shape[-1] // 2
+    dz = np.concatenate((z_vq[:, h:], z_vq[:, :h]), axis=1) - s['z_ref']
+    from itertools import combinations_with_replacement
+    feats = []
+    for d in (1, 2, 3):
+        for c in combinations_with_replacement(range(6), d):
+            feats.append(np.prod(dz[:, list(c)], axis=1))
+    return np.stack(feats, axis=1) @ f['v_coeff'].T

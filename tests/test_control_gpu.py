@@ -210,3 +210,66 @@ def test_mpc_shift_kernel():
     assert np.array_equal(L.to_host(uw), np.concatenate((up[:, 1:], up[:, -1:]), axis=1))
     assert np.array_equal(L.to_host(ua), up[:, 0]) and np.array_equal(L.to_host(ul)[:, k], up[:, 0])
     assert np.array_equal(L.to_host(zw), zr[:, k + 1:k + 2 + N])
+
+
+def test_closed_loop_tpwl_plant_with_ekf_matches_oracle_loop(golden):
+    """Config-4 loop as TemplateController.evaluate runs it (tpwl/controllers.py:85-117): TPWL plant, EKF belief from
+    y = C x + y_ref, receding-horizon iLQR (N = 8) with shifted warm start and u_last -- vs the same loop written
+    with the oracle classes (each pinned bitwise to the reference), noise-free, 2 problems x 5 control steps."""
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost
+    from sofacontrol_b200.mpc import RecedingHorizonILQR, EKFBelief
+    from sofacontrol_b200.tpwl.observer import DiscreteEKFObserver
+    from oracle.tpwl_np import TPWLATVNP
+    from oracle.ilqr_np import ILQRNP
+    from oracle.observer_np import DiscreteEKFObserverNP
+    from oracle.utils_np import QuadraticCost as QCo
+    g = golden("control_small.npz")
+    Cf = g['ekf_Cf']
+    m = _small_model(Cf=Cf, discr='be')
+    N, steps, Bt, dt = 8, 5, 2, 0.01
+    Q = np.zeros((6, 6)); Q[3, 3] = Q[4, 4] = 100.0; Q[5, 5] = 10.0
+    R = 1e-5 * np.eye(3)
+    rng = np.random.default_rng(21)
+    x0 = 0.2 * rng.normal(size=(Bt, 10))
+    th = np.linspace(0, 1.5, steps + N + 1)
+    zref = np.tile(m.z_ref, (Bt, steps + N + 1, 1))
+    zref[:, :, 3] += np.array([0.05, 0.08])[:, None] * np.sin(th)[None]
+    kw = dict(W=g['ekf_W'], V=g['ekf_V'], Sigma0=g['ekf_S0'])
+    sol = iLQR(dt, m, QuadraticCost(Q, R, np.zeros((6, 6))), N)
+    sol.set_target(zref[:, :N + 1])
+    out = RecedingHorizonILQR(sol, observer=EKFBelief(DiscreteEKFObserver(m, **kw))).run(x0, zref, steps)
+    om = TPWLATVNP(m.tpwl_dict, params={'tpwl_method': 'nn', 'dist_weights': {'q': 1.0, 'v': 0.0}}, Hf=None, Cf=Cf,
+                   discr_method='be')
+    om.H, om.z_ref = m.H, m.z_ref
+    for b in range(Bt):
+        ekf = DiscreteEKFObserverNP(om, **kw)
+        ekf.x = x0[b].copy()
+        xp, belief, u_plan, u_last = x0[b].copy(), x0[b].copy(), None, np.zeros(3)
+        for k in range(steps):
+            o = ILQRNP(dt, om, QCo(Q, R, np.zeros((6, 6))), N)
+            o.set_target(zref[b, k:k + N + 1]); o.set_u_last(u_last)
+            ws = None if u_plan is None else np.vstack((u_plan[1:], u_plan[-1:]))
+            _, u_plan, _ = o.ilqr_computation(belief, ws)
+            assert out['iterations'][b, k] == o.iterations
+            assert relerr(out['u'][b, k], u_plan[0]) < TOL
+            xp = om.update_state(xp, u_plan[0], dt)
+            ekf.update(u_plan[0], om.C @ xp + om.y_ref, dt)
+            belief, u_last = ekf.x.copy(), u_plan[0]
+            assert relerr(out['x'][b, k + 1], xp) < TOL
+
+
+def test_closed_loop_tpwl_plant_ssm_controller_runs():
+    """Config 4 'Diamond SSM + TPWL': TPWL plant (Diamond size), Diamond-SSM iLQR controller fed by the SSM observer
+    (tip output [v; q] -> [q; v] -> W_map).  Smoke of the plumbing: shapes, finite results, statuses set."""
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200.tpwl.tpwl import TPWLATV
+    from sofacontrol_b200.SSM.ssm import SSMDynamics
+    from sofacontrol_b200.lqr.ilqr import iLQR
+    from sofacontrol_b200.utils import QuadraticCost
+    from sofacontrol_b200.mpc import RecedingHorizonILQR, SSMOutputBelief
+    w = synth.mpc_ssm_tpwl_workload(16, steps=4, N=10, seed=4)
+    out = RecedingHorizonILQR(w['solver'], plant=w['plant'], observer=SSMOutputBelief(w['ssm']), process_noise_std=1e-4) \
+        .run(w['x0_belief'], w['z_ref'], 4, x0_plant=w['x0_plant'])
+    assert out['x'].shape == (16, 5, 72) and out['u'].shape == (16, 4, 4)
+    assert np.all(np.isfinite(out['u'])) and np.all(out['status'] != 0) and np.all(out['iterations'] >= 1)

@@ -561,6 +561,347 @@ __device__ __noinline__ double fwd_fast(const Ctx c, const IlqrArgs& a, int disc
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Lean forward pass (ilqr.py:117-162): the same arithmetic as fwd_fast with a fraction of its instructions.
+//   * every matrix-vector product of a step is a DMMA pair against a "vector tile": VT holds x_t, u_t, e_t, du_t in
+//     columns 0..3 and VT2 holds d_c, B u, dx in columns 0..2, so A_c x, B u, Q^T e, R^T du (and later A_d x,
+//     sep d_c, sep B u) fall out of the accumulator columns of the lanes that need them: (g, 0) owns row g of the
+//     state update, (g, 1) owns input g, output g and their cost terms (kept in registers, summed once per pass).
+//   * the two 6x6 inverses of the implicit discretisations are in-place Gauss-Jordan sweeps with one matrix ROW per
+//     lane (matrix h = lane >> 4): partial pivoting picks a pivot LANE (a REDUX on the high words of |a_rc|), the
+//     pivot row is broadcast with shuffles from that lane -- no row exchange, no select chains; the row / column
+//     permutation is undone by the addresses of the final stores.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int T_AC = 0, T_AD = 1, T_IA = 2, T_SP = 3, T_IMH = 4, T_W0 = 5, T_VT = 6, T_VT2 = 7;
+
+// rows of `a`: lane (h = lane >> 4, r = lane & 15 < 6) holds row r of matrix h.  On return dst_h = inv(matrix h).
+__device__ __forceinline__ void gj6_rows(double (&a)[6], int lane, double* __restrict__ dst) {
+    const int hs = lane & 16;
+    const bool lo = (lane < 16);
+    bool used = (lane & 15) >= 6;
+    int mycol = 0;
+    int pl[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        // partial pivoting: the unused row with the largest |a_rc| (compared on the high word: 20 mantissa bits;
+        // rows that agree that far are equally good pivots, the first one is taken)
+        const unsigned key = used ? 0u : (((unsigned)__double2hiint(a[c]) & 0x7fffffffu) | 1u);
+        const unsigned m0 = __reduce_max_sync(FULL, lo ? key : 0u);
+        const unsigned m1 = __reduce_max_sync(FULL, lo ? 0u : key);
+        const unsigned bal = __ballot_sync(FULL, key == (lo ? m0 : m1));
+        const int p = __ffs((bal >> hs) & 0xffffu) - 1 + hs;
+        pl[c] = p & 15;
+        double pr[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) pr[j] = __shfl_sync(FULL, a[j], p);
+        const double rp = __drcp_rn(pr[c]);
+        const bool isp = (lane == p);
+        const double w = isp ? rp : -__dmul_rn(a[c], rp);      // pivot row: scale ; other rows: -multiplier
+        const double z = isp ? 0.0 : 1.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            if (j != c) a[j] = fma(w, pr[j], __dmul_rn(a[j], z));
+        }
+        a[c] = w;                                               // the entering identity column e_p
+        if (isp) { used = true; mycol = c; }
+    }
+    // lane r was the pivot of column mycol; register c belongs to the pivot row pl[c] of column c:
+    // inv[mycol][pl[c]] = a[c]
+    if ((lane & 15) < 6) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dst[mycol * LD + pl[c]] = a[c];
+    }
+}
+
+// Model evaluation for the lean pass.  A_c -> tile AC, (dlt - s A_c) -> tile AUX (I - h A_c for be / bil,
+// I + dt A_c for fe, A_c itself for a discrete model), H -> record.  Returns the polynomial part of f_g in lanes
+// (g < 6, q = 0) and the raw output z_g in lanes (g < 6, q = 1).
+__device__ __forceinline__ double ssm_eval_lean(const Ctx c, const Scatter sc, double* __restrict__ AC,
+                                                double* __restrict__ AUX, double s_aux, double d0, double d1,
+                                                double* __restrict__ Hg) {
+    const int lane = c.lane;
+    double* PSI = CTX_WS(c) + W_PHI;
+    double* PV = CTX_WS(c) + W_PV;
+    const double* X = CTX_WS(c) + W_X;
+    const int* fidx = reinterpret_cast<const int*>(CTX_SH + SH_FIDX);
+    if (lane < 21) {
+        const int pk = fidx[6 + lane];
+        PSI[8 + lane] = __dmul_rn(X[pk & 7], X[(pk >> 3) & 7]);
+    } else if (lane < 27) {
+        PSI[2 + lane - 21] = X[lane - 21];
+    }
+    const double xj0 = X[lane % 6], xj1 = X[(32 + lane) % 6], xj2 = X[(64 + lane) % 6];
+    __syncwarp();
+    const double* T = CTX_SH + SH_T;
+    const double* t0 = T + lane * TS;
+    const double* t1 = T + (32 + lane) * TS;
+    const double* t2 = T + (lane < 8 ? 64 + lane : 72) * TS;
+    double g10, g11, g12;
+    {
+        const double2 c0 = *reinterpret_cast<const double2*>(t0);
+        const double2 c1 = *reinterpret_cast<const double2*>(t1);
+        const double2 c2 = *reinterpret_cast<const double2*>(t2);
+        g10 = c0.x; g11 = c1.x; g12 = c2.x;
+    }
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll
+    for (int q = 2; q < 8; q += 2) {
+        const double2 ps = *reinterpret_cast<const double2*>(PSI + q);
+        const double2 c0 = *reinterpret_cast<const double2*>(t0 + q);
+        const double2 c1 = *reinterpret_cast<const double2*>(t1 + q);
+        const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
+        a0 = fma(c0.x, ps.x, a0); b0 = fma(c0.y, ps.y, b0);
+        a1 = fma(c1.x, ps.x, a1); b1 = fma(c1.y, ps.y, b1);
+        a2 = fma(c2.x, ps.x, a2); b2 = fma(c2.y, ps.y, b2);
+    }
+    const double g20 = __dadd_rn(a0, b0), g21 = __dadd_rn(a1, b1), g22 = __dadd_rn(a2, b2);
+    a0 = a1 = a2 = b0 = b1 = b2 = 0.0;
+#pragma unroll
+    for (int q = 8; q < NJ; q += 2) {
+        const double2 ps = *reinterpret_cast<const double2*>(PSI + q);
+        const double2 c0 = *reinterpret_cast<const double2*>(t0 + q);
+        const double2 c1 = *reinterpret_cast<const double2*>(t1 + q);
+        const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
+        a0 = fma(c0.x, ps.x, a0); b0 = fma(c0.y, ps.y, b0);
+        a1 = fma(c1.x, ps.x, a1); b1 = fma(c1.y, ps.y, b1);
+        a2 = fma(c2.x, ps.x, a2); b2 = fma(c2.y, ps.y, b2);
+    }
+    const double g30 = __dadd_rn(a0, b0), g31 = __dadd_rn(a1, b1), g32 = __dadd_rn(a2, b2);
+    const double j0 = __dadd_rn(__dadd_rn(g10, g20), g30);
+    const double j1 = __dadd_rn(__dadd_rn(g11, g21), g31);
+    const double j2 = __dadd_rn(__dadd_rn(g12, g22), g32);
+    AC[sc.o0] = j0;
+    AUX[sc.o0] = __dsub_rn(d0, __dmul_rn(s_aux, j0));
+    if (lane < 4) {
+        AC[sc.o1] = j1;
+        AUX[sc.o1] = __dsub_rn(d1, __dmul_rn(s_aux, j1));
+    } else {
+        Hg[lane - 4] = j1;
+    }
+    if (lane < 8) Hg[28 + lane] = j2;
+    constexpr double third = 1.0 / 3.0;
+    PV[lane] = __dmul_rn(xj0, __dadd_rn(__dadd_rn(g10, __dmul_rn(0.5, g20)), __dmul_rn(third, g30)));
+    PV[32 + lane] = __dmul_rn(xj1, __dadd_rn(__dadd_rn(g11, __dmul_rn(0.5, g21)), __dmul_rn(third, g31)));
+    if (lane < 8) PV[64 + lane] = __dmul_rn(xj2, __dadd_rn(__dadd_rn(g12, __dmul_rn(0.5, g22)), __dmul_rn(third, g32)));
+    __syncwarp();
+    double val = 0.0;
+    if (c.q < 2 && c.g < 6) {
+        const double* pv = PV + 36 * c.q + 6 * c.g;
+        const double2 p01 = *reinterpret_cast<const double2*>(pv);
+        const double2 p23 = *reinterpret_cast<const double2*>(pv + 2);
+        const double2 p45 = *reinterpret_cast<const double2*>(pv + 4);
+        val = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(p01.x, p01.y), p23.x), p23.y), p45.x), p45.y);
+    }
+    return val;
+}
+
+template <int M, int DISCR>
+__device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const double* nx, const double* nu,
+                                        double alpha, const double* K, const double* k, const Rec tr,
+                                        const double* __restrict__ ztar, const double* __restrict__ ulast) {
+    constexpr bool IMPL = (DISCR == SRCB200_DISCR_BE || DISCR == SRCB200_DISCR_BIL);
+    const int lane = c.lane, g = c.g, q = c.q, N = a.N;
+    double* ws = CTX_WS(c);
+    double* X = ws + W_X;
+    double* AC = ws + W_TILES + T_AC * TILE;    // A_c
+    double* AD = ws + W_TILES + T_AD * TILE;    // A_d
+    double* IA = ws + W_TILES + T_IA * TILE;    // inv(A_c)
+    double* SP = ws + W_TILES + T_SP * TILE;    // sep = inv(A_c) (A_d - I)
+    double* IMH = ws + W_TILES + T_IMH * TILE;  // I - h A_c
+    double* W0 = ws + W_TILES + T_W0 * TILE;    // inv(I - h A_c) for bil
+    double* VT = ws + W_TILES + T_VT * TILE;    // columns: x_t | u_t | e_t | du_t
+    double* VT2 = ws + W_TILES + T_VT2 * TILE;  // columns: d_c | B u | dx_t
+    const double* Qt = CTX_SH + SH_Q;  const double* Rt = CTX_SH + SH_R;  const double* Qft = CTX_SH + SH_QF;
+    const double* Brt = CTX_SH + SH_BR; const double* zref = CTX_SH + SH_ZREF;
+    const Scatter sc = make_scatter(lane);
+    const double dt = a.dt;
+    const bool inc = a.cfg.include_input_var_constraint != 0;
+    const bool lf = (q == 0 && g < 6);          // row g of the state update
+    const bool lu = (q == 1);                   // input g / output g / their cost terms
+    // aux tile of the evaluation: dlt - s A_c
+    const double s_aux = (DISCR == SRCB200_DISCR_BE) ? dt : (DISCR == SRCB200_DISCR_BIL) ? 0.5 * dt
+                       : (DISCR == SRCB200_DISCR_FE) ? -dt : -1.0;
+    const bool addI = (DISCR != SRCB200_DISCR_NONE);
+    const double d0 = (addI && lane / 6 == lane % 6) ? 1.0 : 0.0, d1 = (addI && lane == 3) ? 1.0 : 0.0;
+    double* AUX = IMPL ? IMH : AD;
+    const double zr = (lu && g < 6) ? zref[g] : 0.0;
+    const bool dg0 = (q == g), dg1 = (4 + q == g) && (g < 6);   // diagonal flags of the B fragment (k = q / 4 + q, n = g)
+    double cacc = 0.0;
+
+    for (int t = 0; t < 8; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
+    if (lane < 3) ws[W_PHI + (lane == 0 ? 0 : (lane == 1 ? 1 : 29))] = (lane == 0) ? 1.0 : 0.0;   // psi_0 = 1, padding slots 0
+    __syncwarp();
+    if (lane < 8) X[lane] = lane < 6 ? nx[lane] : (lane == 7 ? 1.0 : 0.0);
+    if (lf) { const double v = nx[g]; VT[g * LD] = v; tr.x[g] = v; }
+    double up = (lu && g < M && ulast) ? ulast[g] : 0.0;
+    // prefetch registers of step 0: K[0] as an A fragment, nominal u / k in the input lanes, target in the output lanes
+    double pK0 = 0.0, pK1 = 0.0, p_nu = 0.0, p_k = 0.0, p_nx = 0.0, p_zt = 0.0;
+    if (g < M) {
+        if (K) { pK0 = K[g * 6 + q]; if (q < 2) pK1 = K[g * 6 + 4 + q]; }
+        if (lu) { p_nu = nu[g]; if (k) p_k = k[g]; }
+    }
+    if (lu && g < 6) p_zt = ztar[g];
+    __syncwarp();
+
+    for (int t = 0; t <= N; ++t) {
+        const bool last = (t == N);
+        double u = 0.0, du = 0.0;
+        if (!last) {
+            // u_t = (u_prev[t] + alpha k[t]) + K[t] (x[t] - x_prev[t])          (ilqr.py:140): column 2 of K VT2
+            Frag uf{0.0, 0.0};
+            if (K) {
+                dmma(uf, pK0, VT2[q * LD + g]);
+                dmma(uf, pK1, VT2[(4 + q) * LD + g]);
+            }
+            if (lu) {
+                double v = p_nu;
+                if (k) v = __dadd_rn(v, __dmul_rn(alpha, p_k));
+                if (K) v = __dadd_rn(v, uf.c0);
+                u = v;
+                du = inc ? __dsub_rn(u, up) : u;
+                VT[g * LD + 1] = u;
+                VT[g * LD + 3] = du;
+                if (g < M) tr.u[t * M + g] = u;
+            }
+        }
+        const double zt_now = p_zt;
+        if (t + 1 <= N) {
+            if (t + 1 < N && g < M) {
+                if (K) {
+                    const double* row = K + ((long long)(t + 1) * M + g) * 6;
+                    pK0 = row[q];
+                    if (q < 2) pK1 = row[4 + q];
+                }
+                if (lu) { p_nu = nu[(t + 1) * M + g]; if (k) p_k = k[(t + 1) * M + g]; }
+            }
+            if (K && lf) p_nx = nx[(t + 1) * 6 + g];
+            if (lu && g < 6) p_zt = ztar[(t + 1) * 6 + g];
+        }
+        // model at x_t
+        const double val = ssm_eval_lean(c, sc, AC, AUX, s_aux, d0, d1, tr.H + (long long)t * 36);
+        double e = 0.0;
+        if (lu && g < 6) {
+            e = __dsub_rn(__dadd_rn(val, zr), zt_now);
+            VT[g * LD + 2] = e;
+            tr.e[t * 6 + g] = e;
+        }
+        __syncwarp();   // A_c, aux tile, u, e, du visible
+        const double vb0 = VT[q * LD + g], vb1 = VT[(4 + q) * LD + g];   // B fragment of the vector tile
+        if (last) {
+            // terminal cost .5 e^T Qf e (ilqr.py:164-166)
+            Frag fq{0.0, 0.0};
+            dmma(fq, Qft[q * LD + g], vb0);
+            dmma(fq, Qft[(4 + q) * LD + g], vb1);
+            if (lu) cacc = fma(fq.c0, e, cacc);
+            break;
+        }
+        // A_c x, B u, Q^T e, R^T du                                             (ssm.py:168, 203; ilqr.py:168-175)
+        Frag fax{0.0, 0.0}, fbu{0.0, 0.0}, fq{0.0, 0.0}, fr{0.0, 0.0};
+        dmma(fax, AC[g * LD + q], vb0);        dmma(fax, AC[g * LD + 4 + q], vb1);
+        dmma(fbu, Brt[g * LD + q], vb0);       dmma(fbu, Brt[g * LD + 4 + q], vb1);
+        dmma(fq, Qt[q * LD + g], vb0);         dmma(fq, Qt[(4 + q) * LD + g], vb1);
+        dmma(fr, Rt[q * LD + g], vb0);         dmma(fr, Rt[(4 + q) * LD + g], vb1);
+        double dc = 0.0;
+        if (lf) {
+            // f = r phi + B u,  d_c = (f - A_c x) - B u
+            dc = __dsub_rn(__dsub_rn(__dadd_rn(val, fbu.c1), fax.c0), fbu.c1);
+            *reinterpret_cast<double2*>(VT2 + g * LD) = make_double2(dc, fbu.c1);
+        }
+        if (lu) cacc = fma(fr.c1, du, fma(fq.c0, e, cacc));
+        double xn = 0.0;
+        if (IMPL) {
+            // discretisation (ssm.py:279-301): inv(I - h A_c) and inv(A_c), one row per lane
+            {
+                const int r = lane & 15;
+                const double* src = ((lane & 16) ? AC : IMH) + (r < 6 ? r : 6) * LD;
+                double row[6];
+                const double2 r01 = *reinterpret_cast<const double2*>(src);
+                const double2 r23 = *reinterpret_cast<const double2*>(src + 2);
+                const double2 r45 = *reinterpret_cast<const double2*>(src + 4);
+                row[0] = r01.x; row[1] = r01.y; row[2] = r23.x; row[3] = r23.y; row[4] = r45.x; row[5] = r45.y;
+                gj6_rows(row, lane, (lane & 16) ? IA : (DISCR == SRCB200_DISCR_BE ? AD : W0));
+            }
+            __syncwarp();
+            if (DISCR == SRCB200_DISCR_BIL) {
+                // A_d = (I + h A_c) inv(I - h A_c)
+                Frag f{0.0, 0.0};
+                const double h = 0.5 * dt;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int kk = 4 * s + q;
+                    const double av = (g < 6 && kk < 6) ? __dadd_rn(g == kk ? 1.0 : 0.0, __dmul_rn(h, AC[g * LD + kk])) : 0.0;
+                    dmma(f, av, W0[kk * LD + g]);
+                }
+                store_frag(AD, f, g, q);
+                __syncwarp();
+            }
+            // sep = inv(A_c) (A_d - I)
+            Frag s{0.0, 0.0};
+            {
+                double bv0 = AD[q * LD + g], bv1 = AD[(4 + q) * LD + g];
+                if (dg0) bv0 = __dsub_rn(bv0, 1.0);
+                if (dg1) bv1 = __dsub_rn(bv1, 1.0);
+                dmma(s, IA[g * LD + q], bv0);
+                dmma(s, IA[g * LD + 4 + q], bv1);
+            }
+            store_frag(SP, s, g, q);
+            if (g < 6 && q < 3)
+                *reinterpret_cast<double2*>(tr.A + (long long)t * 36 + g * 6 + 2 * q) = *reinterpret_cast<const double2*>(AD + g * LD + 2 * q);
+            __syncwarp();
+            // B_d = sep B_r ; d_d = sep d_c ; x_{t+1} = (A_d x + B_d u) + d_d with B_d u = sep (B_r u)   (ssm.py:330-333)
+            const double sa0 = SP[g * LD + q], sa1 = SP[g * LD + 4 + q];
+            Frag bd{0.0, 0.0}, sv{0.0, 0.0}, ax{0.0, 0.0};
+            dmma(bd, sa0, Brt[q * LD + g]);       dmma(bd, sa1, Brt[(4 + q) * LD + g]);
+            dmma(sv, sa0, VT2[q * LD + g]);       dmma(sv, sa1, VT2[(4 + q) * LD + g]);
+            dmma(ax, AD[g * LD + q], vb0);        dmma(ax, AD[g * LD + 4 + q], vb1);
+            if (g < 6 && 2 * q < M)
+                *reinterpret_cast<double2*>(tr.B + (long long)t * 6 * M + g * M + 2 * q) = make_double2(bd.c0, bd.c1);
+            if (lf) xn = __dadd_rn(__dadd_rn(ax.c0, sv.c1), sv.c0);
+        } else {
+            // fe: A_d = I + dt A_c (aux tile), B_d = dt B_r, d_d = dt d_c ; discrete model: the maps themselves
+            const double sb = (DISCR == SRCB200_DISCR_FE) ? dt : 1.0;
+            Frag ax{0.0, 0.0}, bu{0.0, 0.0};
+            dmma(ax, AD[g * LD + q], vb0);        dmma(ax, AD[g * LD + 4 + q], vb1);
+            dmma(bu, __dmul_rn(sb, Brt[g * LD + q]), vb0);
+            dmma(bu, __dmul_rn(sb, Brt[g * LD + 4 + q]), vb1);
+            if (g < 6 && q < 3)
+                *reinterpret_cast<double2*>(tr.A + (long long)t * 36 + g * 6 + 2 * q) = *reinterpret_cast<const double2*>(AD + g * LD + 2 * q);
+            if (g < 6 && 2 * q < M) {
+                const double2 b2 = *reinterpret_cast<const double2*>(Brt + g * LD + 2 * q);
+                *reinterpret_cast<double2*>(tr.B + (long long)t * 6 * M + g * M + 2 * q) = make_double2(__dmul_rn(sb, b2.x), __dmul_rn(sb, b2.y));
+            }
+            if (lf) xn = __dadd_rn(__dadd_rn(ax.c0, bu.c1), __dmul_rn(sb, dc));
+        }
+        __syncwarp();   // every lane has read this step's fragments of VT / VT2
+        if (lf) {
+            X[g] = xn;
+            VT[g * LD] = xn;
+            VT2[g * LD + 2] = K ? __dsub_rn(xn, p_nx) : 0.0;
+            tr.x[(long long)(t + 1) * 6 + g] = xn;
+        }
+        up = u;
+        __syncwarp();
+    }
+    // cost = sum over the input / output lanes of their quadratic terms, halved (every term of ilqr.py:164-175 carries 1/2)
+    if (!lu) cacc = 0.0;
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) cacc = __dadd_rn(cacc, __shfl_xor_sync(FULL, cacc, off));
+    cacc = __shfl_sync(FULL, cacc, 1);
+    return __dmul_rn(0.5, cacc);
+}
+
+template <int M>
+__device__ __forceinline__ double fwd_dispatch(const Ctx c, const IlqrArgs& a, int discr, const double* nx, const double* nu,
+                                               double alpha, const double* K, const double* k, const Rec tr,
+                                               const double* __restrict__ ztar, const double* __restrict__ ulast) {
+    switch (discr) {
+        case SRCB200_DISCR_BE:  return fwd_lean<M, SRCB200_DISCR_BE>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
+        case SRCB200_DISCR_BIL: return fwd_lean<M, SRCB200_DISCR_BIL>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
+        case SRCB200_DISCR_FE:  return fwd_lean<M, SRCB200_DISCR_FE>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
+        default:                return fwd_lean<M, SRCB200_DISCR_NONE>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Backward pass (ilqr.py:219-300).  The record of step t-1 is fetched into registers while step t computes.
 // ---------------------------------------------------------------------------------------------------------------
 struct BwdResult { double rho, drho; int pd_fail; };   // pd_fail: horizon index of the failed PD test, -1: none
@@ -884,7 +1225,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
             for (int e = lane; e < N * M; e += 32) nom.u[e] = a.u_init ? a.u_init[b * (long long)N * M + e] : 0.0;
             __syncwarp();
             __threadfence_block();
-            cost = fwd_fast<M>(c, a, discr, nom.x, nom.u, 1.0, nullptr, nullptr, tr0, ztar, ulast);
+            cost = fwd_dispatch<M>(c, a, discr, nom.x, nom.u, 1.0, nullptr, nullptr, tr0, ztar, ulast);
             if (a.ocost0 && lane == 0) a.ocost0[b] = cost;
             // priority class: initial cost above the running mean of the batch -> expected to need many iterations
             cls = 1;
@@ -911,7 +1252,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
                 double cost_t = cost, alpha_acc = 0.0;
                 while (!improved && !failed) {
                     improved = true;
-                    cost_t = fwd_fast<M>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
+                    cost_t = fwd_dispatch<M>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
                     ++trials;
                     double dc = 0.0;
                     const double a2 = __dmul_rn(__dmul_rn(alpha, alpha), 0.5);

@@ -27,11 +27,16 @@ namespace fast {
 
 constexpr int LD = 12;            // tile row stride (doubles): A-/B-fragment loads are bank-conflict free
 constexpr int TILE = 8 * LD;
-constexpr int WARPS = 8;          // problems in flight per CTA (2 CTAs per SM; 20-24 warps at 96/80 registers measured slower)
+constexpr int WARPS = 8;          // problems in flight per CTA.  Two launch shapes of the solve kernel (template CR):
+                                  //   CR = true : 1 CTA per SM,  255 registers, the Jacobian-table rows of a lane in registers
+                                  //   CR = false: 2 CTAs per SM, 128 registers, the table read from shared memory every step
 constexpr int NJ = 30;            // slots per Jacobian row: [deg1 c, 0 | deg2: 6 | deg3: 21, 0] -- degrees on even boundaries
 constexpr int NPD = 73;           // table rows: 72 Jacobian rows (A_c 0..35, H 36..71) + one zero row for idle lanes
 constexpr int TS = 30;            // table row stride (doubles): LDS.128 of 8 consecutive rows hit 8 distinct 16 B banks
 constexpr int NFEAT = 83;
+#ifndef SRCB_GAIN_SHFL
+#define SRCB_GAIN_SHFL 0
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 // per-CTA shared block (doubles)
@@ -47,20 +52,38 @@ constexpr int SH_END = SH_FIDX + 44;
 constexpr int W_PHI = 0;                        // psi slots 0..29 (see NJ), then PV[72]: x_j * value part of row o at W_PHI + 32
 constexpr int W_PV = 32;                        // 72 (+0)
 constexpr int W_X = 104;                        // x_t (6), X[6] = 0, X[7] = 1
-constexpr int W_U = 112;
-constexpr int W_UP = 120;                       // u_{t-1}, then du
-constexpr int W_DC = 128;
-constexpr int W_DD = 136;
-constexpr int W_E = 144;
-constexpr int W_DX = 152;                       // x_t - x_prev_t (6)
-constexpr int W_QE = 160;
-constexpr int W_RDU = 168;
-constexpr int W_TILES = 176;
+constexpr int W_U = 112;                        // rollout kernel: u_t ; backward pass: 2 x 8 doubles of pivot-column broadcast
+constexpr int W_DC = 128;                       // d_c (rollout kernel) / c_u (backward pass)
+constexpr int W_DD = 136;                       // d_d (rollout kernel) / du (backward pass)
+constexpr int W_TILES = 144;
 constexpr int NTILES = 11;
-constexpr int W_SIZE = W_TILES + NTILES * TILE; // 1232 doubles = 9.6 KB per warp
+constexpr int W_SIZE = W_TILES + NTILES * TILE; // 1200 doubles = 9.4 KB per warp
 constexpr size_t SMEM_BYTES = sizeof(double) * (SH_END + WARPS * W_SIZE);
 
 struct Frag { double c0, c1; };
+
+// Optional phase clocks (build with -DSRCB_PHASE_TIMING, read with srcb200_debug_phase): lane 0 of every warp adds
+// the clock64 distance between consecutive marks to a global table.  0..7 forward step, 8..15 backward step.
+#ifdef SRCB_PHASE_TIMING
+__device__ unsigned long long g_phase[32];
+#define PH_DECL long long ph_t = clock64()
+#define PH(i) do { const long long ph_n = clock64(); if (lane == 0) atomicAdd(&g_phase[i], (unsigned long long)(ph_n - ph_t)); ph_t = clock64(); } while (0)
+#else
+#define PH_DECL
+#define PH(i)
+#endif
+
+// Reciprocal without the slow-path branch of __drcp_rn (which splits the basic block and keeps the scheduler from
+// overlapping it with the pivot search): MUFU.RCP64H seed (rcp.approx.ftz.f64, ~2^-20) + two Newton steps; within
+// 1 ulp for normal inputs, inf / nan for 0 / inf / nan like the division it replaces.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
 
 __device__ __forceinline__ void dmma(Frag& c, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -325,242 +348,6 @@ __device__ __forceinline__ bool gj_spd(double* __restrict__ tile, int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Forward pass (ilqr.py:117-162).  Global inputs of step t+1 (nominal u, k, K row, nominal x, target) are fetched
-// into registers while step t computes.
-// ---------------------------------------------------------------------------------------------------------------
-template <int M>
-__device__ __noinline__ double fwd_fast(const Ctx c, const IlqrArgs& a, int discr, const double* nx,
-                                        const double* nu, double alpha, const double* K,
-                                        const double* k, const Rec tr, const double* __restrict__ ztar,
-                                        const double* __restrict__ ulast) {
-    const int lane = c.lane, g = c.g, q = c.q, N = a.N;
-    double* ws = CTX_WS(c);
-    double* X = ws + W_X;   double* U = ws + W_U;   double* UP = ws + W_UP;  double* DC = ws + W_DC;
-    double* DD = ws + W_DD; double* E = ws + W_E;   double* DX = ws + W_DX;  double* QE = ws + W_QE;
-    double* RDU = ws + W_RDU;
-    double* AC = ws + W_TILES + 0 * TILE;   // A_c
-    double* AD = ws + W_TILES + 1 * TILE;   // A_d
-    double* IA = ws + W_TILES + 2 * TILE;   // inv(A_c)
-    double* SP = ws + W_TILES + 3 * TILE;   // sep = inv(A_c) (A_d - I)
-    double* BD = ws + W_TILES + 4 * TILE;   // B_d
-    double* W0 = ws + W_TILES + 5 * TILE;   // inv(I - h A_c) for bil
-    const double* Qt = CTX_SH + SH_Q;  const double* Rt = CTX_SH + SH_R;  const double* Qft = CTX_SH + SH_QF;
-    const double* Brt = CTX_SH + SH_BR; const double* zref = CTX_SH + SH_ZREF;
-    const Scatter sc = make_scatter(lane);
-    const double dt = a.dt;
-    const bool inc = a.cfg.include_input_var_constraint != 0;
-    const int bo0 = (lane / M) * LD + lane % M;                    // B element `lane`
-    const int bo1 = ((32 + lane) / M) * LD + (32 + lane) % M;      // B element `32 + lane` (valid while < 6 M)
-    double cost = 0.0;
-
-    for (int t = 0; t < 6; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
-    if (lane < 8) X[lane] = lane < 6 ? nx[lane] : (lane == 7 ? 1.0 : 0.0);
-    if (lane < 6) tr.x[lane] = nx[lane];
-    if (lane < 8) { UP[lane] = (lane < M && ulast) ? ulast[lane] : 0.0; U[lane] = 0.0; DC[lane] = 0.0; DX[lane] = 0.0; }
-    if (lane < 3) ws[W_PHI + (lane == 0 ? 0 : (lane == 1 ? 1 : 29))] = (lane == 0) ? 1.0 : 0.0;   // psi_0 = 1, padding slots 0
-    // prefetch registers for step 0
-    double p_nu = 0.0, p_k = 0.0, p_K[6] = {0, 0, 0, 0, 0, 0}, p_nx = 0.0, p_zt = 0.0;
-    if (lane < M) {
-        p_nu = nu[lane];
-        if (k) p_k = k[lane];
-        if (K) {
-#pragma unroll
-            for (int jj = 0; jj < 6; ++jj) p_K[jj] = K[lane * 6 + jj];
-        }
-    }
-    if (lane >= 14 && lane < 20) p_zt = ztar[lane - 14];
-    __syncwarp();
-
-    for (int t = 0; t <= N; ++t) {
-        const bool last = (t == N);
-        if (!last && lane < M) {
-            // u_t = (u_prev[t] + alpha k[t]) + K[t] (x[t] - x_prev[t])          (ilqr.py:140)
-            double v = p_nu;
-            if (k) v = __dadd_rn(v, __dmul_rn(alpha, p_k));
-            if (K) {
-                double acc = 0.0;
-#pragma unroll
-                for (int jj = 0; jj < 6; ++jj) acc = fma(p_K[jj], DX[jj], acc);
-                v = __dadd_rn(v, acc);
-            }
-            U[lane] = v;
-            tr.u[t * M + lane] = v;
-        }
-        const double zt_now = p_zt;
-        // issue the loads of step t+1
-        if (t + 1 <= N) {
-            if (t + 1 < N && lane < M) {
-                p_nu = nu[(t + 1) * M + lane];
-                if (k) p_k = k[(t + 1) * M + lane];
-                if (K) {
-                    const double* row = K + ((long long)(t + 1) * M + lane) * 6;
-#pragma unroll
-                    for (int jj = 0; jj < 6; ++jj) p_K[jj] = row[jj];
-                }
-            }
-            if (K && lane < 6) p_nx = nx[(t + 1) * 6 + lane];
-            if (lane >= 14 && lane < 20) p_zt = ztar[(t + 1) * 6 + lane - 14];
-        }
-        // model at x_t: A_c (tile), H_t (record), f, z
-        const double val = ssm_eval_fast(c, sc, AC, tr.H + (long long)t * 36);
-        if (lane >= 14 && lane < 20) {
-            const int i = lane - 14;
-            const double e = __dsub_rn(__dadd_rn(val, zref[i]), zt_now);
-            E[i] = e;
-            tr.e[t * 6 + i] = e;
-        }
-        __syncwarp();   // U, E, AC visible
-        if (last) {
-            // terminal cost .5 e^T Qf e (ilqr.py:164-166)
-            if (lane < 6) {
-                double acc = 0.0;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) acc = fma(E[i], Qft[i * LD + lane], acc);
-                QE[lane] = acc;
-            }
-            __syncwarp();
-            double s1 = 0.0;
-#pragma unroll
-            for (int jj = 0; jj < 6; ++jj) s1 = fma(QE[jj], E[jj], s1);
-            cost = __dadd_rn(cost, __dmul_rn(0.5, s1));
-            break;
-        }
-        // f = r phi + B u,  d_c = (f - A_c x) - B u                            (ssm.py:168, 203)
-        if (lane >= 8 && lane < 14) {
-            const int i = lane - 8;
-            double bu = 0.0, ax = 0.0;
-#pragma unroll
-            for (int jj = 0; jj < M; ++jj) bu = fma(Brt[i * LD + jj], U[jj], bu);
-#pragma unroll
-            for (int kk = 0; kk < 6; ++kk) ax = fma(AC[i * LD + kk], X[kk], ax);
-            DC[i] = __dsub_rn(__dsub_rn(__dadd_rn(val, bu), ax), bu);
-        }
-        // step-cost pieces: QE = e^T Q, RDU = du^T R                            (ilqr.py:168-175)
-        if (lane >= 14 && lane < 20) {
-            const int jj = lane - 14;
-            double acc = 0.0;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) acc = fma(E[i], Qt[i * LD + jj], acc);
-            QE[jj] = acc;
-        }
-        if (lane >= 20 && lane < 20 + M) {
-            const int jj = lane - 20;
-            double acc = 0.0;
-#pragma unroll
-            for (int i = 0; i < M; ++i) {
-                const double du = inc ? __dsub_rn(U[i], UP[i]) : U[i];
-                acc = fma(du, Rt[i * LD + jj], acc);
-            }
-            RDU[jj] = acc;
-        }
-        // discretisation (ssm.py:279-301)
-        if (discr == SRCB200_DISCR_BE || discr == SRCB200_DISCR_BIL) {
-            const double h = (discr == SRCB200_DISCR_BE) ? dt : 0.5 * dt;
-            const int hm = lane >> 4, j = lane & 15;
-            double col[6];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-                double v = 0.0;
-                if (j < 6) {
-                    const double av = AC[r * LD + j];
-                    v = hm ? av : __dsub_rn(r == j ? 1.0 : 0.0, __dmul_rn(h, av));
-                } else if (j < 12) {
-                    v = (r == j - 6) ? 1.0 : 0.0;
-                }
-                col[r] = v;
-            }
-            gj6_pair(col, lane, hm ? IA : (discr == SRCB200_DISCR_BE ? AD : W0));
-            __syncwarp();
-            if (discr == SRCB200_DISCR_BIL) {
-                // A_d = (I + h A_c) inv(I - h A_c)
-                Frag f{0.0, 0.0};
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int kk = 4 * s + q;
-                    const double av = (g < 6 && kk < 6) ? __dadd_rn(g == kk ? 1.0 : 0.0, __dmul_rn(h, AC[g * LD + kk])) : 0.0;
-                    dmma(f, av, W0[kk * LD + g]);
-                }
-                store_frag(AD, f, g, q);
-                __syncwarp();
-            }
-            // sep = inv(A_c) (A_d - I)
-            Frag s{0.0, 0.0};
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const int kk = 4 * s2 + q;
-                const double bv = (kk < 6 && g < 6) ? __dsub_rn(AD[kk * LD + g], kk == g ? 1.0 : 0.0) : 0.0;
-                dmma(s, IA[g * LD + kk], bv);
-            }
-            store_frag(SP, s, g, q);
-            __syncwarp();   // also orders DC / QE / RDU
-            // B_d = sep B_r ; d_d = sep d_c
-            Frag b{0.0, 0.0};
-            mma88<false, false>(b, SP, Brt, g, q);
-            store_frag(BD, b, g, q);
-            if (lane < 6) {
-                double acc = 0.0;
-#pragma unroll
-                for (int kk = 0; kk < 6; ++kk) acc = fma(SP[lane * LD + kk], DC[kk], acc);
-                DD[lane] = acc;
-            }
-        } else {
-            __syncwarp();   // DC visible
-            if (discr == SRCB200_DISCR_FE) {
-                const double v0 = __dmul_rn(dt, AC[c.off0]);
-                AD[c.off0] = (lane / 6 == lane % 6) ? __dadd_rn(1.0, v0) : v0;
-                if (lane < 4) {
-                    const double v1 = __dmul_rn(dt, AC[c.off1]);
-                    AD[c.off1] = (lane == 3) ? __dadd_rn(1.0, v1) : v1;   // element 35 is the (5,5) diagonal
-                }
-                if (lane < 6 * M) BD[bo0] = __dmul_rn(dt, Brt[bo0]);
-                if (32 + lane < 6 * M) BD[bo1] = __dmul_rn(dt, Brt[bo1]);
-                if (lane < 6) DD[lane] = __dmul_rn(dt, DC[lane]);
-            } else {   // already discrete
-                AD[c.off0] = AC[c.off0];
-                if (lane < 4) AD[c.off1] = AC[c.off1];
-                if (lane < 6 * M) BD[bo0] = Brt[bo0];
-                if (32 + lane < 6 * M) BD[bo1] = Brt[bo1];
-                if (lane < 6) DD[lane] = DC[lane];
-            }
-        }
-        __syncwarp();
-        // cost accumulation (identical in every lane)
-        {
-            double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-            for (int jj = 0; jj < 6; ++jj) s1 = fma(QE[jj], E[jj], s1);
-#pragma unroll
-            for (int jj = 0; jj < M; ++jj) s2 = fma(RDU[jj], inc ? __dsub_rn(U[jj], UP[jj]) : U[jj], s2);
-            cost = __dadd_rn(cost, __dadd_rn(__dmul_rn(0.5, s1), __dmul_rn(0.5, s2)));
-        }
-        // x_{t+1} = (A_d x + B_d u) + d_d                                        (ssm.py:330-333)
-        double xn = 0.0;
-        if (lane < 6) {
-            double ax = 0.0, bu = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 6; ++kk) ax = fma(AD[lane * LD + kk], X[kk], ax);
-#pragma unroll
-            for (int jj = 0; jj < M; ++jj) bu = fma(BD[lane * LD + jj], U[jj], bu);
-            xn = __dadd_rn(__dadd_rn(ax, bu), DD[lane]);
-        }
-        // record the linearisation
-        tr.A[(long long)t * 36 + lane] = AD[c.off0];
-        if (lane < 4) tr.A[(long long)t * 36 + 32 + lane] = AD[c.off1];
-        if (lane < 6 * M) tr.B[(long long)t * 6 * M + lane] = BD[bo0];
-        if (32 + lane < 6 * M) tr.B[(long long)t * 6 * M + 32 + lane] = BD[bo1];
-        __syncwarp();
-        if (lane < 6) {
-            X[lane] = xn;
-            DX[lane] = K ? __dsub_rn(xn, p_nx) : 0.0;
-            tr.x[(long long)(t + 1) * 6 + lane] = xn;
-        }
-        if (lane < M) UP[lane] = U[lane];
-        __syncwarp();
-    }
-    return cost;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // Lean forward pass (ilqr.py:117-162): the same arithmetic as fwd_fast with a fraction of its instructions.
 //   * every matrix-vector product of a step is a DMMA pair against a "vector tile": VT holds x_t, u_t, e_t, du_t in
 //     columns 0..3 and VT2 holds d_c, B u, dx in columns 0..2, so A_c x, B u, Q^T e, R^T du (and later A_d x,
@@ -574,26 +361,34 @@ __device__ __noinline__ double fwd_fast(const Ctx c, const IlqrArgs& a, int disc
 constexpr int T_AC = 0, T_AD = 1, T_IA = 2, T_SP = 3, T_IMH = 4, T_W0 = 5, T_VT = 6, T_VT2 = 7;
 
 // rows of `a`: lane (h = lane >> 4, r = lane & 15 < 6) holds row r of matrix h.  On return dst_h = inv(matrix h).
+// Latency matters more than instruction count here (six strictly sequential pivot steps; measured on B200,
+// profiles/lat_microbench_r2.txt: reciprocal 72 cycles, REDUX 23, ballot + ffs 58, 64-bit shuffle 27), so
+//   * every row computes the reciprocal of its OWN candidate while the pivot search runs; the pivot row's one is
+//     broadcast with the row;
+//   * the search key is the high word of |a_rc| with the row index in its low four bits: one REDUX.MAX per matrix
+//     yields the winner AND its lane, no ballot / find-first-set.  Candidates that agree in the leading 16 mantissa
+//     bits count as tied and the lower row wins -- either is as good a pivot as the exact maximum.
 __device__ __forceinline__ void gj6_rows(double (&a)[6], int lane, double* __restrict__ dst) {
-    const int hs = lane & 16;
+    const int r = lane & 15, hs = lane & 16;
     const bool lo = (lane < 16);
-    bool used = (lane & 15) >= 6;
+    const unsigned tag = 15u - (unsigned)r;
+    bool used = (r >= 6);
     int mycol = 0;
     int pl[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-        // partial pivoting: the unused row with the largest |a_rc| (compared on the high word: 20 mantissa bits;
-        // rows that agree that far are equally good pivots, the first one is taken)
-        const unsigned key = used ? 0u : (((unsigned)__double2hiint(a[c]) & 0x7fffffffu) | 1u);
+        const double rown = rcp_fast(a[c]);
+        const unsigned key = used ? 0u : ((((unsigned)__double2hiint(a[c]) & 0x7ffffff0u)) | tag);
         const unsigned m0 = __reduce_max_sync(FULL, lo ? key : 0u);
         const unsigned m1 = __reduce_max_sync(FULL, lo ? 0u : key);
-        const unsigned bal = __ballot_sync(FULL, key == (lo ? m0 : m1));
-        const int p = __ffs((bal >> hs) & 0xffffu) - 1 + hs;
-        pl[c] = p & 15;
+        const unsigned mx = lo ? m0 : m1;
+        const int prow = 15 - (int)(mx & 15u);
+        const int p = hs + prow;
+        pl[c] = prow;
         double pr[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) pr[j] = __shfl_sync(FULL, a[j], p);
-        const double rp = __drcp_rn(pr[c]);
+        for (int j = 0; j < 6; ++j) pr[j] = (j == c) ? 0.0 : __shfl_sync(FULL, a[j], p);
+        const double rp = __shfl_sync(FULL, rown, p);
         const bool isp = (lane == p);
         const double w = isp ? rp : -__dmul_rn(a[c], rp);      // pivot row: scale ; other rows: -multiplier
         const double z = isp ? 0.0 : 1.0;
@@ -606,7 +401,7 @@ __device__ __forceinline__ void gj6_rows(double (&a)[6], int lane, double* __res
     }
     // lane r was the pivot of column mycol; register c belongs to the pivot row pl[c] of column c:
     // inv[mycol][pl[c]] = a[c]
-    if ((lane & 15) < 6) {
+    if (r < 6) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) dst[mycol * LD + pl[c]] = a[c];
     }
@@ -615,7 +410,23 @@ __device__ __forceinline__ void gj6_rows(double (&a)[6], int lane, double* __res
 // Model evaluation for the lean pass.  A_c -> tile AC, (dlt - s A_c) -> tile AUX (I - h A_c for be / bil,
 // I + dt A_c for fe, A_c itself for a discrete model), H -> record.  Returns the polynomial part of f_g in lanes
 // (g < 6, q = 0) and the raw output z_g in lanes (g < 6, q = 1).
-__device__ __forceinline__ double ssm_eval_lean(const Ctx c, const Scatter sc, double* __restrict__ AC,
+// The coefficient rows `lane` and `32 + lane` of the Jacobian table live in REGISTERS for the whole pass (ca, cb:
+// slot 0 = the degree-1 constant, 1..6 = degree 2, 7..27 = degree 3; 112 registers, the kernel runs 8 warps per SM):
+// the table reads were 2/3 of the shared-memory wavefronts of a forward step and the shared-memory pipe was the
+// loaded unit.  Only rows 64..71 (lanes < 8) and the broadcast psi operands still come from shared memory.
+constexpr int NCR = 28;
+__device__ __forceinline__ void load_coeff_rows(int lane, double (&ca)[NCR], double (&cb)[NCR]) {
+    const double* T = CTX_SH + SH_T;
+    const double* t0 = T + lane * TS;
+    const double* t1 = T + (32 + lane) * TS;
+    ca[0] = t0[0]; cb[0] = t1[0];
+#pragma unroll
+    for (int s = 1; s < NCR; ++s) { ca[s] = t0[s + 1]; cb[s] = t1[s + 1]; }
+}
+
+template <bool CR>
+__device__ __forceinline__ double ssm_eval_lean(const Ctx c, const Scatter sc, const double (&ca)[NCR],
+                                                const double (&cb)[NCR], double* __restrict__ AC,
                                                 double* __restrict__ AUX, double s_aux, double d0, double d1,
                                                 double* __restrict__ Hg) {
     const int lane = c.lane;
@@ -631,39 +442,33 @@ __device__ __forceinline__ double ssm_eval_lean(const Ctx c, const Scatter sc, d
     }
     const double xj0 = X[lane % 6], xj1 = X[(32 + lane) % 6], xj2 = X[(64 + lane) % 6];
     __syncwarp();
-    const double* T = CTX_SH + SH_T;
-    const double* t0 = T + lane * TS;
-    const double* t1 = T + (32 + lane) * TS;
-    const double* t2 = T + (lane < 8 ? 64 + lane : 72) * TS;
-    double g10, g11, g12;
-    {
-        const double2 c0 = *reinterpret_cast<const double2*>(t0);
-        const double2 c1 = *reinterpret_cast<const double2*>(t1);
-        const double2 c2 = *reinterpret_cast<const double2*>(t2);
-        g10 = c0.x; g11 = c1.x; g12 = c2.x;
-    }
+    const double* t2 = CTX_SH + SH_T + (lane < 8 ? 64 + lane : 72) * TS;   // lanes >= 8: the zero row (one broadcast read)
+    const double* t0 = CTX_SH + SH_T + lane * TS;
+    const double* t1 = CTX_SH + SH_T + (32 + lane) * TS;
+#define CA(s) (CR ? ca[s] : t0[(s) == 0 ? 0 : (s) + 1])
+#define CB(s) (CR ? cb[s] : t1[(s) == 0 ? 0 : (s) + 1])
+    const double g10 = CA(0), g11 = CB(0), g12 = t2[0];
+    // degree 2: table slots 2..7 (even / odd accumulators)
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
 #pragma unroll
     for (int q = 2; q < 8; q += 2) {
         const double2 ps = *reinterpret_cast<const double2*>(PSI + q);
-        const double2 c0 = *reinterpret_cast<const double2*>(t0 + q);
-        const double2 c1 = *reinterpret_cast<const double2*>(t1 + q);
         const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
-        a0 = fma(c0.x, ps.x, a0); b0 = fma(c0.y, ps.y, b0);
-        a1 = fma(c1.x, ps.x, a1); b1 = fma(c1.y, ps.y, b1);
-        a2 = fma(c2.x, ps.x, a2); b2 = fma(c2.y, ps.y, b2);
+        a0 = fma(CA(q - 1), ps.x, a0); b0 = fma(CA(q), ps.y, b0);
+        a1 = fma(CB(q - 1), ps.x, a1); b1 = fma(CB(q), ps.y, b1);
+        a2 = fma(c2.x, ps.x, a2);      b2 = fma(c2.y, ps.y, b2);
     }
     const double g20 = __dadd_rn(a0, b0), g21 = __dadd_rn(a1, b1), g22 = __dadd_rn(a2, b2);
+    // degree 3: table slots 8..28 (slot 29 is padding)
     a0 = a1 = a2 = b0 = b1 = b2 = 0.0;
 #pragma unroll
     for (int q = 8; q < NJ; q += 2) {
         const double2 ps = *reinterpret_cast<const double2*>(PSI + q);
-        const double2 c0 = *reinterpret_cast<const double2*>(t0 + q);
-        const double2 c1 = *reinterpret_cast<const double2*>(t1 + q);
         const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
-        a0 = fma(c0.x, ps.x, a0); b0 = fma(c0.y, ps.y, b0);
-        a1 = fma(c1.x, ps.x, a1); b1 = fma(c1.y, ps.y, b1);
-        a2 = fma(c2.x, ps.x, a2); b2 = fma(c2.y, ps.y, b2);
+        a0 = fma(CA(q - 1), ps.x, a0);
+        a1 = fma(CB(q - 1), ps.x, a1);
+        if (q + 1 < NJ - 1) { b0 = fma(CA(q), ps.y, b0); b1 = fma(CB(q), ps.y, b1); }
+        a2 = fma(c2.x, ps.x, a2);      b2 = fma(c2.y, ps.y, b2);
     }
     const double g30 = __dadd_rn(a0, b0), g31 = __dadd_rn(a1, b1), g32 = __dadd_rn(a2, b2);
     const double j0 = __dadd_rn(__dadd_rn(g10, g20), g30);
@@ -694,7 +499,7 @@ __device__ __forceinline__ double ssm_eval_lean(const Ctx c, const Scatter sc, d
     return val;
 }
 
-template <int M, int DISCR>
+template <int M, int DISCR, bool CR>
 __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const double* nx, const double* nu,
                                         double alpha, const double* K, const double* k, const Rec tr,
                                         const double* __restrict__ ztar, const double* __restrict__ ulast) {
@@ -726,6 +531,8 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
     const double zr = (lu && g < 6) ? zref[g] : 0.0;
     const bool dg0 = (q == g), dg1 = (4 + q == g) && (g < 6);   // diagonal flags of the B fragment (k = q / 4 + q, n = g)
     double cacc = 0.0;
+    double ca[NCR], cb[NCR];
+    if (CR) load_coeff_rows(lane, ca, cb);
 
     for (int t = 0; t < 8; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
     if (lane < 3) ws[W_PHI + (lane == 0 ? 0 : (lane == 1 ? 1 : 29))] = (lane == 0) ? 1.0 : 0.0;   // psi_0 = 1, padding slots 0
@@ -742,6 +549,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
     if (lu && g < 6) p_zt = ztar[g];
     __syncwarp();
 
+    PH_DECL;
     for (int t = 0; t <= N; ++t) {
         const bool last = (t == N);
         double u = 0.0, du = 0.0;
@@ -763,6 +571,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
                 if (g < M) tr.u[t * M + g] = u;
             }
         }
+        PH(0);
         const double zt_now = p_zt;
         if (t + 1 <= N) {
             if (t + 1 < N && g < M) {
@@ -777,7 +586,9 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
             if (lu && g < 6) p_zt = ztar[(t + 1) * 6 + g];
         }
         // model at x_t
-        const double val = ssm_eval_lean(c, sc, AC, AUX, s_aux, d0, d1, tr.H + (long long)t * 36);
+        PH(1);
+        const double val = ssm_eval_lean<CR>(c, sc, ca, cb, AC, AUX, s_aux, d0, d1, tr.H + (long long)t * 36);
+        PH(2);
         double e = 0.0;
         if (lu && g < 6) {
             e = __dsub_rn(__dadd_rn(val, zr), zt_now);
@@ -808,6 +619,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
         }
         if (lu) cacc = fma(fr.c1, du, fma(fq.c0, e, cacc));
         double xn = 0.0;
+        PH(3);
         if (IMPL) {
             // discretisation (ssm.py:279-301): inv(I - h A_c) and inv(A_c), one row per lane
             {
@@ -821,6 +633,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
                 gj6_rows(row, lane, (lane & 16) ? IA : (DISCR == SRCB200_DISCR_BE ? AD : W0));
             }
             __syncwarp();
+            PH(4);
             if (DISCR == SRCB200_DISCR_BIL) {
                 // A_d = (I + h A_c) inv(I - h A_c)
                 Frag f{0.0, 0.0};
@@ -847,6 +660,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
             if (g < 6 && q < 3)
                 *reinterpret_cast<double2*>(tr.A + (long long)t * 36 + g * 6 + 2 * q) = *reinterpret_cast<const double2*>(AD + g * LD + 2 * q);
             __syncwarp();
+            PH(5);
             // B_d = sep B_r ; d_d = sep d_c ; x_{t+1} = (A_d x + B_d u) + d_d with B_d u = sep (B_r u)   (ssm.py:330-333)
             const double sa0 = SP[g * LD + q], sa1 = SP[g * LD + 4 + q];
             Frag bd{0.0, 0.0}, sv{0.0, 0.0}, ax{0.0, 0.0};
@@ -880,6 +694,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
         }
         up = u;
         __syncwarp();
+        PH(6);
     }
     // cost = sum over the input / output lanes of their quadratic terms, halved (every term of ilqr.py:164-175 carries 1/2)
     if (!lu) cacc = 0.0;
@@ -889,15 +704,15 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
     return __dmul_rn(0.5, cacc);
 }
 
-template <int M>
+template <int M, bool CR>
 __device__ __forceinline__ double fwd_dispatch(const Ctx c, const IlqrArgs& a, int discr, const double* nx, const double* nu,
                                                double alpha, const double* K, const double* k, const Rec tr,
                                                const double* __restrict__ ztar, const double* __restrict__ ulast) {
     switch (discr) {
-        case SRCB200_DISCR_BE:  return fwd_lean<M, SRCB200_DISCR_BE>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
-        case SRCB200_DISCR_BIL: return fwd_lean<M, SRCB200_DISCR_BIL>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
-        case SRCB200_DISCR_FE:  return fwd_lean<M, SRCB200_DISCR_FE>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
-        default:                return fwd_lean<M, SRCB200_DISCR_NONE>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
+        case SRCB200_DISCR_BE:  return fwd_lean<M, SRCB200_DISCR_BE, CR>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
+        case SRCB200_DISCR_BIL: return fwd_lean<M, SRCB200_DISCR_BIL, CR>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
+        case SRCB200_DISCR_FE:  return fwd_lean<M, SRCB200_DISCR_FE, CR>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
+        default:                return fwd_lean<M, SRCB200_DISCR_NONE, CR>(c, a, nx, nu, alpha, K, k, tr, ztar, ulast);
     }
 }
 
@@ -909,12 +724,9 @@ struct BwdResult { double rho, drho; int pd_fail; };   // pd_fail: horizon index
 #define LOAD_STEP(tt)                                                                                        \
     do {                                                                                                     \
         const long long t36 = (long long)(tt) * 36, tB = (long long)(tt) * 6 * M;                            \
-        pa0 = rc.A[t36 + lane];                                                                              \
-        ph0 = rc.H[t36 + lane];                                                                              \
-        pa1 = rc.A[t36 + 32 + (lane & 3)];                                                                   \
-        ph1 = rc.H[t36 + 32 + (lane & 3)];                                                                   \
-        pb0 = rc.B[tB + (lane < 6 * M ? lane : 0)];                                                          \
-        pb1 = rc.B[tB + (32 + lane < 6 * M ? 32 + lane : 0)];                                                \
+        pa = *reinterpret_cast<const double2*>(rc.A + t36 + oA);                                             \
+        ph = *reinterpret_cast<const double2*>(rc.H + t36 + oA);                                             \
+        pb = *reinterpret_cast<const double2*>(rc.B + tB + oB);                                              \
         pe = rc.e[(tt) * 6 + (lane < 6 ? lane : 0)];                                                         \
         pu = rc.u[(tt) * M + (lane & (M - 1))];                                                              \
         pup = ((tt) == 0) ? (ulast ? ulast[lane & (M - 1)] : 0.0) : rc.u[((tt) - 1) * M + (lane & (M - 1))]; \
@@ -925,20 +737,39 @@ struct BwdResult { double rho, drho; int pd_fail; };   // pd_fail: horizon index
 // (same elimination, the product with the identity block is skipped).  Writes -(X) = (K | k) into `out`.
 template <int M>
 __device__ __forceinline__ bool gj_solve_spd(const double* __restrict__ quut, const double* __restrict__ rhs,
-                                             double* __restrict__ out, int lane) {
+                                             double* __restrict__ out, double* bc, int lane) {
     double col[M];
     const int j = lane;
+    // lanes < M: columns of Q_uu~ ; lanes M .. M+6: columns of the right-hand side ; the rest: its zero column 7
+    const double* src = (j < M) ? quut + j : rhs + (j - M < 7 ? j - M : 7);
 #pragma unroll
-    for (int r = 0; r < M; ++r) col[r] = (j < M) ? quut[r * LD + j] : ((j < M + 7) ? rhs[r * LD + (j - M)] : 0.0);
+    for (int r = 0; r < M; ++r) col[r] = src[r * LD];
     bool pd = true;
 #pragma unroll
     for (int c = 0; c < M; ++c) {
+#if SRCB_GAIN_SHFL
         double cc[M];
 #pragma unroll
         for (int r = 0; r < M; ++r) cc[r] = __shfl_sync(FULL, col[r], c);
+#else
+        // column c (the multipliers of this step) goes through shared memory: 4 stores + 4 broadcast loads instead
+        // of 16 shuffles; two alternating buffers, so one __syncwarp per step orders everything
+        double* buf = bc + 8 * (c & 1);
+        if (j == c) {
+#pragma unroll
+            for (int r = 0; r < M; r += 2) *reinterpret_cast<double2*>(buf + r) = make_double2(col[r], col[r + 1]);
+        }
+        __syncwarp();
+        double cc[M];
+#pragma unroll
+        for (int r = 0; r < M; r += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(buf + r);
+            cc[r] = v.x; cc[r + 1] = v.y;
+        }
+#endif
         const double piv = cc[c];
         pd = pd && (piv > 0.0) && !isinf(piv);
-        const double pc = __dmul_rn(col[c], __drcp_rn(piv));
+        const double pc = __dmul_rn(col[c], rcp_fast(piv));
 #pragma unroll
         for (int r = 0; r < M; ++r) col[r] = (r == c) ? pc : fma(-cc[r], pc, col[r]);
     }
@@ -979,11 +810,13 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
     const srcb200_ilqr_config& cf = a.cfg;
     const bool sreg = cf.regularize && cf.state_regularization;
     const bool inc = cf.include_input_var_constraint != 0;
-    const int bo0 = (lane / M) * LD + lane % M;
-    const int bo1 = ((32 + lane) / M) * LD + (32 + lane) % M;
-    const int ko0 = (lane / 6) * LD + lane % 6, ko1 = ((32 + lane) / 6) * LD + (32 + lane) % 6;   // K elements lane, 32+lane
+    // records move as 16-byte pieces in C-fragment coordinates: lane (g, q) owns columns 2q, 2q+1 of row g
+    const bool vA = (g < 6 && q < 3), vB = (g < 6 && 2 * q < M), vK = (g < M && q < 3);
+    const int oA = vA ? g * 6 + 2 * q : 0, oB = vB ? g * M + 2 * q : 0, oT = g * LD + 2 * q;
+    double* BC = ws + W_PV;                            // 2 x 2 x 8 doubles: pivot-column broadcast of the gain solve
     int pd_fail = -1;
-    double pa0, pa1, ph0, ph1, pb0, pb1, pe, pu, pup;   // record of the next step to process, in registers
+    double2 pa, ph, pb;                                // record of the next step to process, in registers
+    double pe, pu, pup;
 
     {
         for (int t = 0; t < NTILES; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
@@ -1008,17 +841,19 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
         if (lane == 0) A[6 * LD + 6] = 1.0;
         __syncwarp();
 
+        PH_DECL;
         for (int t = N - 1; t >= 0; --t) {
             // ---- level 0: stage A_t, B_t, (H_t | e_t), du from the prefetched registers; fetch step t-1
-            A[c.off0] = pa0;
-            H[c.off0] = ph0;
-            if (lane < 4) { A[c.off1] = pa1; H[c.off1] = ph1; }
-            if (lane < 6 * M) B[bo0] = pb0;
-            if (32 + lane < 6 * M) B[bo1] = pb1;
+            if (vA) {
+                *reinterpret_cast<double2*>(A + oT) = pa;
+                *reinterpret_cast<double2*>(H + oT) = ph;
+            }
+            if (vB) *reinterpret_cast<double2*>(B + oT) = pb;
             if (lane < 6) H[lane * LD + 6] = pe;   // rows 6,7 / column 7 of this tile never reach rows<6, cols<7
             if (lane < M) DU[lane] = inc ? __dsub_rn(pu, pup) : pu;
             if (t > 0) LOAD_STEP(t - 1);
             __syncwarp();
+            PH(8);
             // ---- level 1: W = (H|e)^T Q, A'^T (P|p), B^T (P|p), B^T (P + rho I), c_u = R du
             {
                 Frag w{0.0, 0.0}, atp{0.0, 0.0}, btp{0.0, 0.0}, btpr{0.0, 0.0};
@@ -1047,6 +882,7 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
                 if (sreg) store_frag(BTPR, btpr, g, q);
             }
             __syncwarp();
+            PH(9);
             // ---- level 2: (Q_xx|Q_x), Q_uu, (Q_ux|Q_u), Q_uu~, Q_ux~                 (ilqr.py:258-274)
             Frag qxx{0.0, 0.0};
             {
@@ -1081,8 +917,9 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
                 store_frag(RHS, quxt, g, q);                           // P is dead until level 5
             }
             __syncwarp();
+            PH(10);
             // ---- level 3: PD test + gains (K | k) = -Q_uu~^-1 (Q_ux~ | Q_u)         (ilqr.py:276-292)
-            const bool pd = gj_solve_spd<M>(QT, RHS, KT, lane);
+            const bool pd = gj_solve_spd<M>(QT, RHS, KT, BC, lane);
             if (!pd && pd_fail < 0) pd_fail = t;
             if (!pd && cf.regularize) {
                 // ilqr.py:282-287: raise rho and LEAVE the sweep -- the reference then falls through to the decrease
@@ -1109,16 +946,17 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
                 break;
             }
             __syncwarp();
+            PH(11);
             // ---- level 4: K^T Q_uu ; gains to global
             {
                 Frag kq{0.0, 0.0};
                 mma88<true, false>(kq, KT, QUU, g, q);
-                if (lane < 6 * M) Kout[(long long)t * M * 6 + lane] = KT[ko0];
-                if (32 + lane < 6 * M) Kout[(long long)t * M * 6 + 32 + lane] = KT[ko1];
+                if (vK) *reinterpret_cast<double2*>(Kout + (long long)t * M * 6 + g * 6 + 2 * q) = *reinterpret_cast<const double2*>(KT + oT);
                 if (lane < M) kout[t * M + lane] = KT[lane * LD + 6];
                 store_frag(KQ, kq, g, q);
             }
             __syncwarp();
+            PH(12);
             // ---- level 5: (P | p) = (((Q_xx|Q_x) + KQ (K|k)) + K^T (Q_ux|Q_u)) + Q_ux^T (K|k)   (ilqr.py:294-295)
             mma88<false, false>(qxx, KQ, KT, g, q);
             mma88<true, false>(qxx, KT, QUX, g, q);
@@ -1140,6 +978,7 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
             if (q == 3) qxx.c1 = 0.0;
             __syncwarp();                       // every lane has read the right-hand side held in P's tile
             store_frag(P, qxx, g, q);
+            PH(13);
             // the (K | k) tile is W next step: its column 7 must be zero again, rows >= M too (they are: K rows >= M = 0)
         }
         rho_update(cf, false, rho, drho);         // ilqr.py:298 -- after a complete AND after an interrupted sweep
@@ -1182,8 +1021,8 @@ __device__ __forceinline__ void queue_push(int* q, int cap, int lane, int id, in
     if (lane == 0) push_one(q, cap, id, cls);
 }
 
-template <int M>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+template <int M, bool CR>
+__global__ void __launch_bounds__(WARPS * 32, CR ? 1 : 2)
 ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__ IlqrArgs a) {
     build_tables(Mdl, a.Q, a.R, a.Qf, g_sm, M);
     Ctx c;
@@ -1225,7 +1064,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
             for (int e = lane; e < N * M; e += 32) nom.u[e] = a.u_init ? a.u_init[b * (long long)N * M + e] : 0.0;
             __syncwarp();
             __threadfence_block();
-            cost = fwd_dispatch<M>(c, a, discr, nom.x, nom.u, 1.0, nullptr, nullptr, tr0, ztar, ulast);
+            cost = fwd_dispatch<M, CR>(c, a, discr, nom.x, nom.u, 1.0, nullptr, nullptr, tr0, ztar, ulast);
             if (a.ocost0 && lane == 0) a.ocost0[b] = cost;
             // priority class: initial cost above the running mean of the batch -> expected to need many iterations
             cls = 1;
@@ -1252,7 +1091,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
                 double cost_t = cost, alpha_acc = 0.0;
                 while (!improved && !failed) {
                     improved = true;
-                    cost_t = fwd_dispatch<M>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
+                    cost_t = fwd_dispatch<M, CR>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
                     ++trials;
                     double dc = 0.0;
                     const double a2 = __dmul_rn(__dmul_rn(alpha, alpha), 0.5);
@@ -1326,7 +1165,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
 // Open-loop rollout (ssm.py:134-156) for the same model shape: one warp per trajectory, re-linearised every step.
 // ---------------------------------------------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+__global__ void __launch_bounds__(WARPS * 32, 1)
 ssm_rollout_fast_kernel(const __grid_constant__ SsmDev Mdl, long long batch, int N, const double* __restrict__ x0,
                         const double* __restrict__ u, double dt, double* __restrict__ xo, double* __restrict__ zo) {
     build_tables(Mdl, nullptr, nullptr, nullptr, g_sm, M);
@@ -1709,7 +1548,7 @@ int ssm_rollout_fast_launch(const SsmDev& M, long long batch, int N, const doubl
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ctas = (batch + fast::WARPS - 1) / fast::WARPS;
-    const int grid = (int)(ctas < 2LL * sms ? ctas : 2LL * sms);
+    const int grid = (int)(ctas < (long long)sms ? ctas : (long long)sms);
     if (M.m == 8) {
         SRCB_CUDA(cudaFuncSetAttribute(fast::ssm_rollout_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
         fast::ssm_rollout_fast_kernel<8><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, batch, N, x0, u, dt, x, z);
@@ -1723,6 +1562,15 @@ int ssm_rollout_fast_launch(const SsmDev& M, long long batch, int N, const doubl
 }
 
 
+#ifdef SRCB_PHASE_TIMING
+extern "C" int srcb200_debug_phase(unsigned long long* host32, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host32, fast::g_phase, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(fast::g_phase, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 // Dispatch: Gauss-Newton SSM problems with the Trunk/Diamond shape go to the specialised kernel.
 int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bool* handled) {
     *handled = false;
@@ -1733,19 +1581,27 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long ctas = (a.batch + fast::WARPS - 1) / fast::WARPS;
-    int grid = (int)(ctas < 2LL * sms ? ctas : 2LL * sms);   // persistent: 2 CTAs (16 warps) per SM
+    // Persistent launch.  Default shape: two CTAs of 8 warps per SM, 128 registers, Jacobian table in shared memory
+    // (90.5 k solves/s on the 4096-problem benchmark); SRCB200_ILQR_SHAPE=0 selects one CTA per SM with the table rows in
+    // registers (255 registers; 84.4 k: each warp is 1.8 x faster but half as many run).  Small batches are spread over the
+    // SMs: the task queue feeds any number of warps.
+    const char* shp = getenv("SRCB200_ILQR_SHAPE");
+    const bool cr = (shp && shp[0] == '0');
+    const long long slots = (long long)sms * (cr ? 1 : 2);
+    int grid = (int)(a.batch < slots ? a.batch : slots);
     if (grid * fast::WARPS > kIlqrQueueWaiters) grid = kIlqrQueueWaiters / fast::WARPS;
     ilqrq::queue_init_kernel<<<(a.queue_cap + 255) / 256, 256, 0, st>>>(a.work_counter, a.queue_cap, (int)a.batch, a.ws,
                                                                                  a.L.total, a.L.state);
     SRCB_LAUNCH_CHECK("ilqr_queue_init_kernel");
-    if (M.m == 8) {
-        SRCB_CUDA(cudaFuncSetAttribute(fast::ilqr_ssm_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
-        fast::ilqr_ssm_fast_kernel<8><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, a);
-    } else {
-        SRCB_CUDA(cudaFuncSetAttribute(fast::ilqr_ssm_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
-        fast::ilqr_ssm_fast_kernel<4><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, a);
-    }
+#define SRCB_LAUNCH_SHAPE(MM, CRR)                                                                                         \
+    do {                                                                                                                   \
+        SRCB_CUDA(cudaFuncSetAttribute(fast::ilqr_ssm_fast_kernel<MM, CRR>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                       (int)fast::SMEM_BYTES));                                                            \
+        fast::ilqr_ssm_fast_kernel<MM, CRR><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, a);                       \
+    } while (0)
+    if (M.m == 8) { if (cr) SRCB_LAUNCH_SHAPE(8, true); else SRCB_LAUNCH_SHAPE(8, false); }
+    else          { if (cr) SRCB_LAUNCH_SHAPE(4, true); else SRCB_LAUNCH_SHAPE(4, false); }
+#undef SRCB_LAUNCH_SHAPE
     SRCB_LAUNCH_CHECK("ilqr_ssm_fast_kernel");
     *handled = true;
     return 0;

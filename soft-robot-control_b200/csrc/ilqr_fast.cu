@@ -424,7 +424,7 @@ __device__ __forceinline__ void load_coeff_rows(int lane, double (&ca)[NCR], dou
     for (int s = 1; s < NCR; ++s) { ca[s] = t0[s + 1]; cb[s] = t1[s + 1]; }
 }
 
-template <bool CR>
+template <int CR>
 __device__ __forceinline__ double ssm_eval_lean(const Ctx c, const Scatter sc, const double (&ca)[NCR],
                                                 const double (&cb)[NCR], double* __restrict__ AC,
                                                 double* __restrict__ AUX, double s_aux, double d0, double d1,
@@ -445,8 +445,8 @@ __device__ __forceinline__ double ssm_eval_lean(const Ctx c, const Scatter sc, c
     const double* t2 = CTX_SH + SH_T + (lane < 8 ? 64 + lane : 72) * TS;   // lanes >= 8: the zero row (one broadcast read)
     const double* t0 = CTX_SH + SH_T + lane * TS;
     const double* t1 = CTX_SH + SH_T + (32 + lane) * TS;
-#define CA(s) (CR ? ca[s] : t0[(s) == 0 ? 0 : (s) + 1])
-#define CB(s) (CR ? cb[s] : t1[(s) == 0 ? 0 : (s) + 1])
+#define CA(s) (CR >= 1 ? ca[s] : t0[(s) == 0 ? 0 : (s) + 1])
+#define CB(s) (CR >= 2 ? cb[s] : t1[(s) == 0 ? 0 : (s) + 1])
     const double g10 = CA(0), g11 = CB(0), g12 = t2[0];
     // degree 2: table slots 2..7 (even / odd accumulators)
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
@@ -499,7 +499,7 @@ __device__ __forceinline__ double ssm_eval_lean(const Ctx c, const Scatter sc, c
     return val;
 }
 
-template <int M, int DISCR, bool CR>
+template <int M, int DISCR, int CR>
 __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const double* nx, const double* nu,
                                         double alpha, const double* K, const double* k, const Rec tr,
                                         const double* __restrict__ ztar, const double* __restrict__ ulast) {
@@ -532,7 +532,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
     const bool dg0 = (q == g), dg1 = (4 + q == g) && (g < 6);   // diagonal flags of the B fragment (k = q / 4 + q, n = g)
     double cacc = 0.0;
     double ca[NCR], cb[NCR];
-    if (CR) load_coeff_rows(lane, ca, cb);
+    if (CR >= 1) load_coeff_rows(lane, ca, cb);
 
     for (int t = 0; t < 8; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
     if (lane < 3) ws[W_PHI + (lane == 0 ? 0 : (lane == 1 ? 1 : 29))] = (lane == 0) ? 1.0 : 0.0;   // psi_0 = 1, padding slots 0
@@ -704,7 +704,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
     return __dmul_rn(0.5, cacc);
 }
 
-template <int M, bool CR>
+template <int M, int CR>
 __device__ __forceinline__ double fwd_dispatch(const Ctx c, const IlqrArgs& a, int discr, const double* nx, const double* nu,
                                                double alpha, const double* K, const double* k, const Rec tr,
                                                const double* __restrict__ ztar, const double* __restrict__ ulast) {
@@ -1021,8 +1021,9 @@ __device__ __forceinline__ void queue_push(int* q, int cap, int lane, int id, in
     if (lane == 0) push_one(q, cap, id, cls);
 }
 
-template <int M, bool CR>
-__global__ void __launch_bounds__(WARPS * 32, CR ? 1 : 2)
+constexpr int shape_warps(int cr) { return cr == 1 ? 12 : 8; }
+template <int M, int CR>
+__global__ void __launch_bounds__(shape_warps(CR) * 32, CR == 0 ? 2 : 1)
 ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__ IlqrArgs a) {
     build_tables(Mdl, a.Q, a.R, a.Qf, g_sm, M);
     Ctx c;
@@ -1581,26 +1582,28 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // Persistent launch.  Default shape: two CTAs of 8 warps per SM, 128 registers, Jacobian table in shared memory
-    // (90.5 k solves/s on the 4096-problem benchmark); SRCB200_ILQR_SHAPE=0 selects one CTA per SM with the table rows in
-    // registers (255 registers; 84.4 k: each warp is 1.8 x faster but half as many run).  Small batches are spread over the
-    // SMs: the task queue feeds any number of warps.
+    // Persistent launch, three shapes (SRCB200_ILQR_SHAPE): 0 (default) two CTAs of 8 warps per SM, 128 registers, Jacobian
+    // table read from shared memory; 1: one CTA of 12 warps, 168 registers, table row `lane` in registers; 2: one CTA of
+    // 8 warps, 255 registers, rows `lane` and `32 + lane` in registers (each warp ~1.8 x faster, half as many run).  Small
+    // batches are spread over the SMs: the task queue feeds any number of warps.
     const char* shp = getenv("SRCB200_ILQR_SHAPE");
-    const bool cr = (shp && shp[0] == '0');
-    const long long slots = (long long)sms * (cr ? 1 : 2);
+    const int cr = (shp && shp[0] >= '0' && shp[0] <= '2') ? shp[0] - '0' : 0;
+    const int nw = fast::shape_warps(cr);
+    const size_t smem = sizeof(double) * (fast::SH_END + nw * fast::W_SIZE);
+    const long long slots = (long long)sms * (cr == 0 ? 2 : 1);
     int grid = (int)(a.batch < slots ? a.batch : slots);
-    if (grid * fast::WARPS > kIlqrQueueWaiters) grid = kIlqrQueueWaiters / fast::WARPS;
+    if (grid * nw > kIlqrQueueWaiters) grid = kIlqrQueueWaiters / nw;
     ilqrq::queue_init_kernel<<<(a.queue_cap + 255) / 256, 256, 0, st>>>(a.work_counter, a.queue_cap, (int)a.batch, a.ws,
                                                                                  a.L.total, a.L.state);
     SRCB_LAUNCH_CHECK("ilqr_queue_init_kernel");
 #define SRCB_LAUNCH_SHAPE(MM, CRR)                                                                                         \
     do {                                                                                                                   \
         SRCB_CUDA(cudaFuncSetAttribute(fast::ilqr_ssm_fast_kernel<MM, CRR>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                       (int)fast::SMEM_BYTES));                                                            \
-        fast::ilqr_ssm_fast_kernel<MM, CRR><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, a);                       \
+                                       (int)smem));                                                                        \
+        fast::ilqr_ssm_fast_kernel<MM, CRR><<<grid, nw * 32, smem, st>>>(M, a);                                            \
     } while (0)
-    if (M.m == 8) { if (cr) SRCB_LAUNCH_SHAPE(8, true); else SRCB_LAUNCH_SHAPE(8, false); }
-    else          { if (cr) SRCB_LAUNCH_SHAPE(4, true); else SRCB_LAUNCH_SHAPE(4, false); }
+    if (M.m == 8) { if (cr == 0) SRCB_LAUNCH_SHAPE(8, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(8, 1); else SRCB_LAUNCH_SHAPE(8, 2); }
+    else          { if (cr == 0) SRCB_LAUNCH_SHAPE(4, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(4, 1); else SRCB_LAUNCH_SHAPE(4, 2); }
 #undef SRCB_LAUNCH_SHAPE
     SRCB_LAUNCH_CHECK("ilqr_ssm_fast_kernel");
     *handled = true;

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SRCB200_ABI_VERSION 2
+#define SRCB200_ABI_VERSION 3
 
 /* error codes (<0) */
 #define SRCB200_E_NULL        (-1)  /* required pointer is NULL */
@@ -266,6 +266,14 @@ int srcb200_pod_gram(int64_t nf, int64_t ns, const double* X, int64_t ldx, doubl
  * bank blend  W (batch x P) * bank (P x (n*n+n*m+n))  (tpwl.py:246-248).  transA != 0 uses A^T (A is K x M). */
 int srcb200_dgemm(int32_t transA, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                   const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+
+/* Eigen-decomposition of a small symmetric positive semi-definite matrix A (n x n, n <= 160, row-major, lda) by
+ * one-sided Jacobi in one CTA: evals (n, descending), V (n x n, row-major, ldv, column j = eigenvector j).  The
+ * Rayleigh-Ritz / orthonormalisation step of the leading-eigenpair solver on the snapshot Gram matrix that replaces
+ * the full np.linalg.svd of compute_POD (pod.py:191-199: only the modes the energy rule keeps are needed, and
+ * sum(S^2) = trace(G)).  info (device int, may be NULL): sweeps used, -1 if the sweep limit was hit. */
+int srcb200_sym_eig_psd(int32_t n, const double* A, int64_t lda, double* evals, double* V, int64_t ldv,
+                        int32_t* info, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Callers either side of the hot path, batched.  All matrices row-major, device pointers.

@@ -17,7 +17,7 @@ DISCR = {'fe': 0, 'be': 1, 'bil': 2, 'zoh': 3, 'none': 4}
 TPWL_METHOD = {'nn': 0, 'weighting': 1}
 E_NULL, E_DIM, E_METHOD, E_WORKSPACE, E_NOGPU = -1, -2, -3, -4, -5
 ILQR_MODEL_SSM, ILQR_MODEL_TPWL = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 ST_CONVERGED, ST_MAXITER, ST_ABANDONED, ST_NONPD, ST_NONFINITE = 1, 2, 4, 8, 16
 SSM_MAX_ORDER = 4
 
@@ -94,6 +94,7 @@ _SIGS = {
                                              c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                              c_dp, C.c_size_t, c_dp]),
     "srcb200_pod_gram": (C.c_int, [C.c_int64, C.c_int64, c_dp, C.c_int64, c_dp, C.c_int64, C.c_int32, c_dp]),
+    "srcb200_sym_eig_psd": (C.c_int, [C.c_int32, c_dp, C.c_int64, c_dp, c_dp, C.c_int64, c_dp, c_dp]),
     "srcb200_dgemm": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_dp, C.c_int64, c_dp,
                                 C.c_int64, c_dp, C.c_int64, c_dp]),
     "srcb200_ekf_predict_batch": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,

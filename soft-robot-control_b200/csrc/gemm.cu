@@ -70,7 +70,7 @@ template <bool TRANSA, bool SYRK, bool ALIGN16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dgemm_kernel(long long M, long long N, long long K, double alpha, const double* __restrict__ A, long long lda,
              const double* __restrict__ B, long long ldb, double* __restrict__ C, long long ldc, int accumulate,
-             int tiles_m, int tiles_n, long long num_tiles) {
+             int tiles_m, int tiles_n, long long num_tiles, int sb) {
     extern __shared__ __align__(16) double gsm[];
     double* sA = gsm;
     double* sB = gsm + STAGES * A_TILE;
@@ -82,15 +82,47 @@ dgemm_kernel(long long M, long long N, long long K, double alpha, const double* 
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int tm, tn;
         if (SYRK) {
-            // enumerate the upper triangle (tn >= tm) row by row
+            // Upper triangle (tn >= tm), enumerated SUPER-BLOCK by super-block: sb x sb tiles with sb ~ sqrt(grid), so
+            // the ~148 tiles in flight share 2 sb column panels of X instead of (1 + 148): every CTA walks K at the
+            // same pace, a panel chunk is fetched from DRAM once per super-block and served to its sb users by L2.
+            // (Row-by-row enumeration re-read all of X once per wave: 16 x the algorithmic bytes at ns = 8192.)
+            const int nsb = (tiles_m + sb - 1) / sb;
             long long t = tile;
-            tm = 0;
-            int rowlen = tiles_n;
-            while (t >= rowlen) { t -= rowlen; ++tm; --rowlen; }
-            tn = tm + (int)t;
+            tm = tn = 0;
+            bool found = false;
+            for (int I = 0; I < nsb && !found; ++I) {
+                const int r0 = I * sb, h = min(sb, tiles_m - r0);
+                for (int J = I; J < nsb; ++J) {
+                    const int c0 = J * sb, w = min(sb, tiles_m - c0);
+                    const long long cnt = (J == I) ? (long long)h * (h + 1) / 2 : (long long)h * w;
+                    if (t < cnt) {
+                        if (J == I) {
+                            int rr = 0, rowlen = h;
+                            while (t >= rowlen) { t -= rowlen; ++rr; --rowlen; }
+                            tm = r0 + rr; tn = r0 + rr + (int)t;
+                        } else {
+                            tm = r0 + (int)(t / w); tn = c0 + (int)(t % w);
+                        }
+                        found = true;
+                        break;
+                    }
+                    t -= cnt;
+                }
+            }
         } else {
-            tm = (int)(tile / tiles_n);
-            tn = (int)(tile % tiles_n);
+            // same idea for the rectangular tile grid: sb x sb super-blocks, row-major inside
+            const int nsbn = (tiles_n + sb - 1) / sb;
+            const long long per_row = (long long)sb * tiles_n;               // tiles of one full super-block row
+            const int I = (int)(tile / per_row);
+            const int r0 = I * sb, h = min(sb, tiles_m - r0);
+            long long t = tile - (long long)I * per_row;                     // index inside super-block row I (h rows)
+            const long long per_blk = (long long)h * sb;
+            int J = (int)(t / per_blk);
+            if (J >= nsbn) J = nsbn - 1;
+            t -= (long long)J * per_blk;
+            const int c0 = J * sb, w = min(sb, tiles_n - c0);
+            tm = r0 + (int)(t / w);
+            tn = c0 + (int)(t % w);
         }
         const long long m0 = (long long)tm * BM, n0 = (long long)tn * BN;
 
@@ -182,16 +214,18 @@ static int launch_gemm(long long M, long long N, long long K, double alpha, cons
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)(num_tiles < sms ? num_tiles : sms);   // persistent: one CTA per SM walks the tile list
+    int sb = 1;
+    while ((sb + 1) * (sb + 1) <= grid) ++sb;                    // super-block edge of the SYRK walk
     if (al) {
         auto kern = dgemm_kernel<TRANSA, SYRK, true>;
         SRCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, C, ldc, accumulate, tiles_m,
-                                                    tiles_n, num_tiles);
+                                                    tiles_n, num_tiles, sb);
     } else {
         auto kern = dgemm_kernel<TRANSA, SYRK, false>;
         SRCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, C, ldc, accumulate, tiles_m,
-                                                    tiles_n, num_tiles);
+                                                    tiles_n, num_tiles, sb);
     }
     SRCB_LAUNCH_CHECK("dgemm_kernel");
     return 0;

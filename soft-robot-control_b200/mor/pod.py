@@ -1,16 +1,20 @@
 """POD on B200 -- drop-in for sofacontrol/mor/pod.py (POD, compute_POD, run_POD, load_POD, pod_config).
 
 compute_POD replaces np.linalg.svd of the (nf x ns) snapshot matrix (pod.py:191) by the Gram route:
-    G = X^T X  (ns x ns)            FP64 tensor-core (DMMA) SYRK kernel, csrc/gemm.cu  [+ NCCL allreduce when the
+    G = X^T X  (ns x ns)            FP64 tensor-core (DMMA) SYRK kernel, csrc/gemm.cu  [+ NCCL all-reduce when the
                                      rows (DOFs) of X are sharded across GPUs, see compute_POD_sharded]
-    G = V diag(S^2) V^T             symmetric eigen-decomposition of the small Gram matrix on the device
+    leading eigenpairs of G         block subspace iteration + Rayleigh-Ritz on this repo's DMMA GEMM and one-CTA
+                                     Jacobi kernel (mor/eig.py, csrc/eig.cu) -- the energy rule only needs the kept
+                                     modes and sum(S^2) = trace(G), not the full spectrum
     U = X V S^-1                    FP64 DMMA GEMM kernel
 followed by the reference's energy truncation rule (pod.py:193-199).  Singular values below ~sqrt(eps)*S_max are
 not resolved by the Gram route (the condition number is squared); the leading modes that the energy rule keeps
 are, to a subspace angle < 1e-8 (tests/test_pod_gpu.py).
 
-The eigen-decomposition of the ns x ns Gram matrix is delegated to torch.linalg.eigh (cuSOLVER) -- a library
-call outside the hot contraction, recorded as such in DESIGN.md.
+Return-value note: the reference returns every left singular vector / singular value (U_full, Sigma of length
+min(nf, ns)); here U_full / Sigma hold the leading block the solver resolved (>= nbModes + 4 modes, 64 by default).
+`compute_POD(..., full_spectrum=True)` returns all of them through torch.linalg.eigh (cuSOLVER) -- an explicit
+opt-in library call that nothing else in this package uses.
 """
 import os
 
@@ -53,55 +57,79 @@ def energy_mode_count_device(s2, tol):
     return int(idx[0].item()) + 1 if idx.numel() else int(s2.numel())
 
 
-def _finish_pod(Xd, G, tol, full_U, gemm=None):
-    torch = L.torch_mod()
-    lam, V = torch.linalg.eigh(G)                # ascending
-    lam = torch.flip(lam, (0,)).clamp_min(0.0)
-    V = torch.flip(V, (1,)).contiguous()
-    S = torch.sqrt(lam)
-    nb = energy_mode_count_device(lam, tol)
+def _finish_pod(Xd, G, tol, full_U, gemm=None, ops=None):
+    """Leading eigenpairs of the (replicated) Gram matrix -> U = X V S^-1 for the kept modes (full_U: for every mode
+    of the resolved block).  Returns (U, nbModes, S)."""
+    from . import eig
+    lam, V, nb, _ = eig.leading_eigenpairs(G, tol, ops=ops)
+    lam = lam.clamp_min(0.0)
+    S = lam.sqrt()
     keep = V.shape[1] if full_U else nb
-    Vs = (V[:, :keep] / S[:keep].clamp_min(np.finfo(np.float64).tiny)).contiguous()
+    # unresolved directions (S below the Gram route's sqrt(eps) floor) are returned as zero columns, never inf / nan
+    ok = S[:keep] > 1e-7 * S[0]
+    Vs = (V[:, :keep] * (ok / S[:keep].clamp_min(np.finfo(np.float64).tiny))).contiguous()
     U = (gemm or dgemm_device)(Xd, Vs)           # (nf, keep)
     return U, nb, S
 
 
 def compute_POD_device(Xd, tol, full_U=False):
-    """CUDA tensor X (nf, ns) -> (U (nf, nb or ns), nbModes, S (ns)) as CUDA tensors."""
+    """CUDA tensor X (nf, ns) -> (U (nf, nb or block), nbModes, S (block)) as CUDA tensors."""
     G = gram_device(Xd)
     return _finish_pod(Xd, G, tol, full_U)
 
 
-def compute_POD_sharded(X_local, tol, group=None, gram=None, gemm=None):
-    """Row-sharded POD: every rank holds a block of DOF rows X_g (nf_g x ns).  G = sum_g X_g^T X_g through ONE
-    all-reduce (NCCL over NVLink on GPUs), the small eigen-solve is replicated, U_g = X_g V S^-1 stays row-sharded.
-    Returns (U_local, nbModes, S).  `gram` / `gemm` default to the DMMA kernels; the gloo CPU tests of the
-    multi-process logic inject plain torch stand-ins."""
-    from ..parallel import allreduce_sum_
-    G = (gram or gram_device)(X_local)
-    allreduce_sum_(G, group)
-    return _finish_pod(X_local, G, tol, False, gemm)
+def compute_POD_sharded(X_local, tol, group=None, gram=None, gemm=None, ops=None, chunks=1):
+    """Row-sharded POD: every rank holds a block of DOF rows X_g (nf_g x ns).  G = sum_g X_g^T X_g through an
+    all-reduce (NCCL over NVLink on GPUs), the small leading-eigenpair solve is replicated (deterministic start:
+    every rank gets the same modes), U_g = X_g V S^-1 stays row-sharded.  Returns (U_local, nbModes, S).
+    chunks > 1: the local rows are contracted in `chunks` row slabs and each slab's partial Gram is reduced on a side
+    stream while the next slab computes (parallel.overlapped_gram_allreduce).  `gram` / `gemm` / `ops` default to
+    the DMMA kernels; the gloo CPU tests of the multi-process logic inject plain torch stand-ins."""
+    from ..parallel import allreduce_sum_, overlapped_gram_allreduce
+    if ops is None and (gram is not None or gemm is not None):
+        from . import eig
+        ops = eig.TorchOps()                     # injected stand-ins (CPU tests): the small solves follow suit
+    if chunks > 1 and gram is None:
+        G = overlapped_gram_allreduce(X_local, chunks, group)
+    else:
+        G = (gram or gram_device)(X_local)
+        allreduce_sum_(G, group)
+    return _finish_pod(X_local, G, tol, False, gemm, ops)
 
 
-def compute_POD(snapshots, tol, rom_dim=None):
+def _full_spectrum(G):
+    """Opt-in only: every eigenpair of the Gram matrix through torch.linalg.eigh (cuSOLVER)."""
+    torch = L.torch_mod()
+    lam, V = torch.linalg.eigh(G)                # ascending
+    return torch.flip(lam, (0,)).clamp_min(0.0), torch.flip(V, (1,)).contiguous()
+
+
+def compute_POD(snapshots, tol, rom_dim=None, full_spectrum=False):
     """pod.py:181-200.  snapshots: (nf x num_snapshots) host array.  Returns (U_full, U, nbModes, Sigma) like the
-    reference (rom_dim is ignored there too).  U_full holds the left singular vectors of every resolved mode."""
+    reference (rom_dim is ignored there too).  U_full / Sigma cover the leading block of modes the solver resolved
+    (all min(nf, ns) of them with full_spectrum=True, see the module docstring); U = U_full[:, :nbModes]."""
     L.require_gpu()
+    from . import eig
     Xd = L.to_dev(np.asarray(snapshots, dtype=np.float64))
     nf, ns = Xd.shape
     if nf < ns:
-        # thin SVD has min(nf, ns) modes: work on X X^T instead (same kernel on the transposed matrix)
-        Xt = Xd.t().contiguous()
-        G = gram_device(Xt)                      # (nf x nf) = X X^T
-        torch = L.torch_mod()
-        lam, Uf = torch.linalg.eigh(G)
-        lam = torch.flip(lam, (0,)).clamp_min(0.0)
-        Uf = torch.flip(Uf, (1,)).contiguous()
-        S = torch.sqrt(lam)
-        nb = energy_mode_count_device(lam, tol)
+        # thin SVD has min(nf, ns) modes: work on X X^T instead (same kernel on the transposed matrix); its
+        # eigenvectors ARE the left singular vectors
+        G = gram_device(Xd.t().contiguous())     # (nf x nf) = X X^T
+        lam, Uf = _full_spectrum(G) if full_spectrum else eig.leading_eigenpairs(G, tol)[:2]
+        lam = lam.clamp_min(0.0)
+        nb = eig.energy_mode_count(lam, L.torch_mod().diagonal(G).sum(), tol) or int(lam.numel())
         U_full = L.to_host(Uf)
-        return U_full, U_full[:, 0:nb], nb, L.to_host(S)
-    U, nb, S = compute_POD_device(Xd, tol, full_U=True)
+        return U_full, U_full[:, 0:nb], nb, L.to_host(lam.sqrt())
+    if full_spectrum:
+        G = gram_device(Xd)
+        lam, V = _full_spectrum(G)
+        S = lam.sqrt()
+        nb = energy_mode_count_device(lam, tol)
+        ok = S > 1e-7 * S[0]
+        U = dgemm_device(Xd, (V * (ok / S.clamp_min(np.finfo(np.float64).tiny))).contiguous())
+    else:
+        U, nb, S = compute_POD_device(Xd, tol, full_U=True)
     U_full = L.to_host(U)
     return U_full, U_full[:, 0:nb], nb, L.to_host(S)
 

@@ -59,3 +59,51 @@ def gather_sharded(local, total, group=None):
     outs = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(outs, buf, group=group)
     return torch.cat([o[:s.stop - s.start] for o, s in zip(outs, sizes)], dim=0)
+
+
+def overlapped_gram_allreduce(X_local, nblocks, group=None, block_multiple=128):
+    """G = sum over ranks of X_g^T X_g with the reduction of finished pieces overlapped with the contraction of the
+    next ones: the upper triangle of G is cut into `nblocks` block rows; block row I is one DMMA GEMM
+    X[:, I]^T X[:, I:] into its own contiguous buffer, and as soon as it is done a side stream all-reduces that buffer
+    (NCCL, asynchronous) while the compute stream is already in block row I + 1.  Only the upper triangle crosses
+    NVLink (ns^2 / 2 + diagonal blocks instead of ns^2 doubles); the lower one is mirrored locally at the end.
+    Returns the full symmetric G (ns x ns) on every rank."""
+    import torch
+    import torch.distributed as dist
+    from .mor.pod import dgemm_device
+    from . import _lib as L
+    nf, ns = X_local.shape
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    nblk = max(1, min(int(nblocks), -(-ns // block_multiple)))
+    # equal-AREA block rows of the triangle: row I of height h covers h * (ns - c0) entries
+    edges = [0]
+    area = ns * (ns + 1) / 2.0
+    for i in range(1, nblk):
+        # c with  c * ns - c^2 / 2 = i / nblk * area
+        c = ns - (ns * ns - 2.0 * area * i / nblk) ** 0.5
+        c = int(round(c / block_multiple)) * block_multiple
+        if edges[-1] < c < ns:
+            edges.append(c)
+    edges.append(ns)
+    G = L.empty((ns, ns))
+    cur = torch.cuda.current_stream()
+    comm = torch.cuda.Stream() if multi else None
+    pieces, works = [], []
+    for c0, c1 in zip(edges[:-1], edges[1:]):
+        blk = dgemm_device(X_local[:, c0:c1], X_local[:, c0:], transA=True)       # (c1 - c0) x (ns - c0)
+        pieces.append((c0, c1, blk))
+        if multi:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)
+                works.append(dist.all_reduce(blk, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    if multi:
+        cur.wait_stream(comm)
+    for c0, c1, blk in pieces:
+        G[c0:c1, c0:] = blk
+        if c1 < ns:
+            G[c1:, c0:c1] = blk[:, c1 - c0:].t()
+    return G

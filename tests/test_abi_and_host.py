@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing symbol %s" % n
     assert sorted(_lib.EXPORTED_SYMBOLS) == names          # the ctypes table binds exactly the header's API
-    assert _lib.lib().srcb200_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib().srcb200_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header_sizes():

@@ -40,6 +40,62 @@ def test_gram_vs_numpy(nf, ns):
     assert relerr(G2, 2 * ref) < 1e-12
 
 
+@pytest.mark.parametrize("nf,ns", [(700, 1920), (520, 2500)])
+def test_gram_and_gemm_super_block_tile_walk(nf, ns):
+    """Tile lists longer than one super-block (the SYRK / GEMM kernels enumerate sb x sb blocks of tiles so that the
+    tiles in flight share column panels of X): every tile is still visited exactly once."""
+    from sofacontrol_b200.mor import pod
+    rng = np.random.default_rng(ns)
+    X = rng.normal(size=(nf, ns))
+    ref = X.T @ X
+    G = pod.gram_device(_dev(X)).cpu().numpy()
+    assert np.max(np.abs(G - ref)) <= 1e-12 * np.abs(ref).max() * nf ** 0.5 and np.array_equal(G, G.T)
+    Xd = _dev(X)
+    C = pod.dgemm_device(Xd[:, 128:1024], Xd[:, 128:], transA=True).cpu().numpy()      # strided views, rectangular grid
+    assert np.max(np.abs(C - ref[128:1024, 128:])) <= 1e-12 * np.abs(ref).max() * nf ** 0.5
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 33, 64, 129, 160])
+def test_sym_eig_psd_kernel_vs_numpy(n):
+    """One-CTA Jacobi kernel (csrc/eig.cu): eigenvalues to 1e-13 of the largest, V orthonormal, A V = V diag."""
+    import torch
+    from sofacontrol_b200.mor import eig
+    rng = np.random.default_rng(n)
+    B = rng.normal(size=(n + 3, n)) * 10.0 ** (-4.0 * np.arange(n) / max(n - 1, 1))   # eigenvalues over 8 decades, like a Rayleigh-Ritz block
+    A = B.T @ B
+    ev, V = eig.DeviceOps().eig_psd(_dev(A))
+    ev, V = ev.cpu().numpy(), V.cpu().numpy()
+    ref = np.linalg.eigvalsh(A)[::-1]
+    assert np.all(np.diff(ev) <= 0)
+    assert np.abs(ev - ref).max() <= 1e-13 * ref[0]
+    assert np.abs(V.T @ V - np.eye(n)).max() < 1e-9
+    assert np.abs(A @ V - V * ev).max() <= 1e-12 * ref[0]
+
+
+def test_overlapped_gram_single_process_equals_syrk():
+    from sofacontrol_b200.mor import pod
+    from sofacontrol_b200 import parallel
+    rng = np.random.default_rng(3)
+    X = _dev(rng.normal(size=(900, 1500)))
+    G0 = pod.gram_device(X).cpu().numpy()
+    for nb in (1, 3, 5):
+        G = parallel.overlapped_gram_allreduce(X, nb).cpu().numpy()
+        assert np.abs(G - G0).max() <= 1e-12 * np.abs(G0).max() and np.array_equal(G, G.T)
+
+
+def test_compute_pod_full_spectrum_opt_in():
+    from sofacontrol_b200.mor import pod
+    import sofacontrol_b200.synth as synth
+    from oracle import pod_np
+    X, _, _ = synth.pod_snapshots(800, 300, seed=9)
+    Uf, U, nb, S = pod.compute_POD(X, 5e-5, full_spectrum=True)
+    _, Uo, nbo, So = pod_np.compute_POD(X, 5e-5)
+    assert Uf.shape == (800, 300) and S.shape == (300,) and nb == nbo and np.all(np.isfinite(Uf))
+    assert relerr(S[:nb], So[:nb]) < 1e-9 and pod_np.subspace_angle(Uo, U)[0] < 1e-8
+    Uf2, U2, nb2, S2 = pod.compute_POD(X, 5e-5)                       # default: leading block only
+    assert nb2 == nbo and Uf2.shape[1] == S2.shape[0] >= nb + 4 and pod_np.subspace_angle(Uo, U2)[0] < 1e-8
+
+
 def test_compute_pod_small_golden(golden):
     from sofacontrol_b200.mor import pod
     import sofacontrol_b200.synth as synth

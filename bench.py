@@ -496,53 +496,104 @@ def run_ssm_eval(args, rank, world, dev_index):
                                  "21504 flop (padding 16x84x8); peak = measured cuBLAS DGEMM"}}
 
 
-def run_pod_gram(args, rank, world, dev_index):
-    """Kernel (d): POD Gram X^T X with the rows (DOFs) of X sharded across ranks + ONE NCCL all-reduce of G."""
+def pod_sharded_matrix(nf_local, ns, rank, world, r=192, seed=5):
+    """Row shard of a synthetic snapshot matrix with a PRESCRIBED spectrum: X = A diag(s) B^T
+    with s = synth.pod_spectrum(r) (the Diamond-like decay of the small-scale twin), A (sum_g nf_g x r) orthonormal
+    ACROSS the shards (Cholesky-QR with one r x r all-reduce), B (ns x r) orthonormal and identical on every rank.
+    Generated on the device (torch, untimed: data generation is not the path).  Returns (X_g, s)."""
     import torch
     import torch.distributed as dist
-    from sofacontrol_b200.mor import pod
+    import sofacontrol_b200.synth as synth
+    g = torch.Generator(device="cuda").manual_seed(seed * 1000 + rank)
+    A = torch.randn((nf_local, r), device="cuda", dtype=torch.float64, generator=g)
+    C_ = A.t() @ A
+    if world > 1:
+        dist.all_reduce(C_)
+    A = A @ torch.linalg.inv(torch.linalg.cholesky(C_).t())          # A R^-1 with C = R^T R: orthonormal across shards
+    gb = torch.Generator(device="cuda").manual_seed(seed)
+    B, _ = torch.linalg.qr(torch.randn((ns, r), device="cuda", dtype=torch.float64, generator=gb))
+    sv = torch.from_numpy(synth.pod_spectrum(r)).cuda()
+    X = (A * sv) @ B.t()
+    return X.contiguous(), sv
+
+
+def run_pod_gram(args, rank, world, dev_index):
+    """Kernel (d) + its callers: POD of a row-sharded snapshot matrix -- Gram X^T X per rank (DMMA SYRK; block rows with
+    the all-reduce of finished pieces overlapped when world > 1), leading eigenpairs + energy rule (replicated), sharded
+    back-projection U_g = X_g V S^-1.  --pod-full: the per-GPU slice of BASELINE configs[4] (250 000 x 20 000)."""
+    import torch
+    import torch.distributed as dist
+    from sofacontrol_b200.mor import pod, eig
     from sofacontrol_b200 import parallel
-    nf_local, ns = 131072, 8192
-    gen = torch.Generator(device="cuda").manual_seed(5 + rank)
-    X = torch.randn((nf_local, ns), device="cuda", dtype=torch.float64, generator=gen)
-    G = torch.empty((ns, ns), device="cuda", dtype=torch.float64)
+    import sofacontrol_b200.synth as synth
+    nf_local, ns = (250000, 20000) if args.pod_full else (131072, 8192)
+    tol = 5e-5
+    X, sv = pod_sharded_matrix(nf_local, ns, rank, world)
+    lam_true = (sv ** 2)
+    modes_expected = eig.energy_mode_count(lam_true, lam_true.sum(), tol)
+    nblk = max(1, args.pod_overlap) if world > 1 else 1
+
+    def gram():
+        if world > 1 and nblk > 1:
+            return parallel.overlapped_gram_allreduce(X, nblk)
+        G_ = pod.gram_device(X)
+        return parallel.allreduce_sum_(G_)
+
     for _ in range(max(1, args.warmup - 1)):
-        pod.gram_device(X, G)
-        parallel.allreduce_sum_(G)
+        G = gram()
     torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+    E = lambda: torch.cuda.Event(enable_timing=True)
+    ev = [(E(), E(), E(), E()) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     with ClockSampler(dev_index) as clk:
-        for s_, m_, e_ in ev:
-            s_.record()
-            pod.gram_device(X, G)
-            m_.record()
-            parallel.allreduce_sum_(G)
-            e_.record()
+        for e0, e1, e2, e3 in ev:
+            e0.record()
+            G = gram()
+            e1.record()
+            lam, V, nb, info = eig.leading_eigenpairs(G, tol)
+            e2.record()
+            S = lam[:nb].sqrt()
+            U = pod.dgemm_device(X, (V[:, :nb] / S).contiguous())
+            e3.record()
         torch.cuda.synchronize()
-    t_gram = sum(a.elapsed_time(b) for a, b, _ in ev) * 1e-3
-    t_all = sum(a.elapsed_time(c) for a, _, c in ev) * 1e-3
+    t_gram = sum(a.elapsed_time(b) for a, b, _, _ in ev) * 1e-3
+    t_eig = sum(b.elapsed_time(c) for _, b, c, _ in ev) * 1e-3
+    t_all = sum(a.elapsed_time(d) for a, _, _, d in ev) * 1e-3
+    # untimed checks: the modes are the prescribed ones, U is orthonormal across the shards
+    UtU = U.t() @ U
     if world > 1:
-        tt = torch.tensor([t_gram, t_all], device="cuda", dtype=torch.float64)
+        dist.all_reduce(UtU)
+        tt = torch.tensor([t_gram, t_eig, t_all], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_gram, t_all = float(tt[0]), float(tt[1])
+        t_gram, t_eig, t_all = float(tt[0]), float(tt[1]), float(tt[2])
+    orth = float((UtU - torch.eye(nb, device="cuda", dtype=torch.float64)).abs().max())
+    sig_err = float(((S - sv[:nb]).abs().max() / sv[0]))
     hbm, hsrc, fp64 = measured_peaks()
     fl = 2.0 * nf_local * ns * ns
     ach = fl / (t_gram / args.steps) / 1e12
-    return {"metric": "pod_gram_tflops", "value": world * fl * args.steps / t_all / 1e12, "unit": "TFLOP/s (algorithmic, incl. all-reduce)",
+    return {"metric": "pod_gram_tflops", "value": world * fl * args.steps / t_gram / 1e12,
+            "unit": "TFLOP/s (algorithmic Gram flops, all-reduce inside the timed region)",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "POD snapshot Gram (BASELINE configs[4] per-GPU slice, reduced): X_g %d x %d FP64 per GPU (%.1f GB), "
-                                   "G = sum_g X_g^T X_g, one all-reduce of %d x %d" % (nf_local, ns, nf_local * ns * 8 / 1e9, ns, ns),
-                       "allreduce_ms": 1e3 * (t_all - t_gram) / args.steps},
-            "e2e": None, "gpu_launches": args.steps, "clocks": clk.summary(),
-            "roofline": {"kernel": "dgemm_kernel<true,true,true> (SYRK)", "bound": "tensor", "achieved": ach, "peak": fp64,
-                         "unit": "TFLOP/s", "frac": ach / fp64, "traffic": None,
-                         "note": "algorithmic 2 nf ns^2 flop; the SYRK kernel executes only the upper tiles (half), so frac can exceed 1; "
-                                 "peak = measured cuBLAS DGEMM"}}
+            "config": {"workload": "POD of a row-sharded snapshot matrix (BASELINE configs[4]%s): X_g %d x %d FP64 per GPU (%.1f GB), "
+                                   "prescribed spectrum; G = sum_g X_g^T X_g (%s), leading eigenpairs by block subspace iteration, "
+                                   "U_g = X_g V S^-1" % ("" if args.pod_full else ", reduced per-GPU slice", nf_local, ns,
+                                                         nf_local * ns * 8 / 1e9,
+                                                         "%d block rows, all-reduce of finished rows overlapped" % nblk if nblk > 1
+                                                         else "one SYRK launch" + (" + one all-reduce" if world > 1 else "")),
+                       "gram_ms": 1e3 * t_gram / args.steps, "eig_ms": 1e3 * t_eig / args.steps,
+                       "project_ms": 1e3 * (t_all - t_gram - t_eig) / args.steps,
+                       "modes": int(nb), "modes_expected": int(modes_expected), "sigma_relerr": sig_err,
+                       "U_orthonormality": orth, "eig_iterations": info.get("iterations"), "eig_block": info.get("block")},
+            "e2e": None, "gpu_launches": args.steps * nblk + args.steps * 12, "clocks": clk.summary(),
+            "roofline": {"kernel": "dgemm_kernel<true,true,true> (SYRK)" if nblk == 1 else "dgemm_kernel<true,false,true> (block rows)",
+                         "bound": "tensor", "achieved": ach, "peak": fp64,
+                         "unit": "TFLOP/s", "frac": ach / fp64, "traffic": 61.0e9 if (world == 1 and not args.pod_full) else None,
+                         "note": "algorithmic 2 nf ns^2 flop / Gram time (incl. the overlapped all-reduce when world > 1); the kernel "
+                                 "executes only the upper tiles (half), so frac can exceed 1; peak = measured cuBLAS DGEMM; traffic = ncu "
+                                 "dram read+write of one SYRK launch at this size (profiles/ncu_gram_r2.txt; 8.6 GB algorithmic)"}}
 
 
 def run_mpc(args, rank, world, dev_index):
@@ -773,6 +824,8 @@ def main():
     ap.add_argument("--mpc-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--pod-overlap", type=int, default=1, help="pod_gram on > 1 GPU: block rows of the Gram matrix whose all-reduce overlaps the next rows (1 = one SYRK + one all-reduce, the faster choice: the reduction is < 1 %% of the contraction)")
+    ap.add_argument("--pod-full", action="store_true", help="pod_gram at the per-GPU slice of config 5 (250000 x 20000, 40 GB)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -379,7 +379,7 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
         fl = batch * N * 2.0 * P * (n * n + n * m + n)
         roof = {"kernel": "dgemm_kernel (bank blend)", "bound": "tensor", "achieved": fl / (t_dev / args.steps) / 1e12,
                 "peak": fp64, "unit": "TFLOP/s", "traffic": None,
-                "note": "2 P (n^2+nm+n) flop per trajectory-step; whole step time (weights + blend + discretise + step)"}
+                "note": "2 P (n^2+nm+n) flop per trajectory-step over the WHOLE step time; two launches per time step (profiles/launches_tpwl_weighting_r2.csv): blend GEMM over the concatenated [A|B|d] bank 1.75 ms = 25.9 TFLOP/s (73 % of measured DGEMM peak), fused TMA-fed discretise + step + next-weights kernel 0.44 ms; the 44.4 MB bank is L2 resident (bank stream 25 GB/s: not a bound at this batch)"}
         roof["frac"] = roof["achieved"] / roof["peak"]
     return {"metric": "tpwl_%s_rollout_steps_per_sec" % method, "value": steps_total / t_dev, "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,

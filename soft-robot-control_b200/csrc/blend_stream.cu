@@ -16,32 +16,6 @@ constexpr int BS_STAGES = 4;
 constexpr int BS_MAXB = 8;       // trajectories per pass
 constexpr int BS_CHUNKS = 8;     // split of the stored points across CTAs (41 slabs x 8 chunks = 328 CTAs for A)
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(dst)),
-                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-
 // grid = (slabs, BS_CHUNKS).  W is (nb x P) row-major; partial is (BS_CHUNKS x BS_MAXB x width).
 __global__ void __launch_bounds__(BS_COLS)
 blend_stream_kernel(const double* __restrict__ bank, int P, int width, const double* __restrict__ W, int nb,

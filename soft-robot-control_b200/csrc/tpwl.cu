@@ -85,6 +85,29 @@ __device__ __forceinline__ double cta_sum(double v, double* red) {
     return s;
 }
 
+// weights of one state sx (shared memory) into ws (global, P doubles); sd: P doubles of shared scratch
+template <int NT>
+__device__ __forceinline__ void tpwl_weights_one(const TpwlDev& M, const double* __restrict__ sx, double* __restrict__ sd,
+                                                 double* red_d, int* red_i, double* __restrict__ ws) {
+    double dmin;
+    const int bi = tpwl_nearest<NT>(M, sx, sd, red_d, red_i, &dmin);
+    __syncthreads();
+    if (dmin == 0.0) {
+        for (int p = threadIdx.x; p < M.P; p += NT) ws[p] = (p == bi) ? 1.0 : 0.0;
+    } else {
+        double part = 0.0;
+        for (int p = threadIdx.x; p < M.P; p += NT) {
+            // np.exp(-beta * dist / m): ((-beta) * dist) / m
+            const double e = exp(__ddiv_rn(__dmul_rn(-M.beta, sd[p]), dmin));
+            sd[p] = e;
+            part += e;
+        }
+        const double tot = cta_sum<NT>(part, red_d);
+        for (int p = threadIdx.x; p < M.P; p += NT) ws[p] = __ddiv_rn(sd[p], tot);
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kSel)
 tpwl_weights_kernel(TpwlDev M, long long count, const double* __restrict__ x, long long xstride,
                     double* __restrict__ w) {
@@ -96,23 +119,94 @@ tpwl_weights_kernel(TpwlDev M, long long count, const double* __restrict__ x, lo
     for (long long s = blockIdx.x; s < count; s += gridDim.x) {
         for (int i = threadIdx.x; i < M.n; i += kSel) sx[i] = x[s * xstride + i];
         __syncthreads();
-        double dmin;
-        const int bi = tpwl_nearest<kSel>(M, sx, sd, red_d, red_i, &dmin);
-        __syncthreads();
-        double* ws = w + s * (long long)M.P;
-        if (dmin == 0.0) {
-            for (int p = threadIdx.x; p < M.P; p += kSel) ws[p] = (p == bi) ? 1.0 : 0.0;
-        } else {
-            double part = 0.0;
-            for (int p = threadIdx.x; p < M.P; p += kSel) {
-                // np.exp(-beta * dist / m): ((-beta) * dist) / m
-                const double e = exp(__ddiv_rn(__dmul_rn(-M.beta, sd[p]), dmin));
-                sd[p] = e;
-                part += e;
-            }
-            const double tot = cta_sum<kSel>(part, red_d);
-            for (int p = threadIdx.x; p < M.P; p += kSel) ws[p] = __ddiv_rn(sd[p], tot);
+        tpwl_weights_one<kSel>(M, sx, sd, red_d, red_i, w + s * (long long)M.P);
+    }
+}
+
+// ---- weighting-mode rollout, fused per time step ---------------------------------------------------------------
+// The three banks are concatenated once per call into one (P x wd) matrix [A_p | B_p | d_p], so the blend of a time step
+// is ONE DMMA GEMM  W (batch x P) * bank (P x wd)  (tpwl.py:246-248 are three einsums over the same weights); this
+// kernel then takes each trajectory's blended row, discretises it in shared memory (tpwl.py:272-297), steps the state
+// (tpwl.py:336-339) and computes the weights of the NEW state for the next time step's GEMM: two launches per step.
+constexpr int kWS = 256;
+__global__ void tpwl_concat_bank_kernel(TpwlDev M, long long wd, double* __restrict__ cat) {
+    const long long nn = (long long)M.n * M.n, nm = (long long)M.n * M.m;
+    for (long long p = blockIdx.x; p < M.P; p += gridDim.x) {
+        double* row = cat + p * wd;
+        for (long long e = threadIdx.x; e < nn; e += blockDim.x) row[e] = M.A[p * nn + e];
+        for (long long e = threadIdx.x; e < nm; e += blockDim.x) row[nn + e] = M.B[p * nm + e];
+        for (long long e = threadIdx.x; e < M.n; e += blockDim.x) row[nn + nm + e] = M.d[p * M.n + e];
+        for (long long e = nn + nm + M.n + threadIdx.x; e < wd; e += blockDim.x) row[e] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kWS)
+tpwl_weighting_step_kernel(TpwlDev M, long long batch, int disc, double dt, const double* __restrict__ blended, long long wd,
+                           const double* __restrict__ x, long long xstride, const double* __restrict__ u, long long ustride,
+                           double* __restrict__ xn, long long xnstride, double* __restrict__ wnext) {
+    extern __shared__ __align__(128) double sm[];
+    __shared__ double red_d[kWS / 32];
+    __shared__ int red_i[kWS / 32];
+    __shared__ __align__(8) uint64_t full[2];
+    const int n = M.n, m = M.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rowlen = n * n + n * m + n;                       // doubles of one blended row [A | B | d]
+    const unsigned rowbytes = (unsigned)(sizeof(double) * (size_t)((rowlen + 1) & ~1));   // == wd doubles: 16-byte multiple
+    double* buf0 = sm;
+    double* buf1 = sm + wd;
+    double* sx = sm + 2 * wd;
+    double* su = sx + n;
+    double* sxn = su + ((m + 1) & ~1);
+    double* scr = sxn + n;                       // discretisation scratch, then the P distances of the weights
+    // Each trajectory's 44 KB row is pulled by ONE TMA bulk copy (cp.async.bulk + mbarrier) into a two-slot ring: the
+    // row of the CTA's next trajectory streams in while the current one is discretised, stepped and weighted.
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    long long b = blockIdx.x;
+    if (tid == 0 && b < batch) {
+        mbar_expect_tx(&full[0], rowbytes);
+        tma_bulk_g2s(buf0, blended + b * wd, rowbytes, &full[0]);
+    }
+    int it = 0;
+    for (; b < batch; b += gridDim.x, ++it) {
+        const int slot = it & 1;
+        double* sA = slot ? buf1 : buf0;
+        double* sB = sA + n * n;
+        double* sd = sB + n * m;
+        const long long bnext = b + gridDim.x;
+        if (tid == 0 && bnext < batch) {          // slot ^ 1 was released by the __syncthreads that ended the previous trajectory
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // its generic-proxy writes (in-place discretisation) come first
+            mbar_expect_tx(&full[slot ^ 1], rowbytes);
+            tma_bulk_g2s(slot ? buf0 : buf1, blended + bnext * wd, rowbytes, &full[slot ^ 1]);
         }
+        for (int e = tid; e < n; e += kWS) sx[e] = x[b * xstride + e];
+        for (int e = tid; e < m; e += kWS) su[e] = u[b * ustride + e];
+        mbar_wait(&full[slot], (unsigned)((it >> 1) & 1));
+        __syncthreads();
+        if (disc) {
+            discretize_inplace<kWS>(M.discr, dt, sA, sB, sd, n, m, scr);
+            __syncthreads();
+        }
+        for (int i = warp; i < n; i += kWS / 32) {
+            double ax = 0.0, bu = 0.0;
+            for (int k = lane; k < n; k += 32) ax = fma(sA[i * n + k], sx[k], ax);
+            for (int k = lane; k < m; k += 32) bu = fma(sB[i * m + k], su[k], bu);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                ax += __shfl_xor_sync(0xffffffffu, ax, off);
+                bu += __shfl_xor_sync(0xffffffffu, bu, off);
+            }
+            if (lane == 0) {
+                const double v = __dadd_rn(__dadd_rn(ax, bu), sd[i]);
+                sxn[i] = v;
+                xn[b * xnstride + i] = v;
+            }
+        }
+        __syncthreads();
+        if (wnext) tpwl_weights_one<kWS>(M, sxn, scr, red_d, red_i, wnext + b * (long long)M.P);
         __syncthreads();
     }
 }
@@ -557,7 +651,9 @@ extern "C" int srcb200_tpwl_linearize_batch(const srcb200_tpwl_model* mdl, int64
     return 0;
 }
 
-// rollout workspace (weighting only): [ W (batch x P) | A (batch x n x n) | B (batch x n x m) | d (batch x n) ]
+// rollout workspace (weighting only): [ W (batch x P) | A (batch x n x n) | B (batch x n x m) | d (batch x n) | zoh scratch |
+//                                       concatenated bank (P x wd) | blended rows (batch x wd) | blend-stream scratch ]
+static long long weighting_width(const TpwlDev& M) { return ((long long)M.n * M.n + (long long)M.n * M.m + M.n + 1) & ~1LL; }
 extern "C" size_t srcb200_tpwl_rollout_workspace(const srcb200_tpwl_model* mdl, int64_t batch) {
     if (!mdl || batch <= 0) return 0;
     TpwlDev M = to_dev(*mdl);
@@ -565,7 +661,8 @@ extern "C" size_t srcb200_tpwl_rollout_workspace(const srcb200_tpwl_model* mdl, 
     const size_t z = (M.discr == SRCB200_DISCR_ZOH) ? align_up(srcb200_zoh_workspace(M.n, M.m, batch), 256) : 0;
     return align_up(sizeof(double) * (size_t)batch * M.P, 256) + align_up(sizeof(double) * (size_t)batch * M.n * M.n, 256) +
            align_up(sizeof(double) * (size_t)batch * M.n * M.m, 256) + align_up(sizeof(double) * (size_t)batch * M.n, 256) + z +
-           align_up(blend_stream_workspace(M.n * M.n), 256);
+           align_up(sizeof(double) * (size_t)M.P * weighting_width(M), 256) +
+           align_up(sizeof(double) * (size_t)batch * weighting_width(M), 256) + align_up(blend_stream_workspace(M.n * M.n), 256);
 }
 
 extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t batch, int32_t N, const double* x0,
@@ -624,17 +721,40 @@ extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t
         const int grid = (int)(batch < 148 * 16 ? batch : 148 * 16);
         const size_t wsmem = sizeof(double) * (n + M.P);
         SRCB_CUDA(cudaFuncSetAttribute(tpwl_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-        for (int t = 0; t < N; ++t) {
-            // the states of step t live strided inside x: x[b, t, :]
-            tpwl_weights_kernel<<<grid, kSel, wsmem, st>>>(M, batch, x + (long long)t * n, xs, W);
+        const long long wd = weighting_width(M);
+        double* cat = (double*)((char*)zws + zws_bytes);
+        double* blended = (double*)((char*)cat + align_up(sizeof(double) * (size_t)M.P * wd, 256));
+        const bool fused = !(disc && M.discr == SRCB200_DISCR_ZOH) && batch > kBlendStreamMaxBatch;
+        const size_t fsmem = sizeof(double) * (2 * (size_t)wd + 2 * n + ((m + 1) & ~1) +
+                                               (size_t)max(discretize_scratch_doubles(n, m), M.P) + 2);
+        if (fused && fsmem <= 227 * 1024) {
+            // two launches per time step: blend GEMM over the concatenated bank, fused discretise + step + next weights
+            SRCB_CUDA(cudaFuncSetAttribute(tpwl_weighting_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            tpwl_concat_bank_kernel<<<(int)(M.P < 148 * 8 ? M.P : 148 * 8), 256, 0, st>>>(M, wd, cat);
+            SRCB_LAUNCH_CHECK("tpwl_concat_bank_kernel");
+            tpwl_weights_kernel<<<grid, kSel, wsmem, st>>>(M, batch, x, xs, W);
             SRCB_LAUNCH_CHECK("tpwl_weights_kernel");
-            if (int e = blend(M.A, M.P, (long long)n * n, W, batch, Ab, sws, st)) return e;
-            if (int e = blend(M.B, M.P, (long long)n * m, W, batch, Bb, sws, st)) return e;
-            if (int e = blend(M.d, M.P, n, W, batch, db, sws, st)) return e;
-            if (disc) if (int e = discretize_any(n, m, M.discr, batch, dt, Ab, Bb, db, zws, zws_bytes, st)) return e;
-            tpwl_step_kernel<<<grid, 128, 0, st>>>(n, m, batch, Ab, Bb, db, x + (long long)t * n, xs, u + (long long)t * m, us,
-                                                   x + (long long)(t + 1) * n, xs);
-            SRCB_LAUNCH_CHECK("tpwl_step_kernel");
+            const int fgrid = (int)(batch < 148 * 2 ? batch : 148 * 2);
+            for (int t = 0; t < N; ++t) {
+                if (int e = dgemm_device(0, batch, wd, M.P, 1.0, W, M.P, cat, wd, blended, wd, st)) return e;
+                tpwl_weighting_step_kernel<<<fgrid, kWS, fsmem, st>>>(M, batch, disc ? 1 : 0, dt, blended, wd, x + (long long)t * n, xs,
+                                                                      u + (long long)t * m, us, x + (long long)(t + 1) * n, xs,
+                                                                      (t + 1 < N) ? W : nullptr);
+                SRCB_LAUNCH_CHECK("tpwl_weighting_step_kernel");
+            }
+        } else {
+            for (int t = 0; t < N; ++t) {
+                // the states of step t live strided inside x: x[b, t, :]
+                tpwl_weights_kernel<<<grid, kSel, wsmem, st>>>(M, batch, x + (long long)t * n, xs, W);
+                SRCB_LAUNCH_CHECK("tpwl_weights_kernel");
+                if (int e = blend(M.A, M.P, (long long)n * n, W, batch, Ab, sws, st)) return e;
+                if (int e = blend(M.B, M.P, (long long)n * m, W, batch, Bb, sws, st)) return e;
+                if (int e = blend(M.d, M.P, n, W, batch, db, sws, st)) return e;
+                if (disc) if (int e = discretize_any(n, m, M.discr, batch, dt, Ab, Bb, db, zws, zws_bytes, st)) return e;
+                tpwl_step_kernel<<<grid, 128, 0, st>>>(n, m, batch, Ab, Bb, db, x + (long long)t * n, xs, u + (long long)t * m, us,
+                                                       x + (long long)(t + 1) * n, xs);
+                SRCB_LAUNCH_CHECK("tpwl_step_kernel");
+            }
         }
     }
     if (z) {

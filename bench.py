@@ -490,10 +490,17 @@ def run_ssm_eval(args, rank, world, dev_index):
             "config": {"workload": "Trunk SSM batched evaluation + linearisation: %d states per GPU, outputs A_c, d_c, H, c, z "
                                    "(inputs %.0f MB + outputs %.0f MB per launch: larger than L2)" % (count, count * 14 * 8 / 1e6, byts / 1e6 - count * 14 * 8 / 1e6)},
             "e2e": None, "gpu_launches": args.steps, "clocks": clk.summary(),
-            "roofline": {"kernel": "ssm_eval_dmma_kernel<8>", "bound": "tensor", "achieved": ach, "peak": fp64, "unit": "TFLOP/s",
+            "roofline": {"kernel": "ssm_eval_sparse_dmma_kernel<8>", "bound": "tensor", "achieved": ach, "peak": fp64, "unit": "TFLOP/s",
                          "frac": ach / fp64, "traffic": None, "hbm_gbs": byts / (t_dev / args.steps) / 1e9,
-                         "note": "13944 algorithmic flop per state (dense count, SURVEY 8d); 42 DMMA m8n8k4 per state execute "
-                                 "21504 flop (padding 16x84x8); peak = measured cuBLAS DGEMM"}}
+                         "hbm_frac": byts / (t_dev / args.steps) / 1e9 / hbm,
+                         "executed_tflops": 12 * 512.0 * count / (t_dev / args.steps) / 1e12,
+                         "executed_frac": 12 * 512.0 * count / (t_dev / args.steps) / 1e12 / fp64,
+                         "note": "achieved = 13944 ALGORITHMIC flop per state (the dense count of SURVEY 8d: f, A = df/dx, C(x), H) / time; "
+                                 "the kernel contracts only the structural non-zeros of d phi / d x (12 DMMA m8n8k4 = 6144 executed flop "
+                                 "per state, executed_tflops; the dense formulation needs 42 DMMA, of which 35 % padding: "
+                                 "SRCB200_SSM_EVAL_DENSE=1, 0.67 G states/s), so the algorithmic fraction can approach 1 while the tensor "
+                                 "pipe is ~45 % busy; the other bound is the 832 B of I/O per state (hbm_frac of the measured copy "
+                                 "bandwidth); peak = measured cuBLAS DGEMM"}}
 
 
 def pod_sharded_matrix(nf_local, ns, rank, world, r=192, seed=5):

@@ -1518,6 +1518,177 @@ ssm_eval_dmma_kernel(const __grid_constant__ SsmDev Mdl, long long count, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Batched evaluation + linearisation, second generation (continuous / fe / discrete outputs): EIGHT STATES PER WARP
+// as the M dimension of the DMMA tiles, and the SPARSE structure of the contraction.  d phi / d x_j of a degree-<=3
+// monomial is a multiple of an entry of psi = (x, x (x) x) (8 + 24 padded slots), the same psi for every j, so
+//     J_j (8 states x 16 outputs)  =  Psi (8 x 32)  x  T_j (32 x 16),     j = 0..5,
+// with T_j the multiplicity-scaled coefficients of the monomials containing x_j (rows of r_coeff for outputs 0..5,
+// of w_coeff for 6..11): 6 x 8 k-steps x 2 n-tiles = 96 DMMAs per EIGHT states (12 per state; the dense kernel above
+// issues 42 per state, 35 % of them padding).  The Psi fragment is built once per group and reused by all 96; the
+// T_j fragments are read conflict-free from a 24 KB table.  Degree-2 and degree-3 parts accumulate separately, which
+// gives the VALUES by Euler's theorem (x . grad h = p h for a homogeneous h of degree p) without any extra
+// contraction.  A lane ends up owning whole rows (over j) of A_c / H of its state, so f, z, d_c = (f - A x) - B u and
+// c = C(x) - H x are in-lane dot products and the rows leave as 16-byte stores.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int E2_WARPS = 4;
+constexpr int E2_TAB = 6 * 2 * 8 * 32;            // T_j fragments: [j][nt][ks][lane]
+constexpr int E2_G1 = 6 * 2 * 32 * 2;             // degree-1 constants in C-fragment layout: [j][nt][lane] x 2
+constexpr size_t E2_SMEM = sizeof(double) * (SH_END + E2_TAB + E2_G1 + E2_WARPS * (8 * 8 + 8 * 8));
+
+template <int M>
+__global__ void __launch_bounds__(E2_WARPS * 32, 3)
+ssm_eval_sparse_dmma_kernel(const __grid_constant__ SsmDev Mdl, long long count, const double* __restrict__ xg,
+                            const double* __restrict__ ug, double dt, int fe, double* __restrict__ Ao,
+                            double* __restrict__ Bo, double* __restrict__ dout, double* __restrict__ Ho,
+                            double* __restrict__ co, double* __restrict__ zo) {
+    build_tables(Mdl, nullptr, nullptr, nullptr, g_sm, M);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    double* TAB = g_sm + SH_END;
+    double* G1 = TAB + E2_TAB;
+    double* XE = G1 + E2_G1 + warp * 128;          // 8 states x 8: x_0..x_5, 0, 0
+    double* UE = XE + 64;                          // 8 states x 8 inputs
+    const double* T = g_sm + SH_T;
+    const double* Brt = g_sm + SH_BR;
+    const double* zref = g_sm + SH_ZREF;
+    const int* fidx = reinterpret_cast<const int*>(g_sm + SH_FIDX);
+    // fragment tables from the Jacobian table of build_tables (row 6 i + j: d f_i / d x_j, 36 + 6 i + j: d z_i / d x_j;
+    // slot 0: degree-1 constant, 2..7: degree 2 against x_0..x_5, 8..28: degree 3 against the 21 products)
+    for (int e = threadIdx.x; e < E2_TAB; e += blockDim.x) {
+        const int l = e & 31, ks = (e >> 5) & 7, nt = (e >> 8) & 1, j = e >> 9;
+        const int k = 4 * ks + (l & 3), out = 8 * nt + (l >> 2);
+        double v = 0.0;
+        if (out < 12) {
+            const int pd = (out < 6) ? 6 * out + j : 36 + 6 * (out - 6) + j;
+            const int slot = (k < 6) ? 2 + k : ((k >= 8 && k < 29) ? k : -1);
+            if (slot >= 0) v = T[pd * TS + slot];
+        }
+        TAB[e] = v;
+    }
+    for (int e = threadIdx.x; e < E2_G1; e += blockDim.x) {
+        const int h = e & 1, l = (e >> 1) & 31, nt = (e >> 6) & 1, j = e >> 7;
+        const int out = 8 * nt + 2 * (l & 3) + h;
+        double v = 0.0;
+        if (out < 12) v = T[((out < 6) ? 6 * out + j : 36 + 6 * (out - 6) + j) * TS];
+        G1[e] = v;
+    }
+    // psi recipe of this lane: slot 4 ks + q of the 32-slot operand (0..5: x, 8..28: products)
+    int ra[8], rb[8];                              // indices into the padded state row (6, 7 read zeros; 8: the constant 1)
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        const int k = 4 * ks + q;
+        if (k < 6) { ra[ks] = k; rb[ks] = -1; }
+        else if (k >= 8 && k < 29) { const int pk = fidx[6 + k - 8]; ra[ks] = pk & 7; rb[ks] = (pk >> 3) & 7; }
+        else { ra[ks] = 6; rb[ks] = -1; }
+    }
+    __syncthreads();
+    const double sdt = fe ? dt : 1.0;
+    const long long groups = (count + 7) / 8;
+    const long long gstride = (long long)gridDim.x * E2_WARPS;
+    for (long long grp = (long long)blockIdx.x * E2_WARPS + warp; grp < groups; grp += gstride) {
+        const long long st0 = grp * 8;
+        // stage the 8 states / inputs of the group
+        {
+            const int sidx = lane >> 2, c2 = (lane & 3) * 2;          // two consecutive entries per lane
+            const long long st = st0 + sidx;
+            double v0 = 0.0, v1 = 0.0, u0 = 0.0, u1 = 0.0;
+            if (st < count) {
+                if (c2 < 6) { v0 = xg[st * 6 + c2]; v1 = xg[st * 6 + c2 + 1]; }
+                if (ug && c2 < M) { u0 = ug[st * M + c2]; u1 = ug[st * M + c2 + 1]; }
+            }
+            *reinterpret_cast<double2*>(XE + sidx * 8 + c2) = make_double2(v0, v1);
+            *reinterpret_cast<double2*>(UE + sidx * 8 + c2) = make_double2(u0, u1);
+        }
+        __syncwarp();
+        // Psi fragment: A operand (row = state g, k = 4 ks + q)
+        double psi[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const double a = XE[g * 8 + ra[ks]];
+            psi[ks] = (rb[ks] >= 0) ? __dmul_rn(a, XE[g * 8 + rb[ks]]) : a;
+        }
+        const double2 x01 = *reinterpret_cast<const double2*>(XE + g * 8);
+        const double2 x23 = *reinterpret_cast<const double2*>(XE + g * 8 + 2);
+        const double2 x45 = *reinterpret_cast<const double2*>(XE + g * 8 + 4);
+        const double xs[6] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y};
+        // rows owned by this lane: tile 0 -> outputs 2q, 2q+1 ; tile 1 -> outputs 8 + 2q, 9 + 2q  (valid for q < 2)
+        double J[2][2][6];                         // [tile][half][j]
+        double val[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        constexpr double third = 1.0 / 3.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const double* tb = TAB + ((j * 2 + nt) * 8) * 32 + lane;
+                Frag a2{0.0, 0.0}, a3{0.0, 0.0}, b3{0.0, 0.0};
+                dmma(a2, psi[0], tb[0 * 32]);
+                dmma(a3, psi[2], tb[2 * 32]);
+                dmma(b3, psi[3], tb[3 * 32]);
+                dmma(a2, psi[1], tb[1 * 32]);
+                dmma(a3, psi[4], tb[4 * 32]);
+                dmma(b3, psi[5], tb[5 * 32]);
+                dmma(a3, psi[6], tb[6 * 32]);
+                dmma(b3, psi[7], tb[7 * 32]);
+                const double2 g1 = *reinterpret_cast<const double2*>(G1 + ((j * 2 + nt) * 32 + lane) * 2);
+                const double g30 = __dadd_rn(a3.c0, b3.c0), g31 = __dadd_rn(a3.c1, b3.c1);
+                J[nt][0][j] = __dadd_rn(__dadd_rn(g1.x, a2.c0), g30);
+                J[nt][1][j] = __dadd_rn(__dadd_rn(g1.y, a2.c1), g31);
+                // Euler: value += x_j (g1 + g2 / 2 + g3 / 3)
+                val[nt][0] = fma(xs[j], __dadd_rn(__dadd_rn(g1.x, __dmul_rn(0.5, a2.c0)), __dmul_rn(third, g30)), val[nt][0]);
+                val[nt][1] = fma(xs[j], __dadd_rn(__dadd_rn(g1.y, __dmul_rn(0.5, a2.c1)), __dmul_rn(third, g31)), val[nt][1]);
+            }
+        }
+        const long long st = st0 + g;
+        if (st < count) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int out = 8 * nt + 2 * q + h;
+                    if (out >= 12) continue;
+                    const double* Jr = J[nt][h];
+                    double jx = 0.0;                                   // (row of the Jacobian) . x
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) jx = fma(Jr[j], xs[j], jx);
+                    if (out < 6) {
+                        // dynamics row `out`: f = r phi + B u ; d = (f - A x) - B u               (ssm.py:168, 203)
+                        double bu = 0.0;
+#pragma unroll
+                        for (int k2 = 0; k2 < M; ++k2) bu = fma(Brt[out * LD + k2], UE[g * 8 + k2], bu);
+                        const double dc = __dsub_rn(__dsub_rn(__dadd_rn(val[nt][h], bu), jx), bu);
+                        if (Ao) {
+                            double r6[6];
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) {
+                                const double v = fe ? __dmul_rn(dt, Jr[j]) : Jr[j];
+                                r6[j] = (fe && j == out) ? __dadd_rn(1.0, v) : v;
+                            }
+                            double2* dst = reinterpret_cast<double2*>(Ao + st * 36 + out * 6);
+                            dst[0] = make_double2(r6[0], r6[1]); dst[1] = make_double2(r6[2], r6[3]); dst[2] = make_double2(r6[4], r6[5]);
+                        }
+                        if (Bo) {
+#pragma unroll
+                            for (int k2 = 0; k2 < M; k2 += 2)
+                                *reinterpret_cast<double2*>(Bo + st * 6 * M + out * M + k2) =
+                                    make_double2(__dmul_rn(sdt, Brt[out * LD + k2]), __dmul_rn(sdt, Brt[out * LD + k2 + 1]));
+                        }
+                        if (dout) dout[st * 6 + out] = fe ? __dmul_rn(dt, dc) : dc;
+                    } else {
+                        const int i = out - 6;
+                        if (Ho) {
+                            double2* dst = reinterpret_cast<double2*>(Ho + st * 36 + i * 6);
+                            dst[0] = make_double2(Jr[0], Jr[1]); dst[1] = make_double2(Jr[2], Jr[3]); dst[2] = make_double2(Jr[4], Jr[5]);
+                        }
+                        if (zo) zo[st * 6 + i] = __dadd_rn(val[nt][h], zref[i]);
+                        if (co) co[st * 6 + i] = __dsub_rn(val[nt][h], jx);       // c = C(x) - H x  (ssm.py:228-235)
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace fast
 
 int ssm_eval_dmma_launch(const SsmDev& M, long long count, const double* x, const double* u, double dt, double* A,
@@ -1529,6 +1700,26 @@ int ssm_eval_dmma_launch(const SsmDev& M, long long count, const double* x, cons
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool want_dyn = (A || B || d);
+    const bool cont = (dt < 0.0) || M.discr == SRCB200_DISCR_NONE;
+    const char* dense = getenv("SRCB200_SSM_EVAL_DENSE");
+    if ((!want_dyn || cont || M.discr == SRCB200_DISCR_FE) && !(dense && dense[0] == '1')) {
+        // sparse contraction, eight states per warp (no 6 x 6 inverses needed for these outputs)
+        const long long groups = (count + 7) / 8;
+        const long long ctas2 = (groups + fast::E2_WARPS - 1) / fast::E2_WARPS;
+        const int grid2 = (int)(ctas2 < 3LL * sms ? ctas2 : 3LL * sms);
+        const int fe = (!cont && M.discr == SRCB200_DISCR_FE) ? 1 : 0;
+        if (M.m == 8) {
+            SRCB_CUDA(cudaFuncSetAttribute(fast::ssm_eval_sparse_dmma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::E2_SMEM));
+            fast::ssm_eval_sparse_dmma_kernel<8><<<grid2, fast::E2_WARPS * 32, fast::E2_SMEM, st>>>(M, count, x, u, dt, fe, A, B, d, H, c, z);
+        } else {
+            SRCB_CUDA(cudaFuncSetAttribute(fast::ssm_eval_sparse_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::E2_SMEM));
+            fast::ssm_eval_sparse_dmma_kernel<4><<<grid2, fast::E2_WARPS * 32, fast::E2_SMEM, st>>>(M, count, x, u, dt, fe, A, B, d, H, c, z);
+        }
+        SRCB_LAUNCH_CHECK("ssm_eval_sparse_dmma_kernel");
+        *handled = true;
+        return 0;
+    }
     const long long ctas = (count + fast::EV_WARPS - 1) / fast::EV_WARPS;
     const int grid = (int)(ctas < 5LL * sms ? ctas : 5LL * sms);
     if (M.m == 8) fast::ssm_eval_dmma_kernel<8><<<grid, fast::EV_WARPS * 32, 0, st>>>(M, count, x, u, dt, A, B, d, H, c, z);

@@ -303,14 +303,15 @@ def run_ilqr(args, rank, world, dev_index):
                      "unit": "TFLOP/s", "frac": ach / fp64,
                      "traffic": traffic_model,
                      "traffic_source": "modelled from the executed passes (bench.py:ilqr_record_traffic: record + gain "
-                                       "bytes per pass-step); ncu dram read+write of one launch of this workload: 35.7e9 "
-                                       "(profiles/ncu_ilqr_r2_e1.txt)",
+                                       "bytes per pass-step); ncu dram read+write of one launch of this workload: 35.5e9 "
+                                       "(profiles/ncu_ilqr_r2_l2.txt)",
                      "algorithmic_io_bytes": float(batch * (55e3)),
                      "note": "FP64 pipe (DMMA + DFMA): algorithmic flops of the executed passes (dense counts, bench.py:"
                              "ilqr_flops, DESIGN.md) / event time of the single launch; peak = cuBLAS DGEMM 8192^3 "
-                             "measured on this pool (profiles/fp64_peaks_r01.json), of measured; the kernel is bound by "
-                             "dependent-issue latency and the shared-memory/shuffle pipe (n = 6), see "
-                             "profiles/ncu_ilqr_r2_e1.txt and ncu_ilqr_r2_e1_lines.txt"},
+                             "measured on this pool (profiles/fp64_peaks_r01.json), of measured; the kernel is bound by the "
+                             "dependent-issue latency of one warp (n = 6: issue slots 32 %, L1/shared 58-72 %, FP64 pipe "
+                             "16 %) and, at 4096 problems, by the serial chain of the longest solves (22 % of the warp-time "
+                             "idle in the task queue): profiles/ncu_ilqr_r2_l2.txt, ncu_ilqr_r2_l2_lines.txt, DESIGN.md 4.1"},
     }
     if strong is not None:
         res["strong"] = strong

@@ -84,8 +84,13 @@ class SSM:
     def _handle(self, kind):
         """kind: 'cont' (r_coeff, B_r, discretised by discr_method), 'cont_raw' (no discretisation),
         'disc' (rd_coeff, Bd_r)."""
+        # the device copies capture the coefficient arrays: key them on a content fingerprint (a few KB, microseconds)
+        # so a model whose coefficients / z_ref were modified after first use is uploaded again
+        fp = hash(b"".join(np.ascontiguousarray(a, dtype=np.float64).tobytes() for a in
+                           (self.rd_coeff if kind == 'disc' else self.r_coeff, self.Bd_r if kind == 'disc' else self.B_r,
+                            self.w_coeff, self.v_coeff, np.asarray(self.z_ref, dtype=np.float64).reshape(-1))))
         key = (kind, self.discr_method)
-        if key in self._dev:
+        if key in self._dev and self._dev[key][2] == fp:
             return self._dev[key][0]
         L.require_gpu()
         torch = L.torch_mod()
@@ -103,7 +108,7 @@ class SSM:
                        nfeat=self.mono_table.shape[0], discr_method=L.DISCR[method],
                        r_coeff=L.ptr(bufs['r']), w_coeff=L.ptr(bufs['w']), v_coeff=L.ptr(bufs['v']),
                        B_r=L.ptr(bufs['B']), z_ref=L.ptr(bufs['z']), mono=L.ptr(bufs['mono']))
-        self._dev[key] = (h, bufs)
+        self._dev[key] = (h, bufs, fp)
         return h
 
     def device_model(self):

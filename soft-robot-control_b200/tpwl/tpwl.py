@@ -69,6 +69,13 @@ class TPWL:
         self._dev_d = None    # device copies of the pre-discretised bank
 
     # ---- device bank --------------------------------------------------------------------------------------------
+    def invalidate_device_cache(self):
+        """Drops the device copies of the bank, the output model and the discretised banks.  They are captured at
+        first use (44 MB at the Diamond size: too large to fingerprint per call); call this after modifying
+        tpwl_dict / H / z_ref in place."""
+        self._dev = None
+        self._zoh_cache = None
+
     def _bank(self):
         if self._dev is None:
             L.require_gpu()
@@ -265,8 +272,9 @@ class TPWL:
 
     def _zoh_bank_model(self, dt):
         cache = getattr(self, '_zoh_cache', None)
-        if cache is None or cache[0] != dt:
-            cache = (dt, self._discretize_bank_device(dt))
+        key = (dt, self.discr_method, id(self._bank()))        # a new device bank (invalidate_device_cache) re-discretises
+        if cache is None or cache[0] != key:
+            cache = (key, self._discretize_bank_device(dt))
             self._zoh_cache = cache
         h = self.device_model(continuous=True)
         A, B, d = cache[1]

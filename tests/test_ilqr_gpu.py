@@ -244,6 +244,24 @@ def test_specialised_kernels_agree_with_generic_kernels():
         assert relerr(a, b) < 1e-11
 
 
+@pytest.mark.parametrize("m", [4, 8])
+def test_launch_shapes_of_the_fast_kernel_agree(m, monkeypatch):
+    """SRCB200_ILQR_SHAPE 0 / 1 / 2 (16 / 12 / 8 warps per SM; Jacobian-table rows in shared memory / one / two in
+    registers) run the same arithmetic: same iterations and statuses, x, u, K to 1e-12."""
+    import sofacontrol_b200.synth as synth
+    w = synth.trunk_ilqr_batch(40, N=30, seed=9, m=m)
+    _, model = _ssm(m)
+    res = {}
+    for shape in ("0", "1", "2"):
+        monkeypatch.setenv("SRCB200_ILQR_SHAPE", shape)
+        s = _solver(model, m, w['z_target'])
+        res[shape] = s.ilqr_computation(w['x0']) + (s.info['iterations'], s.info['status'])
+    for shape in ("1", "2"):
+        assert np.array_equal(res[shape][3], res["0"][3]) and np.array_equal(res[shape][4], res["0"][4])
+        for a, b in zip(res[shape][:3], res["0"][:3]):
+            assert relerr(a, b) < 1e-12
+
+
 def test_receding_horizon_closed_loop_matches_oracle_loop():
     """Config-4 driver (receding-horizon iLQR with shifted warm start + u_last) vs the same loop written with the
     numpy oracle solver and model, noise-free, small case."""

@@ -196,3 +196,40 @@ def test_c_abi_error_codes_on_device():
     assert lib.srcb200_ilqr_solve_batch(7, C_addr(h), sol._cfg(), pr, res, L.ptr(small), 128, None) == L.E_DIM
     with pytest.raises(L.Srcb200Error):
         L.check(L.E_WORKSPACE)
+
+
+def test_device_copies_follow_modified_model_data():
+    """The device handle is keyed on a fingerprint of the coefficient arrays: editing the model after first use
+    (here r_coeff and z_ref) must change the results like it does in the reference class."""
+    g, o = _models(4, discrete=False, discr_method='fe')
+    rng = np.random.default_rng(5)
+    x, u = 0.3 * rng.normal(size=6), rng.uniform(0, 800, size=4)
+    A0, B0, d0 = g.get_jacobians(x, u=u, dt=0.02)
+    g.r_coeff = g.r_coeff * 1.5
+    o.r_coeff = o.r_coeff * 1.5
+    g.z_ref = g.z_ref + 1.0
+    o.z_ref = o.z_ref + 1.0
+    A1, B1, d1 = g.get_jacobians(x, u=u, dt=0.02)
+    Ao, Bo, do_ = o.get_jacobians(x, u=u, dt=0.02)
+    assert relerr(A1, Ao) < TOL and not np.allclose(A1, A0)
+    assert relerr(g.x_to_zfyf(x[None, :], zf=True), o.x_to_zfyf(x[None, :], zf=True)) < TOL
+
+
+@pytest.mark.parametrize("dense", ["0", "1"])
+def test_sparse_and_dense_evaluation_kernels_agree_with_oracle(dense, monkeypatch):
+    """Kernel (b) in both formulations (eight-states-per-warp sparse contraction / dense 42-DMMA contraction) on a batch
+    that is not a multiple of 8: A_c, d_c, H, c, z vs the oracle."""
+    monkeypatch.setenv("SRCB200_SSM_EVAL_DENSE", dense)
+    from sofacontrol_b200 import _lib as L
+    g, o = _models(8, discrete=False, discr_method='be')
+    rng = np.random.default_rng(11)
+    X = 0.4 * rng.normal(size=(45, 6))
+    U = rng.uniform(0, 800, size=(45, 8))
+    out = g._eval_device(L.to_dev(X), L.to_dev(U), -1.0, 'cont_raw', ('A', 'd', 'H', 'c', 'z'))
+    for i in (0, 7, 8, 44):
+        Ac, Bc, dc = o.get_continuous_jacobians(X[i], U[i])
+        H, c = o.get_observer_jacobians(X[i])
+        assert relerr(out['A'][i].cpu().numpy(), Ac) < TOL and relerr(out['H'][i].cpu().numpy(), H) < TOL
+        assert d_ok(out["d"][i].cpu().numpy(), dc, o, X[i], U[i], dt=1.0)
+        assert np.abs(out['c'][i].cpu().numpy() - c).max() <= 1e-9 * max(1.0, np.abs(o.C_map(X[i])).max())
+        assert relerr(out['z'][i].cpu().numpy(), o.x_to_zfyf(X[i][None, :], zf=True)[0]) < TOL

@@ -8,7 +8,8 @@ independent solves per GPU, horizon 100, Gauss-Newton tracking of randomised fig
 batched solve of the whole batch (ONE launch of ilqr_solve_kernel).  Metric: iLQR solves/s (whole job).
 
   value      : device-resident inputs, CUDA events on the launching stream, L2 flushed between steps (untimed).
-  e2e        : the public host API path -- pinned host buffers, H2D of x0 / targets, solve, D2H of x, u, K, cost.
+  e2e        : the public host API path -- pinned host buffers, H2D of x0 / targets, solve, D2H of x, u, K, cost, every
+               step; double-buffered (the D2H of step i overlaps the solve of step i + 1, iLQR.solve_pinned_stream).
   roofline   : algorithmic FP64 flops of the solve kernel / its event time against the measured cuBLAS DGEMM rate.
   strong     : (N > 1) the SAME 4096 problems split across the N ranks (BASELINE configs[2] "sharded across 1/2/4/8
                GPUs"), measured in the same run next to the weak-scaling `value` (4096 per GPU, same seed per rank).
@@ -259,10 +260,16 @@ def run_ilqr(args, rank, world, dev_index):
     outs_h = None
     for _ in range(2):
         outs_h = solver.solve_pinned(x0_h, zt_h, outs_h)
+    for outs_h in solver.solve_pinned_stream([(x0_h, zt_h)] * 3):
+        pass
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        outs_h = solver.solve_pinned(x0_h, zt_h, outs_h)
+    # every step: H2D of its inputs from pinned memory, the solve, D2H of its results into pinned memory; the D2H of step i
+    # overlaps the solve of step i + 1 (iLQR.solve_pinned_stream), the last one is drained inside the timed region
+    n_out = 0
+    for outs_h in solver.solve_pinned_stream([(x0_h, zt_h)] * args.steps):
+        n_out += 1
+    assert n_out == args.steps
     barrier()
     t_e2e = time.perf_counter() - t0
     h2d = x0_h.numel() * 8 + zt_h.numel() * 8

@@ -66,11 +66,15 @@ struct Frag { double c0, c1; };
 // the clock64 distance between consecutive marks to a global table.  0..7 forward step, 8..15 backward step.
 #ifdef SRCB_PHASE_TIMING
 __device__ unsigned long long g_phase[32];
-#define PH_DECL long long ph_t = clock64()
-#define PH(i) do { const long long ph_n = clock64(); if (lane == 0) atomicAdd(&g_phase[i], (unsigned long long)(ph_n - ph_t)); ph_t = clock64(); } while (0)
+// per-warp accumulation in registers, one atomic per phase and PASS (not per step: 2368 warps hammering 14 words would
+// distort the loaded measurement)
+#define PH_DECL long long ph_t = clock64(); long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PH(i) do { const long long ph_n = clock64(); ph_acc[(i) & 7] += ph_n - ph_t; ph_t = ph_n; } while (0)
+#define PH_FLUSH(base) do { if (lane == 0) { _Pragma("unroll") for (int ph_i = 0; ph_i < 8; ++ph_i) if (ph_acc[ph_i]) atomicAdd(&g_phase[(base) + ph_i], (unsigned long long)ph_acc[ph_i]); } } while (0)
 #else
 #define PH_DECL
 #define PH(i)
+#define PH_FLUSH(base)
 #endif
 
 // Reciprocal without the slow-path branch of __drcp_rn (which splits the basic block and keeps the scheduler from
@@ -696,6 +700,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
         __syncwarp();
         PH(6);
     }
+    PH_FLUSH(0);
     // cost = sum over the input / output lanes of their quadratic terms, halved (every term of ilqr.py:164-175 carries 1/2)
     if (!lu) cacc = 0.0;
 #pragma unroll
@@ -981,6 +986,7 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
             PH(13);
             // the (K | k) tile is W next step: its column 7 must be zero again, rows >= M too (they are: K rows >= M = 0)
         }
+        PH_FLUSH(8);
         rho_update(cf, false, rho, drho);         // ilqr.py:298 -- after a complete AND after an interrupted sweep
     }
     return BwdResult{rho, drho, pd_fail};
@@ -1021,9 +1027,12 @@ __device__ __forceinline__ void queue_push(int* q, int cap, int lane, int id, in
     if (lane == 0) push_one(q, cap, id, cls);
 }
 
-constexpr int shape_warps(int cr) { return cr == 1 ? 12 : 8; }
-template <int M, int CR>
-__global__ void __launch_bounds__(shape_warps(CR) * 32, CR == 0 ? 2 : 1)
+// launch shape S: 0 = 2 CTAs x 8 warps, table in shared memory; 1 = 12 warps, one row in registers; 2 = 8 warps, two rows;
+// 3 = 12 warps, table in shared memory (168 registers: room for the software-pipelined table loads)
+constexpr int shape_warps(int s) { return (s == 1 || s == 3) ? 12 : 8; }
+constexpr int shape_rows(int s) { return s == 3 ? 0 : s; }
+template <int M, int S>
+__global__ void __launch_bounds__(shape_warps(S) * 32, S == 0 ? 2 : 1)
 ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__ IlqrArgs a) {
     build_tables(Mdl, a.Q, a.R, a.Qf, g_sm, M);
     Ctx c;
@@ -1065,7 +1074,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
             for (int e = lane; e < N * M; e += 32) nom.u[e] = a.u_init ? a.u_init[b * (long long)N * M + e] : 0.0;
             __syncwarp();
             __threadfence_block();
-            cost = fwd_dispatch<M, CR>(c, a, discr, nom.x, nom.u, 1.0, nullptr, nullptr, tr0, ztar, ulast);
+            cost = fwd_dispatch<M, (S == 3 ? 0 : S)>(c, a, discr, nom.x, nom.u, 1.0, nullptr, nullptr, tr0, ztar, ulast);
             if (a.ocost0 && lane == 0) a.ocost0[b] = cost;
             // priority class: initial cost above the running mean of the batch -> expected to need many iterations
             cls = 1;
@@ -1092,7 +1101,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
                 double cost_t = cost, alpha_acc = 0.0;
                 while (!improved && !failed) {
                     improved = true;
-                    cost_t = fwd_dispatch<M, CR>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
+                    cost_t = fwd_dispatch<M, (S == 3 ? 0 : S)>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
                     ++trials;
                     double dc = 0.0;
                     const double a2 = __dmul_rn(__dmul_rn(alpha, alpha), 0.5);
@@ -1778,7 +1787,7 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
     // 8 warps, 255 registers, rows `lane` and `32 + lane` in registers (each warp ~1.8 x faster, half as many run).  Small
     // batches are spread over the SMs: the task queue feeds any number of warps.
     const char* shp = getenv("SRCB200_ILQR_SHAPE");
-    const int cr = (shp && shp[0] >= '0' && shp[0] <= '2') ? shp[0] - '0' : 0;
+    const int cr = (shp && shp[0] >= '0' && shp[0] <= '3') ? shp[0] - '0' : 0;
     const int nw = fast::shape_warps(cr);
     const size_t smem = sizeof(double) * (fast::SH_END + nw * fast::W_SIZE);
     const long long slots = (long long)sms * (cr == 0 ? 2 : 1);
@@ -1793,8 +1802,8 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
                                        (int)smem));                                                                        \
         fast::ilqr_ssm_fast_kernel<MM, CRR><<<grid, nw * 32, smem, st>>>(M, a);                                            \
     } while (0)
-    if (M.m == 8) { if (cr == 0) SRCB_LAUNCH_SHAPE(8, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(8, 1); else SRCB_LAUNCH_SHAPE(8, 2); }
-    else          { if (cr == 0) SRCB_LAUNCH_SHAPE(4, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(4, 1); else SRCB_LAUNCH_SHAPE(4, 2); }
+    if (M.m == 8) { if (cr == 0) SRCB_LAUNCH_SHAPE(8, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(8, 1); else if (cr == 2) SRCB_LAUNCH_SHAPE(8, 2); else SRCB_LAUNCH_SHAPE(8, 3); }
+    else          { if (cr == 0) SRCB_LAUNCH_SHAPE(4, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(4, 1); else if (cr == 2) SRCB_LAUNCH_SHAPE(4, 2); else SRCB_LAUNCH_SHAPE(4, 3); }
 #undef SRCB_LAUNCH_SHAPE
     SRCB_LAUNCH_CHECK("ilqr_ssm_fast_kernel");
     *handled = true;

@@ -262,6 +262,27 @@ def test_launch_shapes_of_the_fast_kernel_agree(m, monkeypatch):
             assert relerr(a, b) < 1e-12
 
 
+def test_pinned_stream_api_equals_single_calls():
+    """iLQR.solve_pinned_stream (double-buffered D2H) returns, batch by batch, exactly what solve_pinned returns."""
+    import torch
+    import sofacontrol_b200.synth as synth
+    _, model = _ssm(8)
+    ws = [synth.trunk_ilqr_batch(16, N=20, seed=s_, m=8) for s_ in (1, 2, 3, 4, 5)]
+    s = _solver(model, 8, ws[0]['z_target'])
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    batches = [(pin(w['x0']), pin(w['z_target'])) for w in ws]
+    single = []
+    for x0h, zth in batches:
+        o = s.solve_pinned(x0h, zth)
+        single.append({k: v.clone() for k, v in o.items()})
+    n = 0
+    for o, ref in zip(s.solve_pinned_stream(batches), single):
+        for k in ref:
+            assert torch.equal(o[k], ref[k]), k
+        n += 1
+    assert n == len(batches)
+
+
 def test_receding_horizon_closed_loop_matches_oracle_loop():
     """Config-4 driver (receding-horizon iLQR with shifted warm start + u_last) vs the same loop written with the
     numpy oracle solver and model, noise-free, small case."""

@@ -775,6 +775,35 @@ def _cpu_tpwl_worker(args):
     return len(idx) * N, time.perf_counter() - t0
 
 
+def _cpu_tpwl_weighting_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    idx, N = args
+    import sofacontrol_b200.synth as synth
+    from oracle.tpwl_np import TPWLATVNP
+    data, Hf = synth.tpwl_bank()
+    o = TPWLATVNP(data, params={'tpwl_method': 'weighting', 'dist_weights': {'q': 1.0, 'v': 0.0}, 'beta_weighting': 25.0},
+                  Hf=Hf, discr_method='fe')
+    x0, u = synth.tpwl_rollout_batch(max(idx) + 1, N=N, seed=2)
+    t0 = time.perf_counter()
+    for b in idx:
+        o.rollout(x0[b], u[b], 0.01)
+    return len(idx) * N, time.perf_counter() - t0
+
+
+def _cpu_ssm_rollout_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    count, N, seed = args
+    import sofacontrol_b200.synth as synth
+    from oracle.ssm_np import SSMDynamicsNP
+    s = synth.trunk_ssm(8)
+    o = SSMDynamicsNP(s['z_ref'], discrete=False, discr_method='be', model=s['model'], params=s['params'])
+    rng = np.random.default_rng(seed)
+    t0 = time.perf_counter()
+    for _ in range(count):
+        o.rollout(0.05 * rng.normal(size=6), rng.uniform(0, 800, size=(N, 8)), 0.02)
+    return count * N, time.perf_counter() - t0
+
+
 def _cpu_ssm_eval_worker(args):
     os.environ["OMP_NUM_THREADS"] = "1"
     count, seed = args
@@ -805,6 +834,14 @@ def secondary_cpu_baseline(name):
         v = _cpu_pool(_cpu_tpwl_worker, [(list(range(c * 2, c * 2 + 2)), 100) for c in range(cores)])
         return {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
                 "sample": "2 trajectories x 100 steps per core of the same seeded batch (oracle/tpwl_np.py, numpy)"}
+    if name == "tpwl_rollout_weighting":
+        v = _cpu_pool(_cpu_tpwl_weighting_worker, [([c], 40) for c in range(cores)])
+        return {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                "sample": "1 trajectory x 40 steps per core, method weighting, fe per step (oracle/tpwl_np.py, numpy)"}
+    if name == "ssm_rollout":
+        v = _cpu_pool(_cpu_ssm_rollout_worker, [(2, 100, c) for c in range(cores)])
+        return {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                "sample": "2 trajectories x 100 steps per core, be discretisation (oracle/ssm_np.py, numpy)"}
     if name == "ssm_eval":
         v = _cpu_pool(_cpu_ssm_eval_worker, [(400, c) for c in range(cores)])
         return {"value": v, "unit": "states/s", "cores": cores, "kind": "port",
@@ -870,9 +907,12 @@ def main():
         # the other kernels of the path, outside the headline's timed region (their own events, warm-up and L2 policy)
         import copy
         sec = {}
-        for name, steps in (("tpwl_rollout_nn", 5), ("ssm_eval", 5), ("pod_gram", 2), ("mpc", 1)):
+        for name, steps in (("tpwl_rollout_nn", 5), ("tpwl_rollout_weighting", 2), ("ssm_eval", 5), ("ssm_rollout", 5),
+                            ("ilqr_tpwl", 2), ("pod_gram", 2), ("mpc", 1)):
             a2 = copy.copy(args)
             a2.batch, a2.steps, a2.warmup, a2.horizon = 4096, steps, 3, 100
+            if name == "ilqr_tpwl":
+                a2.batch, a2.warmup = 1184, 1                # 8 problems per SM: the Diamond TPWL solver runs one CTA per problem
             a2.mpc_steps = 25
             try:
                 r2 = runners[name](a2, rank, world, local)

@@ -52,7 +52,6 @@ constexpr int SH_END = SH_FIDX + 44;
 constexpr int W_PHI = 0;                        // psi slots 0..29 (see NJ), then PV[72]: x_j * value part of row o at W_PHI + 32
 constexpr int W_PV = 32;                        // 72 (+0)
 constexpr int W_X = 104;                        // x_t (6), X[6] = 0, X[7] = 1
-constexpr int W_U = 112;                        // rollout kernel: u_t ; backward pass: 2 x 8 doubles of pivot-column broadcast
 constexpr int W_DC = 128;                       // d_c (rollout kernel) / c_u (backward pass)
 constexpr int W_DD = 136;                       // d_d (rollout kernel) / du (backward pass)
 constexpr int W_TILES = 144;
@@ -185,11 +184,6 @@ __device__ void build_tables(const SsmDev& M, const double* Qg, const double* Rg
     __syncthreads();
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Model evaluation at the state in X: fills psi, then A_c -> tile AC, H -> record Hg, and returns in lanes 8..13 the
-// polynomial part of f_i (i = lane - 8) and in lanes 14..19 the raw output z_i (i = lane - 14).
-// Row o = 32 r + lane of the Jacobian table is handled by `lane` in round r (r = 2: lanes < 8).
-// ---------------------------------------------------------------------------------------------------------------
 struct Scatter { int o0, o1, o2; };   // per-lane tile offsets of the Jacobian outputs of rounds 0, 1, 2
 
 __device__ __forceinline__ Scatter make_scatter(int lane) {
@@ -198,84 +192,6 @@ __device__ __forceinline__ Scatter make_scatter(int lane) {
     s.o1 = ((32 + lane) / 6) * LD + (32 + lane) % 6;                     // A_c, o = 32 + lane (lanes < 4)
     s.o2 = 0;
     return s;
-}
-
-__device__ __forceinline__ double ssm_eval_fast(const Ctx c, const Scatter sc, double* __restrict__ AC,
-                                                double* __restrict__ Hg) {
-    const int lane = c.lane;
-    double* PSI = CTX_WS(c) + W_PHI;
-    double* PV = CTX_WS(c) + W_PV;
-    const double* X = CTX_WS(c) + W_X;
-    const int* fidx = reinterpret_cast<const int*>(CTX_SH + SH_FIDX);
-    // psi: slots 2..7 = x, slots 8..28 = the 21 quadratic monomials x_a x_b (phi_6..phi_26 of ssm.py:158-164)
-    if (lane < 21) {
-        const int pk = fidx[6 + lane];
-        PSI[8 + lane] = __dmul_rn(X[pk & 7], X[(pk >> 3) & 7]);
-    } else if (lane < 27) {
-        PSI[2 + lane - 21] = X[lane - 21];
-    }
-    const double xj0 = X[lane % 6], xj1 = X[(32 + lane) % 6], xj2 = X[(64 + lane) % 6];
-    __syncwarp();
-    const double* T = CTX_SH + SH_T;
-    const double* t0 = T + lane * TS;
-    const double* t1 = T + (32 + lane) * TS;
-    const double* t2 = T + (lane < 8 ? 64 + lane : 72) * TS;             // lanes >= 8: the zero row (one broadcast read)
-    // degree 1: the coefficient itself
-    double g10, g11, g12;
-    {
-        const double2 c0 = *reinterpret_cast<const double2*>(t0);
-        const double2 c1 = *reinterpret_cast<const double2*>(t1);
-        const double2 c2 = *reinterpret_cast<const double2*>(t2);
-        g10 = c0.x; g11 = c1.x; g12 = c2.x;
-    }
-    // degree 2: slots 2..7 (even / odd accumulators)
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
-#pragma unroll
-    for (int q = 2; q < 8; q += 2) {
-        const double2 ps = *reinterpret_cast<const double2*>(PSI + q);
-        const double2 c0 = *reinterpret_cast<const double2*>(t0 + q);
-        const double2 c1 = *reinterpret_cast<const double2*>(t1 + q);
-        const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
-        a0 = fma(c0.x, ps.x, a0); b0 = fma(c0.y, ps.y, b0);
-        a1 = fma(c1.x, ps.x, a1); b1 = fma(c1.y, ps.y, b1);
-        a2 = fma(c2.x, ps.x, a2); b2 = fma(c2.y, ps.y, b2);
-    }
-    const double g20 = __dadd_rn(a0, b0), g21 = __dadd_rn(a1, b1), g22 = __dadd_rn(a2, b2);
-    // degree 3: slots 8..29
-    a0 = a1 = a2 = b0 = b1 = b2 = 0.0;
-#pragma unroll
-    for (int q = 8; q < NJ; q += 2) {
-        const double2 ps = *reinterpret_cast<const double2*>(PSI + q);
-        const double2 c0 = *reinterpret_cast<const double2*>(t0 + q);
-        const double2 c1 = *reinterpret_cast<const double2*>(t1 + q);
-        const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
-        a0 = fma(c0.x, ps.x, a0); b0 = fma(c0.y, ps.y, b0);
-        a1 = fma(c1.x, ps.x, a1); b1 = fma(c1.y, ps.y, b1);
-        a2 = fma(c2.x, ps.x, a2); b2 = fma(c2.y, ps.y, b2);
-    }
-    const double g30 = __dadd_rn(a0, b0), g31 = __dadd_rn(a1, b1), g32 = __dadd_rn(a2, b2);
-    // Jacobian entries: A_c into its tile, H_t straight to the trajectory record
-    const double j0 = __dadd_rn(__dadd_rn(g10, g20), g30);
-    const double j1 = __dadd_rn(__dadd_rn(g11, g21), g31);
-    const double j2 = __dadd_rn(__dadd_rn(g12, g22), g32);
-    AC[sc.o0] = j0;
-    if (lane < 4) AC[sc.o1] = j1; else if (Hg) Hg[lane - 4] = j1;
-    if (lane < 8 && Hg) Hg[28 + lane] = j2;
-    // values by Euler's theorem: x_j (g1 + g2 / 2 + g3 / 3) summed over the six columns j of an output row
-    constexpr double third = 1.0 / 3.0;
-    PV[lane] = __dmul_rn(xj0, __dadd_rn(__dadd_rn(g10, __dmul_rn(0.5, g20)), __dmul_rn(third, g30)));
-    PV[32 + lane] = __dmul_rn(xj1, __dadd_rn(__dadd_rn(g11, __dmul_rn(0.5, g21)), __dmul_rn(third, g31)));
-    if (lane < 8) PV[64 + lane] = __dmul_rn(xj2, __dadd_rn(__dadd_rn(g12, __dmul_rn(0.5, g22)), __dmul_rn(third, g32)));
-    __syncwarp();
-    double val = 0.0;
-    if (lane >= 8 && lane < 20) {
-        const double* pv = PV + 6 * (lane - 8);
-        const double2 p01 = *reinterpret_cast<const double2*>(pv);
-        const double2 p23 = *reinterpret_cast<const double2*>(pv + 2);
-        const double2 p45 = *reinterpret_cast<const double2*>(pv + 4);
-        val = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(p01.x, p01.y), p23.x), p23.y), p45.x), p45.y);
-    }
-    return val;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -321,34 +237,6 @@ __device__ __forceinline__ void gj6_pair(double (&col)[6], int lane, double* __r
 #pragma unroll
         for (int r = 0; r < 6; ++r) dst[r * LD + (j - 6)] = col[r];
     }
-}
-
-// inv(Q_uu~) (M x M, no pivoting) + PD test from the pivots.  Reads the matrix from `tile`, writes the inverse back.
-template <int M>
-__device__ __forceinline__ bool gj_spd(double* __restrict__ tile, int lane) {
-    double col[M];
-    const int j = lane;
-#pragma unroll
-    for (int r = 0; r < M; ++r) col[r] = (j < M) ? tile[r * LD + j] : ((j - M == r) ? 1.0 : 0.0);
-    bool pd = true;
-#pragma unroll
-    for (int c = 0; c < M; ++c) {
-        double cc[M];
-#pragma unroll
-        for (int r = 0; r < M; ++r) cc[r] = __shfl_sync(FULL, col[r], c);
-        const double piv = cc[c];
-        pd = pd && (piv > 0.0) && !isinf(piv);
-        const double pc = __dmul_rn(col[c], __drcp_rn(piv));
-#pragma unroll
-        for (int r = 0; r < M; ++r) col[r] = (r == c) ? pc : fma(-cc[r], pc, col[r]);
-    }
-    __syncwarp();
-    if (j >= M && j < 2 * M) {
-#pragma unroll
-        for (int r = 0; r < M; ++r) tile[r * LD + (j - M)] = col[r];
-    }
-    __syncwarp();
-    return pd;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -503,7 +391,9 @@ __device__ __forceinline__ double ssm_eval_lean(const Ctx c, const Scatter sc, c
     return val;
 }
 
-template <int M, int DISCR, int CR>
+// REC = false: open-loop rollout (ssm.py:134-156) -- no cost, no gains, no trajectory record: tr.x receives the states,
+// tr.e the outputs z_t (instead of the output errors), nothing else is written.
+template <int M, int DISCR, int CR, bool REC = true>
 __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const double* nx, const double* nu,
                                         double alpha, const double* K, const double* k, const Rec tr,
                                         const double* __restrict__ ztar, const double* __restrict__ ulast) {
@@ -550,7 +440,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
         if (K) { pK0 = K[g * 6 + q]; if (q < 2) pK1 = K[g * 6 + 4 + q]; }
         if (lu) { p_nu = nu[g]; if (k) p_k = k[g]; }
     }
-    if (lu && g < 6) p_zt = ztar[g];
+    if (REC && lu && g < 6) p_zt = ztar[g];
     __syncwarp();
 
     PH_DECL;
@@ -572,7 +462,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
                 du = inc ? __dsub_rn(u, up) : u;
                 VT[g * LD + 1] = u;
                 VT[g * LD + 3] = du;
-                if (g < M) tr.u[t * M + g] = u;
+                if (REC && g < M) tr.u[t * M + g] = u;
             }
         }
         PH(0);
@@ -587,21 +477,24 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
                 if (lu) { p_nu = nu[(t + 1) * M + g]; if (k) p_k = k[(t + 1) * M + g]; }
             }
             if (K && lf) p_nx = nx[(t + 1) * 6 + g];
-            if (lu && g < 6) p_zt = ztar[(t + 1) * 6 + g];
+            if (REC && lu && g < 6) p_zt = ztar[(t + 1) * 6 + g];
         }
         // model at x_t
         PH(1);
-        const double val = ssm_eval_lean<CR>(c, sc, ca, cb, AC, AUX, s_aux, d0, d1, tr.H + (long long)t * 36);
+        // (rollout: the observer Jacobian goes to a scratch tile instead of a record)
+        const double val = ssm_eval_lean<CR>(c, sc, ca, cb, AC, AUX, s_aux, d0, d1,
+                                             REC ? tr.H + (long long)t * 36 : ws + W_TILES + 8 * TILE);
         PH(2);
         double e = 0.0;
         if (lu && g < 6) {
-            e = __dsub_rn(__dadd_rn(val, zr), zt_now);
-            VT[g * LD + 2] = e;
-            tr.e[t * 6 + g] = e;
+            e = REC ? __dsub_rn(__dadd_rn(val, zr), zt_now) : __dadd_rn(val, zr);
+            if (REC) VT[g * LD + 2] = e;
+            if (REC || tr.e) tr.e[t * 6 + g] = e;
         }
         __syncwarp();   // A_c, aux tile, u, e, du visible
         const double vb0 = VT[q * LD + g], vb1 = VT[(4 + q) * LD + g];   // B fragment of the vector tile
         if (last) {
+            if (!REC) break;
             // terminal cost .5 e^T Qf e (ilqr.py:164-166)
             Frag fq{0.0, 0.0};
             dmma(fq, Qft[q * LD + g], vb0);
@@ -613,15 +506,17 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
         Frag fax{0.0, 0.0}, fbu{0.0, 0.0}, fq{0.0, 0.0}, fr{0.0, 0.0};
         dmma(fax, AC[g * LD + q], vb0);        dmma(fax, AC[g * LD + 4 + q], vb1);
         dmma(fbu, Brt[g * LD + q], vb0);       dmma(fbu, Brt[g * LD + 4 + q], vb1);
-        dmma(fq, Qt[q * LD + g], vb0);         dmma(fq, Qt[(4 + q) * LD + g], vb1);
-        dmma(fr, Rt[q * LD + g], vb0);         dmma(fr, Rt[(4 + q) * LD + g], vb1);
+        if (REC) {
+            dmma(fq, Qt[q * LD + g], vb0);         dmma(fq, Qt[(4 + q) * LD + g], vb1);
+            dmma(fr, Rt[q * LD + g], vb0);         dmma(fr, Rt[(4 + q) * LD + g], vb1);
+        }
         double dc = 0.0;
         if (lf) {
             // f = r phi + B u,  d_c = (f - A_c x) - B u
             dc = __dsub_rn(__dsub_rn(__dadd_rn(val, fbu.c1), fax.c0), fbu.c1);
             *reinterpret_cast<double2*>(VT2 + g * LD) = make_double2(dc, fbu.c1);
         }
-        if (lu) cacc = fma(fr.c1, du, fma(fq.c0, e, cacc));
+        if (REC && lu) cacc = fma(fr.c1, du, fma(fq.c0, e, cacc));
         double xn = 0.0;
         PH(3);
         if (IMPL) {
@@ -661,7 +556,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
                 dmma(s, IA[g * LD + 4 + q], bv1);
             }
             store_frag(SP, s, g, q);
-            if (g < 6 && q < 3)
+            if (REC && g < 6 && q < 3)
                 *reinterpret_cast<double2*>(tr.A + (long long)t * 36 + g * 6 + 2 * q) = *reinterpret_cast<const double2*>(AD + g * LD + 2 * q);
             __syncwarp();
             PH(5);
@@ -671,7 +566,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
             dmma(bd, sa0, Brt[q * LD + g]);       dmma(bd, sa1, Brt[(4 + q) * LD + g]);
             dmma(sv, sa0, VT2[q * LD + g]);       dmma(sv, sa1, VT2[(4 + q) * LD + g]);
             dmma(ax, AD[g * LD + q], vb0);        dmma(ax, AD[g * LD + 4 + q], vb1);
-            if (g < 6 && 2 * q < M)
+            if (REC && g < 6 && 2 * q < M)
                 *reinterpret_cast<double2*>(tr.B + (long long)t * 6 * M + g * M + 2 * q) = make_double2(bd.c0, bd.c1);
             if (lf) xn = __dadd_rn(__dadd_rn(ax.c0, sv.c1), sv.c0);
         } else {
@@ -681,9 +576,9 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
             dmma(ax, AD[g * LD + q], vb0);        dmma(ax, AD[g * LD + 4 + q], vb1);
             dmma(bu, __dmul_rn(sb, Brt[g * LD + q]), vb0);
             dmma(bu, __dmul_rn(sb, Brt[g * LD + 4 + q]), vb1);
-            if (g < 6 && q < 3)
+            if (REC && g < 6 && q < 3)
                 *reinterpret_cast<double2*>(tr.A + (long long)t * 36 + g * 6 + 2 * q) = *reinterpret_cast<const double2*>(AD + g * LD + 2 * q);
-            if (g < 6 && 2 * q < M) {
+            if (REC && g < 6 && 2 * q < M) {
                 const double2 b2 = *reinterpret_cast<const double2*>(Brt + g * LD + 2 * q);
                 *reinterpret_cast<double2*>(tr.B + (long long)t * 6 * M + g * M + 2 * q) = make_double2(__dmul_rn(sb, b2.x), __dmul_rn(sb, b2.y));
             }
@@ -1175,9 +1070,10 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
 // Open-loop rollout (ssm.py:134-156) for the same model shape: one warp per trajectory, re-linearised every step.
 // ---------------------------------------------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(WARPS * 32, 1)
-ssm_rollout_fast_kernel(const __grid_constant__ SsmDev Mdl, long long batch, int N, const double* __restrict__ x0,
-                        const double* __restrict__ u, double dt, double* __restrict__ xo, double* __restrict__ zo) {
+__global__ void __launch_bounds__(WARPS * 32, 2)
+ssm_rollout_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__ IlqrArgs a, long long batch,
+                        const double* __restrict__ x0, const double* __restrict__ u, double* __restrict__ xo,
+                        double* __restrict__ zo) {
     build_tables(Mdl, nullptr, nullptr, nullptr, g_sm, M);
     Ctx c;
     c.lane = threadIdx.x & 31;
@@ -1186,122 +1082,21 @@ ssm_rollout_fast_kernel(const __grid_constant__ SsmDev Mdl, long long batch, int
     c.off0 = (c.lane / 6) * LD + c.lane % 6;
     c.off1 = ((32 + c.lane) / 6) * LD + (32 + c.lane) % 6;
     c.ws_off = SH_END + (threadIdx.x >> 5) * W_SIZE;
-    const int lane = c.lane, g = c.g, q = c.q, discr = Mdl.discr;
-    double* ws = CTX_WS(c);
-    double* X = ws + W_X;   double* U = ws + W_U;   double* DC = ws + W_DC;  double* DD = ws + W_DD;
-    double* AC = ws + W_TILES + 0 * TILE;  double* AD = ws + W_TILES + 1 * TILE;  double* IA = ws + W_TILES + 2 * TILE;
-    double* SP = ws + W_TILES + 3 * TILE;  double* BD = ws + W_TILES + 4 * TILE;  double* W0 = ws + W_TILES + 5 * TILE;
-    const double* Brt = CTX_SH + SH_BR; const double* zref = CTX_SH + SH_ZREF;
-    const Scatter sc = make_scatter(lane);
-    const int bo0 = (lane / M) * LD + lane % M, bo1 = ((32 + lane) / M) * LD + (32 + lane) % M;
-
-    // every trajectory costs the same: static striding is perfectly balanced, no work counter needed
+    const int N = a.N, discr = Mdl.discr;
+    // every trajectory costs the same: static striding is perfectly balanced, no work counter needed.  The step is the
+    // iLQR kernel's lean forward step without cost, gains and record (fwd_lean<.., REC = false>).
     for (long long b = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); b < batch; b += (long long)gridDim.x * WARPS) {
+        Rec tr;
+        tr.x = xo + b * (long long)(N + 1) * 6;
+        tr.e = zo ? zo + b * (long long)(N + 1) * 6 : nullptr;
+        tr.u = nullptr; tr.H = nullptr; tr.A = nullptr; tr.B = nullptr; tr.idx = nullptr;
+        const double* xb = x0 + b * 6;
         const double* ub = u + b * (long long)N * M;
-        double* xb = xo + b * (long long)(N + 1) * 6;
-        double* zb = zo ? zo + b * (long long)(N + 1) * 6 : nullptr;
-        for (int t = 0; t < 6; ++t) zero_tile(ws + W_TILES + t * TILE, lane);
-        if (lane < 8) { X[lane] = lane < 6 ? x0[b * 6 + lane] : (lane == 7 ? 1.0 : 0.0); U[lane] = 0.0; DC[lane] = 0.0; }
-        if (lane < 6) xb[lane] = x0[b * 6 + lane];
-        if (lane < 3) ws[W_PHI + (lane == 0 ? 0 : (lane == 1 ? 1 : 29))] = (lane == 0) ? 1.0 : 0.0;
-        double p_u = (lane < M && N > 0) ? ub[lane] : 0.0;
-        __syncwarp();
-        for (int t = 0; t <= N; ++t) {
-            const bool last = (t == N);
-            if (!last && lane < M) U[lane] = p_u;
-            if (t + 1 < N && lane < M) p_u = ub[(t + 1) * M + lane];
-            const double val = ssm_eval_fast(c, sc, AC, nullptr);
-            if (zb && lane >= 14 && lane < 20) zb[t * 6 + lane - 14] = __dadd_rn(val, zref[lane - 14]);
-            __syncwarp();
-            if (last) break;
-            if (lane >= 8 && lane < 14) {
-                const int i = lane - 8;
-                double bu = 0.0, ax = 0.0;
-#pragma unroll
-                for (int jj = 0; jj < M; ++jj) bu = fma(Brt[i * LD + jj], U[jj], bu);
-#pragma unroll
-                for (int kk = 0; kk < 6; ++kk) ax = fma(AC[i * LD + kk], X[kk], ax);
-                DC[i] = __dsub_rn(__dsub_rn(__dadd_rn(val, bu), ax), bu);
-            }
-            if (discr == SRCB200_DISCR_BE || discr == SRCB200_DISCR_BIL) {
-                const double h = (discr == SRCB200_DISCR_BE) ? dt : 0.5 * dt;
-                const int hm = lane >> 4, j = lane & 15;
-                double col[6];
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    double v = 0.0;
-                    if (j < 6) {
-                        const double av = AC[r * LD + j];
-                        v = hm ? av : __dsub_rn(r == j ? 1.0 : 0.0, __dmul_rn(h, av));
-                    } else if (j < 12) {
-                        v = (r == j - 6) ? 1.0 : 0.0;
-                    }
-                    col[r] = v;
-                }
-                gj6_pair(col, lane, hm ? IA : (discr == SRCB200_DISCR_BE ? AD : W0));
-                __syncwarp();
-                if (discr == SRCB200_DISCR_BIL) {
-                    Frag f{0.0, 0.0};
-#pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        const int kk = 4 * s + q;
-                        const double av = (g < 6 && kk < 6) ? __dadd_rn(g == kk ? 1.0 : 0.0, __dmul_rn(h, AC[g * LD + kk])) : 0.0;
-                        dmma(f, av, W0[kk * LD + g]);
-                    }
-                    store_frag(AD, f, g, q);
-                    __syncwarp();
-                }
-                Frag s{0.0, 0.0};
-#pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    const int kk = 4 * s2 + q;
-                    const double bv = (kk < 6 && g < 6) ? __dsub_rn(AD[kk * LD + g], kk == g ? 1.0 : 0.0) : 0.0;
-                    dmma(s, IA[g * LD + kk], bv);
-                }
-                store_frag(SP, s, g, q);
-                __syncwarp();
-                Frag bf{0.0, 0.0};
-                mma88<false, false>(bf, SP, Brt, g, q);
-                store_frag(BD, bf, g, q);
-                if (lane < 6) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int kk = 0; kk < 6; ++kk) acc = fma(SP[lane * LD + kk], DC[kk], acc);
-                    DD[lane] = acc;
-                }
-            } else {
-                __syncwarp();
-                if (discr == SRCB200_DISCR_FE) {
-                    const double v0 = __dmul_rn(dt, AC[c.off0]);
-                    AD[c.off0] = (lane / 6 == lane % 6) ? __dadd_rn(1.0, v0) : v0;
-                    if (lane < 4) {
-                        const double v1 = __dmul_rn(dt, AC[c.off1]);
-                        AD[c.off1] = (lane == 3) ? __dadd_rn(1.0, v1) : v1;
-                    }
-                    if (lane < 6 * M) BD[bo0] = __dmul_rn(dt, Brt[bo0]);
-                    if (32 + lane < 6 * M) BD[bo1] = __dmul_rn(dt, Brt[bo1]);
-                    if (lane < 6) DD[lane] = __dmul_rn(dt, DC[lane]);
-                } else {
-                    AD[c.off0] = AC[c.off0];
-                    if (lane < 4) AD[c.off1] = AC[c.off1];
-                    if (lane < 6 * M) BD[bo0] = Brt[bo0];
-                    if (32 + lane < 6 * M) BD[bo1] = Brt[bo1];
-                    if (lane < 6) DD[lane] = DC[lane];
-                }
-            }
-            __syncwarp();
-            double xn = 0.0;
-            if (lane < 6) {
-                double ax = 0.0, bu = 0.0;
-#pragma unroll
-                for (int kk = 0; kk < 6; ++kk) ax = fma(AD[lane * LD + kk], X[kk], ax);
-#pragma unroll
-                for (int jj = 0; jj < M; ++jj) bu = fma(BD[lane * LD + jj], U[jj], bu);
-                xn = __dadd_rn(__dadd_rn(ax, bu), DD[lane]);
-            }
-            __syncwarp();
-            if (lane < 6) { X[lane] = xn; xb[(long long)(t + 1) * 6 + lane] = xn; }
-            __syncwarp();
+        switch (discr) {
+            case SRCB200_DISCR_BE:  fwd_lean<M, SRCB200_DISCR_BE, 0, false>(c, a, xb, ub, 1.0, nullptr, nullptr, tr, nullptr, nullptr); break;
+            case SRCB200_DISCR_BIL: fwd_lean<M, SRCB200_DISCR_BIL, 0, false>(c, a, xb, ub, 1.0, nullptr, nullptr, tr, nullptr, nullptr); break;
+            case SRCB200_DISCR_FE:  fwd_lean<M, SRCB200_DISCR_FE, 0, false>(c, a, xb, ub, 1.0, nullptr, nullptr, tr, nullptr, nullptr); break;
+            default:                fwd_lean<M, SRCB200_DISCR_NONE, 0, false>(c, a, xb, ub, 1.0, nullptr, nullptr, tr, nullptr, nullptr); break;
         }
         __syncwarp();
     }
@@ -1749,13 +1544,16 @@ int ssm_rollout_fast_launch(const SsmDev& M, long long batch, int N, const doubl
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long ctas = (batch + fast::WARPS - 1) / fast::WARPS;
-    const int grid = (int)(ctas < (long long)sms ? ctas : (long long)sms);
+    const int grid = (int)(ctas < 2LL * sms ? ctas : 2LL * sms);
+    IlqrArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = 6; a.m = M.m; a.nz = 6; a.N = N; a.batch = batch; a.dt = dt;
     if (M.m == 8) {
         SRCB_CUDA(cudaFuncSetAttribute(fast::ssm_rollout_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
-        fast::ssm_rollout_fast_kernel<8><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, batch, N, x0, u, dt, x, z);
+        fast::ssm_rollout_fast_kernel<8><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, a, batch, x0, u, x, z);
     } else {
         SRCB_CUDA(cudaFuncSetAttribute(fast::ssm_rollout_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast::SMEM_BYTES));
-        fast::ssm_rollout_fast_kernel<4><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, batch, N, x0, u, dt, x, z);
+        fast::ssm_rollout_fast_kernel<4><<<grid, fast::WARPS * 32, fast::SMEM_BYTES, st>>>(M, a, batch, x0, u, x, z);
     }
     SRCB_LAUNCH_CHECK("ssm_rollout_fast_kernel");
     *handled = true;

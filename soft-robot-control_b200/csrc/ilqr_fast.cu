@@ -436,7 +436,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
     double up = (lu && g < M && ulast) ? ulast[g] : 0.0;
     // prefetch registers of step 0: K[0] as an A fragment, nominal u / k in the input lanes, target in the output lanes
     double pK0 = 0.0, pK1 = 0.0, p_nu = 0.0, p_k = 0.0, p_nx = 0.0, p_zt = 0.0;
-    if (g < M) {
+    if (g < M && N > 0) {
         if (K) { pK0 = K[g * 6 + q]; if (q < 2) pK1 = K[g * 6 + 4 + q]; }
         if (lu) { p_nu = nu[g]; if (k) p_k = k[g]; }
     }

@@ -177,12 +177,16 @@ class iLQR:
         torch = L.torch_mod()
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
-        ring = [None] * depth           # (pinned outputs, completion event, device outputs kept alive)
+        # pinned output buffers are allocated once per solver and depth (cudaHostAlloc of 2 x 203 MB is far slower than a solve)
+        cache = getattr(self, '_pin_rings', None)
+        if cache is None:
+            cache = self._pin_rings = {}
+        ring = cache.setdefault(depth, [None] * depth)      # (pinned outputs, completion event, device outputs kept alive)
         pending = []
         for i, (x0_h, zt_h) in enumerate(batches):
             out = self.solve_device(x0_h.cuda(non_blocking=True), zt_h.cuda(non_blocking=True))
             slot = i % depth
-            if ring[slot] is None:
+            if ring[slot] is None or any(ring[slot][0][k].shape != out[k].shape for k in ring[slot][0]):
                 ring[slot] = [{k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
                                for k in ('x', 'u', 'K', 'cost', 'iterations', 'status')}, torch.cuda.Event(), None]
             ready = torch.cuda.Event()

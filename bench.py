@@ -489,6 +489,22 @@ def run_ssm_eval(args, rank, world, dev_index):
         tt = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev = float(tt[0])
+    # e2e: pinned host x / u in, pinned A, d, H, c, z out (a quarter of the states: 0.9 GB of results per step cross PCIe)
+    cnt_e = count // 4
+    xh, uh = x[:cnt_e].cpu().pin_memory(), u[:cnt_e].cpu().pin_memory()
+    outh = None
+    t_e2e = None
+    for rep in range(3):
+        if rep == 1:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        o = g._eval_device(xh.cuda(non_blocking=True), uh.cuda(non_blocking=True), -1.0, 'cont_raw', want)
+        if outh is None:
+            outh = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in o.items()}
+        for k, v in outh.items():
+            v.copy_(o[k], non_blocking=True)
+        torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / 2
     hbm, hsrc, fp64 = measured_peaks()
     ach = count * 13944.0 / (t_dev / args.steps) / 1e12
     byts = count * (14 + 36 + 6 + 36 + 6 + 6) * 8
@@ -497,7 +513,11 @@ def run_ssm_eval(args, rank, world, dev_index):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "Trunk SSM batched evaluation + linearisation: %d states per GPU, outputs A_c, d_c, H, c, z "
                                    "(inputs %.0f MB + outputs %.0f MB per launch: larger than L2)" % (count, count * 14 * 8 / 1e6, byts / 1e6 - count * 14 * 8 / 1e6)},
-            "e2e": None, "gpu_launches": args.steps, "clocks": clk.summary(),
+            "e2e": {"value": cnt_e * world / t_e2e, "unit": "states/s", "h2d_bytes_per_step": int(cnt_e * 14 * 8),
+                    "d2h_bytes_per_step": int(cnt_e * 90 * 8),
+                    "note": "PCIe-bound: 720 B of results per state leave the device; consumers on the device (SCP adapters, "
+                            "iLQR) never take this path"},
+            "gpu_launches": args.steps, "clocks": clk.summary(),
             "roofline": {"kernel": "ssm_eval_sparse_dmma_kernel<8>", "bound": "tensor", "achieved": ach, "peak": fp64, "unit": "TFLOP/s",
                          "frac": ach / fp64, "traffic": None, "hbm_gbs": byts / (t_dev / args.steps) / 1e9,
                          "hbm_frac": byts / (t_dev / args.steps) / 1e9 / hbm,

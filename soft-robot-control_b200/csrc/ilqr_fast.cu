@@ -337,30 +337,43 @@ __device__ __forceinline__ double ssm_eval_lean(const Ctx c, const Scatter sc, c
     const double* t2 = CTX_SH + SH_T + (lane < 8 ? 64 + lane : 72) * TS;   // lanes >= 8: the zero row (one broadcast read)
     const double* t0 = CTX_SH + SH_T + lane * TS;
     const double* t1 = CTX_SH + SH_T + (32 + lane) * TS;
-#define CA(s) (CR >= 1 ? ca[s] : t0[(s) == 0 ? 0 : (s) + 1])
-#define CB(s) (CR >= 2 ? cb[s] : t1[(s) == 0 ? 0 : (s) + 1])
-    const double g10 = CA(0), g11 = CB(0), g12 = t2[0];
-    // degree 2: table slots 2..7 (even / odd accumulators)
+    // The 15 slot pairs are software-pipelined by hand: the 16-byte loads of pair i + 1 (psi and the table rows
+    // lane / 32+lane / 64+lane) are issued, then a __syncwarp(), then the six FMAs of pair i.  The barrier is what pins the
+    // schedule: left to itself (also with ordered volatile loads) ptxas sinks every table load next to its two FMAs and
+    // re-uses one register quad, which serialises a shared-memory latency per FMA pair -- 2.2 k of the 4.9 k cycles of
+    // a lone warp's forward step (tools/phase_clocks.py).
+    auto ld2 = [](const double* p) { return *reinterpret_cast<const double2*>(p); };
+    double2 ps = ld2(PSI + 2), c2 = ld2(t2 + 2), c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
+    if (CR < 1) c0 = ld2(t0 + 2);
+    if (CR < 2) c1 = ld2(t1 + 2);
+    const double g10 = CR >= 1 ? ca[0] : t0[0], g11 = CR >= 2 ? cb[0] : t1[0], g12 = t2[0];
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+    double g20 = 0.0, g21 = 0.0, g22 = 0.0;
 #pragma unroll
-    for (int q = 2; q < 8; q += 2) {
-        const double2 ps = *reinterpret_cast<const double2*>(PSI + q);
-        const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
-        a0 = fma(CA(q - 1), ps.x, a0); b0 = fma(CA(q), ps.y, b0);
-        a1 = fma(CB(q - 1), ps.x, a1); b1 = fma(CB(q), ps.y, b1);
-        a2 = fma(c2.x, ps.x, a2);      b2 = fma(c2.y, ps.y, b2);
-    }
-    const double g20 = __dadd_rn(a0, b0), g21 = __dadd_rn(a1, b1), g22 = __dadd_rn(a2, b2);
-    // degree 3: table slots 8..28 (slot 29 is padding)
-    a0 = a1 = a2 = b0 = b1 = b2 = 0.0;
-#pragma unroll
-    for (int q = 8; q < NJ; q += 2) {
-        const double2 ps = *reinterpret_cast<const double2*>(PSI + q);
-        const double2 c2 = *reinterpret_cast<const double2*>(t2 + q);
-        a0 = fma(CA(q - 1), ps.x, a0);
-        a1 = fma(CB(q - 1), ps.x, a1);
-        if (q + 1 < NJ - 1) { b0 = fma(CA(q), ps.y, b0); b1 = fma(CB(q), ps.y, b1); }
-        a2 = fma(c2.x, ps.x, a2);      b2 = fma(c2.y, ps.y, b2);
+    for (int q = 2; q < NJ; q += 2) {
+        double2 psn = ps, c0n = c0, c1n = c1, c2n = c2;
+        if (q + 2 < NJ) {
+            psn = ld2(PSI + q + 2);
+            if (CR < 1) c0n = ld2(t0 + q + 2);
+            if (CR < 2) c1n = ld2(t1 + q + 2);
+            c2n = ld2(t2 + q + 2);
+            __syncwarp();
+        }
+        const double k0x = CR >= 1 ? ca[q - 1] : c0.x, k1x = CR >= 2 ? cb[q - 1] : c1.x;
+        a0 = fma(k0x, ps.x, a0);
+        a1 = fma(k1x, ps.x, a1);
+        a2 = fma(c2.x, ps.x, a2);
+        if (q + 1 < NJ - 1) {                       // slot 29 is padding
+            const double k0y = CR >= 1 ? ca[q] : c0.y, k1y = CR >= 2 ? cb[q] : c1.y;
+            b0 = fma(k0y, ps.y, b0);
+            b1 = fma(k1y, ps.y, b1);
+        }
+        b2 = fma(c2.y, ps.y, b2);
+        if (q == 6) {                               // end of the degree-2 slots (2..7)
+            g20 = __dadd_rn(a0, b0); g21 = __dadd_rn(a1, b1); g22 = __dadd_rn(a2, b2);
+            a0 = a1 = a2 = b0 = b1 = b2 = 0.0;
+        }
+        ps = psn; c0 = c0n; c1 = c1n; c2 = c2n;
     }
     const double g30 = __dadd_rn(a0, b0), g31 = __dadd_rn(a1, b1), g32 = __dadd_rn(a2, b2);
     const double j0 = __dadd_rn(__dadd_rn(g10, g20), g30);

@@ -1044,7 +1044,11 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
                     trace[it * 4 + 0] = cost;
                     trace[it * 4 + 1] = failed ? 0.0 : alpha_acc;
                     trace[it * 4 + 2] = rho_bwd;
+#ifdef SRCB_PHASE_TIMING
+                    { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); trace[it * 4 + 3] = (double)gt; }   // timeline study
+#else
                     trace[it * 4 + 3] = (double)pd_fail;
+#endif
                 }
                 ++it;
                 if (!isfinite(cost)) { status |= SRCB200_ILQR_ST_NONFINITE; stop = true; }

@@ -101,11 +101,28 @@ __device__ __forceinline__ void mma88(Frag& c, const double* __restrict__ A, con
         dmma(c, TA ? A[k * LD + g] : A[g * LD + k], TB ? B[g * LD + k] : B[k * LD + g]);
     }
 }
+// C-fragment coordinates (row g, columns 2q, 2q+1) <-> tile.  With the row stride of 12 doubles that makes every DMMA
+// fragment LOAD conflict-free, a 16-byte access of this pattern is a 2-way bank conflict (rows g and g + 1 of a quarter
+// warp overlap in 8 of the 32 banks: 8 wavefronts instead of 4 -- it was a third of all excess shared-memory wavefronts
+// of the kernel, and the shared-memory pipe is the loaded unit).  Two 8-byte accesses in which odd rows take their two
+// columns in the opposite order touch 16 distinct 8-byte banks per half warp: 2 + 2 wavefronts.
+__device__ __forceinline__ void sts_pair(double* __restrict__ T, int g, int q, double v0, double v1) {
+    const int odd = g & 1;
+    double* p = T + g * LD + 2 * q;
+    p[odd] = odd ? v1 : v0;
+    p[odd ^ 1] = odd ? v0 : v1;
+}
+__device__ __forceinline__ double2 lds_pair(const double* __restrict__ T, int g, int q) {
+    const int odd = g & 1;
+    const double* p = T + g * LD + 2 * q;
+    const double a = p[odd], b = p[odd ^ 1];
+    return odd ? make_double2(b, a) : make_double2(a, b);
+}
 __device__ __forceinline__ void store_frag(double* __restrict__ T, const Frag& c, int g, int q) {
-    *reinterpret_cast<double2*>(T + g * LD + 2 * q) = make_double2(c.c0, c.c1);
+    sts_pair(T, g, q, c.c0, c.c1);
 }
 __device__ __forceinline__ Frag load_frag(const double* __restrict__ T, int g, int q) {
-    const double2 v = *reinterpret_cast<const double2*>(T + g * LD + 2 * q);
+    const double2 v = lds_pair(T, g, q);
     return Frag{v.x, v.y};
 }
 __device__ __forceinline__ void zero_tile(double* __restrict__ T, int lane) {
@@ -570,7 +587,7 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
             }
             store_frag(SP, s, g, q);
             if (REC && g < 6 && q < 3)
-                *reinterpret_cast<double2*>(tr.A + (long long)t * 36 + g * 6 + 2 * q) = *reinterpret_cast<const double2*>(AD + g * LD + 2 * q);
+                *reinterpret_cast<double2*>(tr.A + (long long)t * 36 + g * 6 + 2 * q) = lds_pair(AD, g, q);
             __syncwarp();
             PH(5);
             // B_d = sep B_r ; d_d = sep d_c ; x_{t+1} = (A_d x + B_d u) + d_d with B_d u = sep (B_r u)   (ssm.py:330-333)
@@ -590,9 +607,9 @@ __device__ __noinline__ double fwd_lean(const Ctx c, const IlqrArgs& a, const do
             dmma(bu, __dmul_rn(sb, Brt[g * LD + q]), vb0);
             dmma(bu, __dmul_rn(sb, Brt[g * LD + 4 + q]), vb1);
             if (REC && g < 6 && q < 3)
-                *reinterpret_cast<double2*>(tr.A + (long long)t * 36 + g * 6 + 2 * q) = *reinterpret_cast<const double2*>(AD + g * LD + 2 * q);
+                *reinterpret_cast<double2*>(tr.A + (long long)t * 36 + g * 6 + 2 * q) = lds_pair(AD, g, q);
             if (REC && g < 6 && 2 * q < M) {
-                const double2 b2 = *reinterpret_cast<const double2*>(Brt + g * LD + 2 * q);
+                const double2 b2 = lds_pair(Brt, g, q);
                 *reinterpret_cast<double2*>(tr.B + (long long)t * 6 * M + g * M + 2 * q) = make_double2(__dmul_rn(sb, b2.x), __dmul_rn(sb, b2.y));
             }
             if (lf) xn = __dadd_rn(__dadd_rn(ax.c0, bu.c1), __dmul_rn(sb, dc));
@@ -725,7 +742,7 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
     const bool inc = cf.include_input_var_constraint != 0;
     // records move as 16-byte pieces in C-fragment coordinates: lane (g, q) owns columns 2q, 2q+1 of row g
     const bool vA = (g < 6 && q < 3), vB = (g < 6 && 2 * q < M), vK = (g < M && q < 3);
-    const int oA = vA ? g * 6 + 2 * q : 0, oB = vB ? g * M + 2 * q : 0, oT = g * LD + 2 * q;
+    const int oA = vA ? g * 6 + 2 * q : 0, oB = vB ? g * M + 2 * q : 0;
     double* BC = ws + W_PV;                            // 2 x 2 x 8 doubles: pivot-column broadcast of the gain solve
     int pd_fail = -1;
     double2 pa, ph, pb;                                // record of the next step to process, in registers
@@ -755,13 +772,14 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
         __syncwarp();
 
         PH_DECL;
+        const Frag rfrag = load_frag(Rt, g, q);      // R in C-fragment coordinates: constant over the sweep
         for (int t = N - 1; t >= 0; --t) {
             // ---- level 0: stage A_t, B_t, (H_t | e_t), du from the prefetched registers; fetch step t-1
             if (vA) {
-                *reinterpret_cast<double2*>(A + oT) = pa;
-                *reinterpret_cast<double2*>(H + oT) = ph;
+                sts_pair(A, g, q, pa.x, pa.y);
+                sts_pair(H, g, q, ph.x, ph.y);
             }
-            if (vB) *reinterpret_cast<double2*>(B + oT) = pb;
+            if (vB) sts_pair(B, g, q, pb.x, pb.y);
             if (lane < 6) H[lane * LD + 6] = pe;   // rows 6,7 / column 7 of this tile never reach rows<6, cols<7
             if (lane < M) DU[lane] = inc ? __dsub_rn(pu, pup) : pu;
             if (t > 0) LOAD_STEP(t - 1);
@@ -801,13 +819,13 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
             {
                 mma88<false, false>(qxx, W, H, g, q);                  // (c_xx | c_x) = W (H | e)
                 mma88<false, false>(qxx, ATP, A, g, q);                // + (A^T P | A^T p) A'
-                Frag quu = load_frag(Rt, g, q);
+                Frag quu = rfrag;
                 mma88<false, false>(quu, BTP, B, g, q);                // R + (B^T P) B
                 Frag qux{(q == 3 && g < M) ? CU[g] : 0.0, 0.0};
                 mma88<false, false>(qux, BTP, A, g, q);                // (0 | c_u) + (B^T P | B^T p) A'
                 Frag quut, quxt;
                 if (sreg) {
-                    quut = load_frag(Rt, g, q);
+                    quut = rfrag;
                     mma88<false, false>(quut, BTPR, B, g, q);
                     quxt = Frag{0.0, 0.0};
                     mma88<false, false>(quxt, BTPR, A, g, q);
@@ -864,7 +882,7 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
             {
                 Frag kq{0.0, 0.0};
                 mma88<true, false>(kq, KT, QUU, g, q);
-                if (vK) *reinterpret_cast<double2*>(Kout + (long long)t * M * 6 + g * 6 + 2 * q) = *reinterpret_cast<const double2*>(KT + oT);
+                if (vK) *reinterpret_cast<double2*>(Kout + (long long)t * M * 6 + g * 6 + 2 * q) = lds_pair(KT, g, q);
                 if (lane < M) kout[t * M + lane] = KT[lane * LD + 6];
                 store_frag(KQ, kq, g, q);
             }

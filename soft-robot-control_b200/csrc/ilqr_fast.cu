@@ -953,10 +953,8 @@ __device__ __forceinline__ void queue_push(int* q, int cap, int lane, int id, in
     if (lane == 0) push_one(q, cap, id, cls);
 }
 
-// launch shape S: 0 = 2 CTAs x 8 warps, table in shared memory; 1 = 12 warps, one row in registers; 2 = 8 warps, two rows;
-// 3 = 12 warps, table in shared memory (168 registers: room for the software-pipelined table loads)
-constexpr int shape_warps(int s) { return (s == 1 || s == 3) ? 12 : 8; }
-constexpr int shape_rows(int s) { return s == 3 ? 0 : s; }
+// launch shape S: 0 = 2 CTAs x 8 warps, table in shared memory; 1 = 12 warps, one row in registers; 2 = 8 warps, two rows
+constexpr int shape_warps(int s) { return s == 1 ? 12 : 8; }
 template <int M, int S>
 __global__ void __launch_bounds__(shape_warps(S) * 32, S == 0 ? 2 : 1)
 ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__ IlqrArgs a) {
@@ -1000,7 +998,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
             for (int e = lane; e < N * M; e += 32) nom.u[e] = a.u_init ? a.u_init[b * (long long)N * M + e] : 0.0;
             __syncwarp();
             __threadfence_block();
-            cost = fwd_dispatch<M, (S == 3 ? 0 : S)>(c, a, discr, nom.x, nom.u, 1.0, nullptr, nullptr, tr0, ztar, ulast);
+            cost = fwd_dispatch<M, S>(c, a, discr, nom.x, nom.u, 1.0, nullptr, nullptr, tr0, ztar, ulast);
             if (a.ocost0 && lane == 0) a.ocost0[b] = cost;
             // priority class: initial cost above the running mean of the batch -> expected to need many iterations
             cls = 1;
@@ -1027,7 +1025,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
                 double cost_t = cost, alpha_acc = 0.0;
                 while (!improved && !failed) {
                     improved = true;
-                    cost_t = fwd_dispatch<M, (S == 3 ? 0 : S)>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
+                    cost_t = fwd_dispatch<M, S>(c, a, discr, rcur.x, rcur.u, alpha, Kbuf, kbuf, rtrial, ztar, ulast);
                     ++trials;
                     double dc = 0.0;
                     const double a2 = __dmul_rn(__dmul_rn(alpha, alpha), 0.5);
@@ -1620,7 +1618,7 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
     // 8 warps, 255 registers, rows `lane` and `32 + lane` in registers (each warp ~1.8 x faster, half as many run).  Small
     // batches are spread over the SMs: the task queue feeds any number of warps.
     const char* shp = getenv("SRCB200_ILQR_SHAPE");
-    const int cr = (shp && shp[0] >= '0' && shp[0] <= '3') ? shp[0] - '0' : 0;
+    const int cr = (shp && shp[0] >= '0' && shp[0] <= '2') ? shp[0] - '0' : 0;
     const int nw = fast::shape_warps(cr);
     const size_t smem = sizeof(double) * (fast::SH_END + nw * fast::W_SIZE);
     const long long slots = (long long)sms * (cr == 0 ? 2 : 1);
@@ -1635,8 +1633,8 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
                                        (int)smem));                                                                        \
         fast::ilqr_ssm_fast_kernel<MM, CRR><<<grid, nw * 32, smem, st>>>(M, a);                                            \
     } while (0)
-    if (M.m == 8) { if (cr == 0) SRCB_LAUNCH_SHAPE(8, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(8, 1); else if (cr == 2) SRCB_LAUNCH_SHAPE(8, 2); else SRCB_LAUNCH_SHAPE(8, 3); }
-    else          { if (cr == 0) SRCB_LAUNCH_SHAPE(4, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(4, 1); else if (cr == 2) SRCB_LAUNCH_SHAPE(4, 2); else SRCB_LAUNCH_SHAPE(4, 3); }
+    if (M.m == 8) { if (cr == 0) SRCB_LAUNCH_SHAPE(8, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(8, 1); else SRCB_LAUNCH_SHAPE(8, 2); }
+    else          { if (cr == 0) SRCB_LAUNCH_SHAPE(4, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(4, 1); else SRCB_LAUNCH_SHAPE(4, 2); }
 #undef SRCB_LAUNCH_SHAPE
     SRCB_LAUNCH_CHECK("ilqr_ssm_fast_kernel");
     *handled = true;

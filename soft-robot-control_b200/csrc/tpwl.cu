@@ -543,6 +543,8 @@ tpwl_rollout_nn_multi_kernel(TpwlDev M, long long batch, int N, const double* __
 
 int tpwl_rollout_nn_screen_launch(const TpwlDev& M, long long batch, int N, const double* x0, const double* u,
                                   double* x, int* idx, cudaStream_t st, bool* handled);
+int tpwl_rollout_nn_resident_launch(const TpwlDev& M, long long batch, int N, const double* x0, const double* u,
+                                    double* x, int* idx, cudaStream_t st, bool* handled);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -683,9 +685,10 @@ extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t
             return fail(SRCB200_E_METHOD, "nn rollout with zoh needs a pre-discretised bank: discretise the bank once "
                                           "(srcb200_zoh_batch) and pass it with discr_method NONE");
         bool screened = false;
-        if (!disc) if (int e = tpwl_rollout_nn_screen_launch(M, batch, N, x0, u, x, idx, st, &screened)) return e;
+        if (!disc) if (int e = tpwl_rollout_nn_resident_launch(M, batch, N, x0, u, x, idx, st, &screened)) return e;
+        if (!disc && !screened) if (int e = tpwl_rollout_nn_screen_launch(M, batch, N, x0, u, x, idx, st, &screened)) return e;
         if (screened) {
-            // exact two-stage search kernel (tpwl_screen.cu) took it
+            // resident-entry kernel (tpwl_resident.cu) or the exact two-stage search kernel (tpwl_screen.cu) took it
         } else if (!disc && M.r <= 128) {
             const long long groups = (batch + kMT - 1) / kMT;
             const int g2 = (int)(groups < 148 * 8 ? groups : 148 * 8);

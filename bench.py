@@ -372,8 +372,9 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
         byt = batch * N * ((n * n + n * m + n) * 8 + (2 * n + m) * 8) + N * P * r * 8
         ops = batch * N * 2.0 * P * r
         dram = 0.25e9 * batch / 4096.0          # ncu dram read+write of one launch (profiles/ncu_tpwl_screen_r01.txt)
+        l2_peak = 17978.0                       # GB/s, tools/l2_bw_microbench.cu gather pattern (profiles/l2_bw_microbench_r2.txt)
         roof = {"kernel": "tpwl_rollout_nn_screen_kernel<36,4>", "bound": "l2/lsu (on-chip: the 44 MB bank is L2 resident)",
-                "achieved": byt / (t_dev / args.steps) / 1e9, "peak": None, "unit": "GB/s (L2 -> SM, algorithmic)",
+                "achieved": byt / (t_dev / args.steps) / 1e9, "peak": l2_peak, "unit": "GB/s (L2 -> SM, algorithmic)",
                 "traffic": dram, "hbm_frac": dram / (t_dev / args.steps) / 1e9 / hbm,
                 "l1tex_pct_ncu": 65.0, "lts_pct_ncu": 12.0, "issue_active_pct_ncu": 52.0,
                 "fp32_screen_tops": ops / (t_dev / args.steps) / 1e12,
@@ -381,8 +382,10 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
                         "288000 B once per time step for the whole batch (SURVEY 8d).  These bytes move L2 -> SM, not HBM -> "
                         "L2: DRAM traffic is 0.25 GB per launch (hbm_frac, of " + hsrc + "); the limiters ncu reports are the "
                         "L1/LSU pipe (65 %) and FP32 issue of the exact two-stage search (52 %), "
-                        "profiles/ncu_tpwl_screen_r01.txt.  frac = the L1/LSU utilisation ncu measured."}
-        roof["frac"] = 0.65
+                        "profiles/ncu_tpwl_screen_r01.txt.  peak = L2 -> SM bandwidth measured on this pool for the same "
+                        "access pattern (random 44 KB entries, 16-byte loads, all SMs: 18.0 TB/s; coalesced sweep 20.5 TB/s; "
+                        "tools/l2_bw_microbench.cu), of measured; frac = achieved / peak."}
+        roof["frac"] = roof["achieved"] / l2_peak
     else:
         fl = batch * N * 2.0 * P * (n * n + n * m + n)
         roof = {"kernel": "dgemm_kernel (bank blend)", "bound": "tensor", "achieved": fl / (t_dev / args.steps) / 1e12,
@@ -596,6 +599,7 @@ def run_pod_gram(args, rank, world, dev_index):
     t_gram = sum(a.elapsed_time(b) for a, b, _, _ in ev) * 1e-3
     t_eig = sum(b.elapsed_time(c) for _, b, c, _ in ev) * 1e-3
     t_all = sum(a.elapsed_time(d) for a, _, _, d in ev) * 1e-3
+    fl = 2.0 * nf_local * ns * ns
     # untimed checks: the modes are the prescribed ones, U is orthonormal across the shards
     UtU = U.t() @ U
     if world > 1:
@@ -605,8 +609,20 @@ def run_pod_gram(args, rank, world, dev_index):
         t_gram, t_eig, t_all = float(tt[0]), float(tt[1]), float(tt[2])
     orth = float((UtU - torch.eye(nb, device="cuda", dtype=torch.float64)).abs().max())
     sig_err = float(((S - sv[:nb]).abs().max() / sv[0]))
+    e2e = None
+    if world == 1 and not args.pod_full:
+        # e2e: the reference-facing call compute_POD (pod.py:181-200) on a HOST snapshot matrix, modes back on the host
+        Xh = X.cpu().numpy()
+        del U, G
+        t0 = time.perf_counter()
+        U_full, U_h, nb_h, S_h = pod.compute_POD(Xh, tol)
+        t_e2e = time.perf_counter() - t0
+        e2e = {"value": fl / t_e2e / 1e12, "unit": "TFLOP/s (algorithmic Gram flops / whole compute_POD call)",
+               "h2d_bytes_per_step": int(Xh.nbytes), "d2h_bytes_per_step": int(U_full.nbytes + S_h.nbytes),
+               "seconds": t_e2e, "modes": int(nb_h),
+               "note": "host numpy matrix in (pageable, 8.6 GB over PCIe), U / Sigma out: the copy dominates"}
+        del Xh
     hbm, hsrc, fp64 = measured_peaks()
-    fl = 2.0 * nf_local * ns * ns
     ach = fl / (t_gram / args.steps) / 1e12
     return {"metric": "pod_gram_tflops", "value": world * fl * args.steps / t_gram / 1e12,
             "unit": "TFLOP/s (algorithmic Gram flops, all-reduce inside the timed region)",
@@ -622,7 +638,7 @@ def run_pod_gram(args, rank, world, dev_index):
                        "project_ms": 1e3 * (t_all - t_gram - t_eig) / args.steps,
                        "modes": int(nb), "modes_expected": int(modes_expected), "sigma_relerr": sig_err,
                        "U_orthonormality": orth, "eig_iterations": info.get("iterations"), "eig_block": info.get("block")},
-            "e2e": None, "gpu_launches": args.steps * nblk + args.steps * 12, "clocks": clk.summary(),
+            "e2e": e2e, "gpu_launches": args.steps * nblk + args.steps * 12, "clocks": clk.summary(),
             "roofline": {"kernel": "dgemm_kernel<true,true,true> (SYRK)" if nblk == 1 else "dgemm_kernel<true,false,true> (block rows)",
                          "bound": "tensor", "achieved": ach, "peak": fp64,
                          "unit": "TFLOP/s", "frac": ach / fp64, "traffic": 61.0e9 if (world == 1 and not args.pod_full) else None,
@@ -734,6 +750,15 @@ def run_ilqr_tpwl(args, rank, world, dev_index):
         tt = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev = float(tt[0])
+    # e2e: the reference-facing call, host arrays in (x0, targets), host arrays out (x, u, K)
+    solver.set_target(zt)
+    t0 = time.perf_counter()
+    xh, uh_, Kh = solver.ilqr_computation(x0)
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt[0])
     it = out['iterations'].cpu().numpy(); tr = out['trials'].cpu().numpy(); st = out['status'].cpu().numpy()
     # DMMA work of the backward sweeps: (76x73x72 + 8x76x72 + 72x73x84) fused multiply-adds per step
     flops = 2.0 * (76 * 73 * 72 + 8 * 76 * 72 + 72 * 73 * 84) * N * float(it.sum())
@@ -748,7 +773,10 @@ def run_ilqr_tpwl(args, rank, world, dev_index):
                        "batch_per_gpu": batch, "horizon": N, "l2": "256 MB buffer written between timed steps (untimed)",
                        "converged_frac": float((st & 1).mean()), "mean_iterations": float(it.mean()),
                        "mean_forward_passes": float((tr + 1).mean())},
-            "e2e": None, "gpu_launches": args.steps, "clocks": clk.summary(),
+            "e2e": {"value": batch * world / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int((x0.size + zt.size) * 8),
+                    "d2h_bytes_per_step": int((xh.size + uh_.size + Kh.size) * 8),
+                    "note": "one iLQR.ilqr_computation call on host arrays (pageable), results x, u, K back on the host"},
+            "gpu_launches": args.steps, "clocks": clk.summary(),
             "roofline": {"kernel": "ilqr_solve_kernel<TpwlPolicyT<72,4,6>>", "bound": "tensor", "achieved": ach, "peak": fp64,
                          "unit": "TFLOP/s", "frac": ach / fp64, "traffic": None,
                          "note": "flops of the three DMMA products of every backward step only (forward passes and the "

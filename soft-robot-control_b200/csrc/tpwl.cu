@@ -60,7 +60,7 @@ tpwl_nearest_kernel(TpwlDev M, long long count, const double* __restrict__ x, in
         for (int i = threadIdx.x; i < M.n; i += kSel) sx[i] = x[s * M.n + i];
         __syncthreads();
         double dmin;
-        const int bi = tpwl_nearest<kSel>(M, sx, nullptr, red_d, red_i, &dmin);
+        const int bi = tpwl_nearest<kSel, true>(M, sx, nullptr, red_d, red_i, &dmin);
         if (threadIdx.x == 0) {
             idx[s] = bi;
             if (dist) dist[s] = dmin;
@@ -90,7 +90,7 @@ template <int NT>
 __device__ __forceinline__ void tpwl_weights_one(const TpwlDev& M, const double* __restrict__ sx, double* __restrict__ sd,
                                                  double* red_d, int* red_i, double* __restrict__ ws) {
     double dmin;
-    const int bi = tpwl_nearest<NT>(M, sx, sd, red_d, red_i, &dmin);
+    const int bi = tpwl_nearest<NT, true>(M, sx, sd, red_d, red_i, &dmin);
     __syncthreads();
     if (dmin == 0.0) {
         for (int p = threadIdx.x; p < M.P; p += NT) ws[p] = (p == bi) ? 1.0 : 0.0;
@@ -337,7 +337,7 @@ tpwl_rollout_nn_kernel(TpwlDev M, long long batch, int N, const double* __restri
         __syncthreads();
         for (int t = 0; t < N; ++t) {
             for (int i = tid; i < m; i += kSel) su[i] = ub[t * m + i];
-            const int p = tpwl_nearest<kSel>(M, sx, nullptr, red_d, red_i, nullptr);
+            const int p = tpwl_nearest<kSel, true>(M, sx, nullptr, red_d, red_i, nullptr);
             if (idxo && tid == 0) idxo[b * (long long)N + t] = p;
             const double* Ap = M.A + (long long)p * n * n;
             const double* Bp = M.B + (long long)p * n * m;
@@ -728,8 +728,9 @@ extern "C" int srcb200_tpwl_rollout_batch(const srcb200_tpwl_model* mdl, int64_t
         double* cat = (double*)((char*)zws + zws_bytes);
         double* blended = (double*)((char*)cat + align_up(sizeof(double) * (size_t)M.P * wd, 256));
         const bool fused = !(disc && M.discr == SRCB200_DISCR_ZOH) && batch > kBlendStreamMaxBatch;
-        const size_t fsmem = sizeof(double) * (2 * (size_t)wd + 2 * n + ((m + 1) & ~1) +
-                                               (size_t)max(discretize_scratch_doubles(n, m), M.P) + 2);
+        // fe (and an already discrete bank) discretises elementwise: no LU scratch, two CTAs fit on an SM
+        const int dscr = (disc && M.discr != SRCB200_DISCR_FE) ? discretize_scratch_doubles(n, m) : 0;
+        const size_t fsmem = sizeof(double) * (2 * (size_t)wd + 2 * n + ((m + 1) & ~1) + (size_t)max(dscr, M.P) + 2);
         if (fused && fsmem <= 227 * 1024) {
             // two launches per time step: blend GEMM over the concatenated bank, fused discretise + step + next weights
             SRCB_CUDA(cudaFuncSetAttribute(tpwl_weighting_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));

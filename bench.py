@@ -390,7 +390,7 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
         fl = batch * N * 2.0 * P * (n * n + n * m + n)
         roof = {"kernel": "dgemm_kernel (bank blend)", "bound": "tensor", "achieved": fl / (t_dev / args.steps) / 1e12,
                 "peak": fp64, "unit": "TFLOP/s", "traffic": None,
-                "note": "2 P (n^2+nm+n) flop per trajectory-step over the WHOLE step time; two launches per time step (profiles/launches_tpwl_weighting_r2.csv): blend GEMM over the concatenated [A|B|d] bank 1.75 ms = 25.9 TFLOP/s (73 % of measured DGEMM peak), fused TMA-fed discretise + step + next-weights kernel 0.44 ms; the 44.4 MB bank is L2 resident (bank stream 25 GB/s: not a bound at this batch)"}
+                "note": "2 P (n^2+nm+n) flop per trajectory-step over the WHOLE step time; two launches per time step (profiles/launches_tpwl_weighting_r2.csv): blend GEMM over the concatenated [A|B|d] bank 1.555 ms = 29.2 TFLOP/s (82 % of measured DGEMM peak), fused TMA-fed discretise + step + next-weights kernel 0.287 ms (profiles/launches_tpwl_weighting_r2_mbar.csv); the 44.4 MB bank is L2 resident (bank stream 25 GB/s: not a bound at this batch)"}
         roof["frac"] = roof["achieved"] / roof["peak"]
     return {"metric": "tpwl_%s_rollout_steps_per_sec" % method, "value": steps_total / t_dev, "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
@@ -400,7 +400,7 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
                        "horizon": N, "l2": "256 MB buffer written between timed steps (untimed)"},
             "e2e": {"value": steps_total / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": int((x0h.size + uh.size) * 8),
                     "d2h_bytes_per_step": int(batch * (N + 1) * (n + 6) * 8)},
-            "gpu_launches": args.steps * (1 if method == 'nn' else N * 7) + args.steps, "clocks": clk.summary(),
+            "gpu_launches": args.steps * (1 if method == 'nn' else 2 * N + 2), "clocks": clk.summary(),
             "roofline": roof}
 
 
@@ -641,10 +641,10 @@ def run_pod_gram(args, rank, world, dev_index):
             "e2e": e2e, "gpu_launches": args.steps * nblk + args.steps * 12, "clocks": clk.summary(),
             "roofline": {"kernel": "dgemm_kernel<true,true,true> (SYRK)" if nblk == 1 else "dgemm_kernel<true,false,true> (block rows)",
                          "bound": "tensor", "achieved": ach, "peak": fp64,
-                         "unit": "TFLOP/s", "frac": ach / fp64, "traffic": 61.0e9 if (world == 1 and not args.pod_full) else None,
+                         "unit": "TFLOP/s", "frac": ach / fp64, "traffic": 86.4e9 if (world == 1 and not args.pod_full) else None,
                          "note": "algorithmic 2 nf ns^2 flop / Gram time (incl. the overlapped all-reduce when world > 1); the kernel "
                                  "executes only the upper tiles (half), so frac can exceed 1; peak = measured cuBLAS DGEMM; traffic = ncu "
-                                 "dram read+write of one SYRK launch at this size (profiles/ncu_gram_r2.txt; 8.6 GB algorithmic)"}}
+                                 "dram read+write of one SYRK launch at this size (profiles/ncu_gram_r2_mbar_pace.txt: 83-168 GB between captures, 8.6 GB algorithmic; tensor pipe 88-89 % active, DRAM at 5-9 % of its peak: the re-reads of free-running CTAs are not the bound, the pace keeper that removes them costs 5 %)"}}
 
 
 def run_mpc(args, rank, world, dev_index):

@@ -13,6 +13,7 @@
 //
 // Reference math sites: sofacontrol/mor/pod.py:181-200 (SVD of the snapshot matrix -> eig of X^T X),
 // pod.py:22-72 (projections), sofacontrol/tpwl/tpwl.py:246-248 (einsum bank blend).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace srcb {
@@ -23,6 +24,8 @@ constexpr int LDA_NT = BK + 4;   // non-transposed A tile stored [m][k]: row str
 constexpr int A_TILE = (BK * LDT > BM * LDA_NT) ? BK * LDT : BM * LDA_NT;
 constexpr int B_TILE = BK * LDT;
 constexpr size_t GEMM_SMEM = sizeof(double) * STAGES * (A_TILE + B_TILE);
+constexpr int kPaceSlots = 4, kPaceInts = 1 << 16;
+__device__ int g_gemm_pace[kPaceSlots * kPaceInts];   // pace-keeper counters of up to kPaceSlots SYRK launches in flight
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -81,7 +84,7 @@ template <bool TRANSA, bool SYRK, bool ALIGN16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dgemm_kernel(long long M, long long N, long long K, double alpha, const double* __restrict__ A, long long lda,
              const double* __restrict__ B, long long ldb, double* __restrict__ C, long long ldc, int accumulate,
-             int tiles_m, int tiles_n, long long num_tiles, int sb) {
+             int tiles_m, int tiles_n, long long num_tiles, int sb, int* __restrict__ pace, int pace_w, int pace_windows, int pace_slack) {
     extern __shared__ __align__(16) double gsm[];
     __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
     double* sA = gsm;
@@ -156,6 +159,20 @@ dgemm_kernel(long long M, long long N, long long K, double alpha, const double* 
             const long long j = gk + kt;
             const int st = (int)(j % STAGES);
             const long long use = j / STAGES;
+            if (pace && tid == 0 && ((int)kt & (pace_w - 1)) == 0) {       // pace_w is a power of two
+                // Pace keeper (long-K SYRK): the CTAs that work on the same round of tiles share column panels of X
+                // through L2 only while they walk K together.  Every pace_w chunks a CTA reports its window and waits
+                // (bounded: this is a hint, never a dependency) until all CTAs of the round have entered the previous
+                // one: the pack stays within two windows, far inside what L2 holds.
+                const long long round = tile / gridDim.x, left = num_tiles - round * gridDim.x;
+                const int expect = (int)(left < gridDim.x ? left : gridDim.x), w = (int)kt >> (31 - __clz(pace_w));
+                int* row = pace + round * pace_windows;
+                atomicAdd(row + w, 1);
+                if (w >= pace_slack) {
+                    const long long t0 = clock64();
+                    while (*(volatile int*)(row + w - pace_slack) < expect && clock64() - t0 < 60000) { }
+                }
+            }
             if (use > 0) mbar_wait(&empty[st], (unsigned)((use - 1) & 1));
             double* a = sA + st * A_TILE;
             double* b = sB + st * B_TILE;
@@ -238,16 +255,35 @@ static int launch_gemm(long long M, long long N, long long K, double alpha, cons
     const int grid = (int)(num_tiles < sms ? num_tiles : sms);   // persistent: one CTA per SM walks the tile list
     int sb = 1;
     while ((sb + 1) * (sb + 1) <= grid) ++sb;                    // super-block edge of the SYRK walk
+    // pace keeper of the long-K SYRK (see the kernel): one counter per (round of tiles, window of K chunks).  OFF by
+    // default: measured at 131072 x 8192 (profiles/ncu_gram_r2_mbar_pace.txt) free-running CTAs read 83-168 GB from
+    // DRAM (8.6 GB algorithmic) in 290 ms, paced ones (SRCB200_GEMM_PACE=1: slack of one window) 60.9 GB in 309 ms --
+    // the kernel is bound by the tensor pipe (88 % active), DRAM runs at 5-9 % of its peak, so the re-reads are free
+    // and waiting for the slowest CTA is not.
+    int* pace = nullptr;
+    int pace_w = 32, pace_windows = 0, pace_slack = 0;
+    const long long KT = (K + BK - 1) / BK;
+    if (const char* env = getenv("SRCB200_GEMM_PACE")) pace_slack = atoi(env);     // 0: free-running CTAs
+    if (SYRK && KT >= 512 && grid > 1 && pace_slack > 0) {
+        static int* base = nullptr;
+        static unsigned launches = 0;
+        if (!base) SRCB_CUDA(cudaGetSymbolAddress((void**)&base, g_gemm_pace));
+        const long long rounds = (num_tiles + grid - 1) / grid;
+        while (rounds * ((KT + pace_w - 1) / pace_w) > kPaceInts) pace_w *= 2;
+        pace_windows = (int)((KT + pace_w - 1) / pace_w);
+        pace = base + (size_t)(launches++ % kPaceSlots) * kPaceInts;
+        SRCB_CUDA(cudaMemsetAsync(pace, 0, sizeof(int) * (size_t)rounds * pace_windows, st));
+    }
     if (al) {
         auto kern = dgemm_kernel<TRANSA, SYRK, true>;
         SRCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, C, ldc, accumulate, tiles_m,
-                                                    tiles_n, num_tiles, sb);
+                                                    tiles_n, num_tiles, sb, pace, pace_w, pace_windows, pace_slack);
     } else {
         auto kern = dgemm_kernel<TRANSA, SYRK, false>;
         SRCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         kern<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, C, ldc, accumulate, tiles_m,
-                                                    tiles_n, num_tiles, sb);
+                                                    tiles_n, num_tiles, sb, pace, pace_w, pace_windows, pace_slack);
     }
     SRCB_LAUNCH_CHECK("dgemm_kernel");
     return 0;

@@ -3,10 +3,18 @@
 //
 //   stage 1  FP32 squared distances a^ to all P stored points from an FP32 copy of the point bank that stays in
 //            shared memory for the whole kernel (144 KB at the Diamond size), for up to 8 trajectories at once (every
-//            bank value is read once per step and used 8 times), with the rigorous error bound on d^ = sqrt(a^)
-//                eps_p = 2^-24 (34 d^_p + 2 (max_p ||Q_p|| + ||q||)) + 1e-14 d^_p
-//            (derivation: ilqr_fwd_tpwl.cuh).  With eps(d) = c1 d + c0 the candidate test "lower bound <= smallest
-//            upper bound" is one float compare per point against a per-trajectory threshold on a^ (rounded UP);
+//            bank value is read once per step and used 8 times).  Bank and state are CENTRED on the bank mean mu (in
+//            float64, before the conversion) and the squared distance is expanded,
+//                a^_p = (|b_p - mu|^2 + |c - mu|^2) - 2 (b_p - mu).(c - mu),
+//            so the inner loop is ONE FMA per (point, coordinate, trajectory) instead of a subtraction and an FMA.
+//            Rigorous bound (u = 2^-24; b, c the centred vectors): the float32 operands carry relative error u, the
+//            FMA chain of length r adds gamma_r sum|b_j c_j| <= r u |b||c|, the two norms are rounded once each, the
+//            final add and FMA once each:
+//                |a^_p - |b_p - c|^2|  <=  u (|b| + |c|)^2 (r/2 + 4.5)  <=  E2 := (r/2 + 8) u (max_p|b_p| + |c|)^2 (1 + 1e-3)
+//            (float64 roundings of the centring and of the reference's own distances are 1e-16-relative: inside the
+//            slack).  The reference's float64 argmin p* has |b_p* - c|^2 <= min_p |b_p - c|^2 (1 + 1e-12), hence
+//            a^_p* <= min a^ + 2 E2 (+ slack): one float compare per point against a per-trajectory threshold
+//            (rounded UP);
 //   stage 2  the FP64 argmin is provably among the candidates.  One candidate (the usual case: measured 701
 //            candidates per 700 searches): done.  Several: one warp re-scores them with the bit-exact numpy-order
 //            FP64 distance (tpwl.cuh), first-occurrence argmin.  None / more than 32 / NaN: that warp runs the full
@@ -31,13 +39,15 @@ constexpr int kSCand = 32;          // candidate slots per trajectory (one warp 
 static_assert(kSHW == kST, "one warp per trajectory slot");
 
 struct ScreenPlan {                 // byte offsets; the per-half arrays exist twice, `hstride` bytes apart
-    size_t bank, half, hstride, sx, sxn, su, xfT, redf, thr2, xnorm, cnt, cand, sel, fb, total;
+    size_t bank, nb, mu, half, hstride, sx, sxn, su, xfT, redf, thr2, xnorm, ncf, cnt, cand, sel, fb, total;
 };
 __host__ __device__ inline ScreenPlan make_screen_plan(int n, int m, int r, int P) {
     ScreenPlan S;
     size_t o = 0;
     auto take = [&o](size_t bytes) { const size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
     S.bank = take(sizeof(float) * (size_t)r * P);
+    S.nb = take(sizeof(float) * (size_t)P);
+    S.mu = take(sizeof(double) * (size_t)r);
     S.half = o;
     o = 0;
     S.sx = take(sizeof(double) * kST * n);
@@ -47,6 +57,7 @@ __host__ __device__ inline ScreenPlan make_screen_plan(int n, int m, int r, int 
     S.xfT = take(sizeof(float) * (size_t)r * kST);
     S.redf = take(sizeof(float) * kST * kSHW);
     S.thr2 = take(sizeof(float) * kST);
+    S.ncf = take(sizeof(float) * kST);
     S.cnt = take(sizeof(int) * kST);
     S.cand = take(sizeof(int) * kST * kSCand);
     S.sel = take(sizeof(int) * kST);
@@ -80,27 +91,36 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
     float* xfT = reinterpret_cast<float*>(hb + S.xfT);              // r x kST: the screened part of the 8 states
     float* redf = reinterpret_cast<float*>(hb + S.redf);
     float* thr2 = reinterpret_cast<float*>(hb + S.thr2);
+    float* ncf = reinterpret_cast<float*>(hb + S.ncf);               // |c - mu|^2 of the 8 states
+    float* nbs = reinterpret_cast<float*>(smraw + S.nb);             // |b_p - mu|^2
+    double* smu = reinterpret_cast<double*>(smraw + S.mu);           // bank mean
     int* cnt = reinterpret_cast<int*>(hb + S.cnt);
     int* cand = reinterpret_cast<int*>(hb + S.cand);
     int* sel = reinterpret_cast<int*>(hb + S.sel);
     int* fb = reinterpret_cast<int*>(hb + S.fb);
     double* shared_tail = reinterpret_cast<double*>(smraw + S.half + 2 * S.hstride);     // [0]: bank norm bound
-    const double w = useq ? M.wq : M.wv;
     const double* bankT = useq ? M.qT : M.vT;
     const int xoff = useq ? r : 0;                                  // x = [v; q]
 
-    // ---- FP32 bank + the largest weighted point norm, once per CTA (both halves together)
+    // ---- bank mean, centred FP32 bank, centred squared norms and the largest centred norm: once per CTA
     {
         double* redd = reinterpret_cast<double*>(smraw + S.half);   // scratch before the halves start using their arrays
+        for (int j = tid; j < r; j += kSThreads) {
+            double acc = 0.0;
+            for (int p2 = 0; p2 < P; ++p2) acc += bankT[(size_t)j * P + p2];
+            smu[j] = acc / (double)P;       // any centre is valid; every CTA computes the same one
+        }
+        __syncthreads();
         double bmax = 0.0;
         for (int p = tid; p < P; p += kSThreads) {
             double sq = 0.0;
             for (int j = 0; j < r; ++j) {
-                const double v = bankT[(size_t)j * P + p];
+                const double v = bankT[(size_t)j * P + p] - smu[j];
                 bank[j * P + p] = (float)v;
                 sq = fma(v, v, sq);
             }
-            bmax = fmax(bmax, w * sqrt(sq));
+            nbs[p] = (float)sq;
+            bmax = fmax(bmax, sqrt(sq));
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, off));
@@ -113,13 +133,14 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
         }
         __syncthreads();
     }
-    const double bank_norm = shared_tail[0];
-    const bool screen_ok = isfinite(bank_norm) && bank_norm < 1e100;
+    const double bank_norm = shared_tail[0];                       // max_p |b_p - mu|, rounded up
+    const bool screen_ok = isfinite(bank_norm) && bank_norm < 1e17;
     const double u24 = 5.9604644775390625e-08;                     // 2^-24
     int pt[kSPts];
     bool has[kSPts];
+    float nbf[kSPts];
 #pragma unroll
-    for (int k = 0; k < kSPts; ++k) { pt[k] = ht + k * kSHalf; has[k] = pt[k] < P; }
+    for (int k = 0; k < kSPts; ++k) { pt[k] = ht + k * kSHalf; has[k] = pt[k] < P; nbf[k] = has[k] ? nbs[pt[k]] : 0.f; }
     __syncthreads();        // the scratch is free again
 
     const long long groups = (batch + tpg - 1) / tpg;
@@ -144,17 +165,22 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
             {
                 double s2 = 0.0;
                 for (int j = lane; j < r; j += 32) {
-                    const double v = sx[hw * n + xoff + j];
+                    const double v = sx[hw * n + xoff + j] - smu[j];
                     xfT[j * kST + hw] = (float)v;
                     s2 = fma(v, v, s2);
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-                if (lane == 0) { xnorm[hw] = sqrt(s2) * (1.0 + 1e-9); cnt[hw] = 0; fb[hw] = screen_ok ? 0 : 1; }
+                if (lane == 0) {
+                    xnorm[hw] = sqrt(s2) * (1.0 + 1e-9);
+                    ncf[hw] = (float)s2;
+                    cnt[hw] = 0;
+                    fb[hw] = screen_ok ? 0 : 1;
+                }
             }
             half_sync(half);
             if (screen_ok) {
-                // ---- stage 1: FP32 squared distances of this thread's points to the 8 states
+                // ---- stage 1: FP32 dot products of this thread's (centred) points with the 8 (centred) states
                 float a[kSPts][kST];
 #pragma unroll
                 for (int k = 0; k < kSPts; ++k)
@@ -172,11 +198,18 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                     for (int k = 0; k < kSPts; ++k) {
                         const float q = bp[k][j * P];
 #pragma unroll
-                        for (int tr = 0; tr < kST; ++tr) {
-                            const float d = q - xs[tr];
-                            a[k][tr] = fmaf(d, d, a[k][tr]);
-                        }
+                        for (int tr = 0; tr < kST; ++tr) a[k][tr] = fmaf(q, xs[tr], a[k][tr]);
                     }
+                }
+                // a^ = (|b|^2 + |c|^2) - 2 b.c
+                {
+                    const float4 na = *reinterpret_cast<const float4*>(ncf);
+                    const float4 nb4 = *reinterpret_cast<const float4*>(ncf + 4);
+                    const float ncs[kST] = {na.x, na.y, na.z, na.w, nb4.x, nb4.y, nb4.z, nb4.w};
+#pragma unroll
+                    for (int k = 0; k < kSPts; ++k)
+#pragma unroll
+                        for (int tr = 0; tr < kST; ++tr) a[k][tr] = fmaf(-2.f, a[k][tr], nbf[k] + ncs[tr]);
                 }
                 // ---- per-trajectory minimum of a^ -> threshold (one warp per trajectory does the bound arithmetic)
 #pragma unroll
@@ -194,12 +227,13 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
 #pragma unroll
                     for (int off = 4; off > 0; off >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, off));
                     if (lane == 0) {
-                        const double c1 = (0.5 * RT + 16.0) * u24 + 1e-14;   // 34 u at r = 36; grows with the sum length
-                        const double c0 = u24 * 2.0 * (bank_norm + w * xnorm[hw]);
-                        const double U = (1.0 + c1) * w * sqrt((double)v) + c0;     // smallest upper bound
-                        const double T = (U + c0) / (w * (1.0 - c1));
-                        const double T2 = T * T * (1.0 + 1e-6);
-                        thr2[hw] = (T2 < 3.0e38) ? __double2float_ru(T2) : INFINITY;   // NaN: no candidate -> full search
+                        const double c2 = (0.5 * r + 8.0) * u24 * 1.001 + 1e-12;
+                        const double sn = bank_norm + xnorm[hw];
+                        const double E2 = c2 * sn * sn + 1e-36;           // + underflow of the float32 products
+                        const double am = (double)v;                      // smallest a^ (may be slightly negative)
+                        const double T2 = am + 2.0 * E2 + 1e-6 * (fabs(am) + 2.0 * E2);
+                        // not representable / NaN: no candidate -> this trajectory runs the full float64 search
+                        thr2[hw] = (sn < 1e17 && T2 < 3.0e38) ? __double2float_ru(T2) : __int_as_float(0x7fc00000);
                     }
                 }
                 half_sync(half);

@@ -67,6 +67,14 @@ __host__ __device__ inline ScreenPlan make_screen_plan(int n, int m, int r, int 
     return S;
 }
 
+#ifdef SRCB_NN_PHASES
+__device__ unsigned long long g_nn_phase[8];   // cycles per phase of the time loop (thread 0 of half 0 of CTA 0), [7] = steps
+#define NN_PH(i) do { if (tid == 0 && blockIdx.x == 0) { const long long tn_ = clock64(); atomicAdd(&g_nn_phase[i], (unsigned long long)(tn_ - tph_)); tph_ = tn_; } } while (0)
+#else
+#define NN_PH(i) do { } while (0)
+#endif
+
+
 __device__ __forceinline__ void half_sync(int half) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(kSHalf) : "memory");
 }
@@ -75,7 +83,7 @@ template <int RT, int CM>
 __global__ void __launch_bounds__(kSThreads, 1)
 tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* __restrict__ x0,
                               const double* __restrict__ u, double* __restrict__ xo, int* __restrict__ idxo, int useq,
-                              int tpg) {
+                              int tpg, int stagger) {
     // RT / CM > 0: r (and n = 2r) / m are compile-time constants (Diamond: 36, 4): unrolled loops, constant divisions.
     // tpg <= kST: trajectories per group, chosen by the launcher so that every half gets the same number of groups.
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -143,6 +151,13 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
     for (int k = 0; k < kSPts; ++k) { pt[k] = ht + k * kSHalf; has[k] = pt[k] < P; nbf[k] = has[k] ? nbs[pt[k]] : 0.f; }
     __syncthreads();        // the scratch is free again
 
+    // The two halves run the same phases with the same period: started together they would collide in every phase
+    // (both searching: FP32 issue; both gathering: the load path).  Half 1 starts `stagger` cycles late and the offset
+    // persists, so one half searches while the other gathers.
+    if (half == 1 && stagger > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < stagger) { }
+    }
     const long long groups = (batch + tpg - 1) / tpg;
     for (long long gidx = (long long)blockIdx.x * 2 + half; gidx < groups; gidx += (long long)gridDim.x * 2) {
         const long long b0 = gidx * tpg;
@@ -160,6 +175,10 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
             su[e] = (tr < nt && N > 0) ? u[((b0 + tr) * (long long)N) * m + i] : 0.0;
         }
         half_sync(half);
+#ifdef SRCB_NN_PHASES
+        long long tph_ = clock64();
+        if (tid == 0 && blockIdx.x == 0) atomicAdd(&g_nn_phase[7], (unsigned long long)N);
+#endif
         for (int t = 0; t < N; ++t) {
             // ---- FP32 copy and norm of the screened part of every state (warp hw <-> trajectory slot hw)
             {
@@ -179,6 +198,7 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                 }
             }
             half_sync(half);
+            NN_PH(0);
             if (screen_ok) {
                 // ---- stage 1: FP32 dot products of this thread's (centred) points with the 8 (centred) states
                 float a[kSPts][kST];
@@ -222,6 +242,7 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                     if (lane == 0) redf[tr * kSHW + hw] = v;
                 }
                 half_sync(half);
+            NN_PH(1);
                 {
                     float v = (lane < kSHW) ? redf[hw * kSHW + lane] : INFINITY;
 #pragma unroll
@@ -237,6 +258,7 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                     }
                 }
                 half_sync(half);
+            NN_PH(2);
                 // ---- candidates
 #pragma unroll
                 for (int tr = 0; tr < kST; ++tr) {
@@ -250,6 +272,7 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                     }
                 }
                 half_sync(half);
+            NN_PH(3);
                 // ---- stage 2 (warp hw <-> trajectory hw)
                 const int c = cnt[hw];
                 if (c == 1) {
@@ -291,6 +314,7 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                 if (lane == 0) sel[hw] = (bi == 0x7fffffff) ? 0 : bi;
             }
             half_sync(half);
+            NN_PH(4);
             if (idxo && ht < nt) idxo[(b0 + ht) * (long long)N + t] = sel[ht];
             // ---- x+ = (A_i x + B_i u) + d_i (tpwl.py:231-234): four lanes per (trajectory, row), two rows per lane
             //      group and pass with all loads of both rows issued first; u of the next step is fetched meanwhile
@@ -303,7 +327,10 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                 const int part = ht & 3;
                 constexpr int QROWS = kSHalf / 4;
                 for (int rb = 0; rb < tpg * n; rb += 2 * QROWS) {
-                    const int row0 = rb + (ht >> 2), row1 = row0 + QROWS;
+                    // compile-time shape: a lane group takes two ADJACENT rows (same trajectory, n even), so the state
+                    // values are read once for both rows -- 9 LDS.128 instead of 36 LDS.64 per pass in a phase whose
+                    // limiter is the load / shared-memory instruction queue
+                    const int row0 = (RT > 0) ? rb + 2 * (ht >> 2) : rb + (ht >> 2), row1 = (RT > 0) ? row0 + 1 : row0 + QROWS;
                     const bool act0 = row0 < tpg * n, act1 = row1 < tpg * n;
                     const int tr0 = act0 ? row0 / n : 0, tr1 = act1 ? row1 / n : 0;
                     const int i0 = act0 ? row0 - tr0 * n : 0, i1 = act1 ? row1 - tr1 * n : 0;
@@ -313,6 +340,14 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                     const double* x0s = sx + tr0 * n;
                     const double* x1s = sx + tr1 * n;
                     double ax0 = 0.0, ax1 = 0.0, bu0 = 0.0, bu1 = 0.0;
+                    // B / d of both rows are requested together with A: one memory round trip per pass, not two
+                    const double* B0 = M.B + (pa * n + i0) * m;
+                    const double* B1 = M.B + (pb * n + i1) * m;
+                    const double d0 = __ldcg(M.d + pa * n + i0), d1 = __ldcg(M.d + pb * n + i1);
+                    double b0v = 0.0, b1v = 0.0;
+                    if (CM > 0 && CM <= 4) {
+                        if (part < m) { b0v = __ldcg(B0 + part); b1v = __ldcg(B1 + part); }
+                    }
                     if constexpr (RT > 0 && (2 * RT) % 8 == 0) {
                         // 16-byte loads: lane `part` takes elements 8 s + 2 part, 8 s + 2 part + 1 (rows are 16-byte
                         // aligned: n even, bank base from cudaMalloc); half the load instructions / L1 tag lookups
@@ -320,25 +355,31 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                         double2 v0[NK], v1[NK];
 #pragma unroll
                         for (int s2 = 0; s2 < NK; ++s2) {
-                            v0[s2] = *reinterpret_cast<const double2*>(A0 + 8 * s2 + 2 * part);
-                            v1[s2] = *reinterpret_cast<const double2*>(A1 + 8 * s2 + 2 * part);
+                            // L2-only loads: with ~173 KB of shared memory the L1 holds far fewer lines than the gather
+                            // keeps in flight, and an allocating load waits for a free line
+                            v0[s2] = __ldcg(reinterpret_cast<const double2*>(A0 + 8 * s2 + 2 * part));
+                            v1[s2] = __ldcg(reinterpret_cast<const double2*>(A1 + 8 * s2 + 2 * part));
                         }
 #pragma unroll
                         for (int s2 = 0; s2 < NK; ++s2) {
-                            const int k = 8 * s2 + 2 * part;
-                            ax0 = fma(v0[s2].x, x0s[k], ax0); ax0 = fma(v0[s2].y, x0s[k + 1], ax0);
-                            ax1 = fma(v1[s2].x, x1s[k], ax1); ax1 = fma(v1[s2].y, x1s[k + 1], ax1);
+                            const double2 xv = *reinterpret_cast<const double2*>(x0s + 8 * s2 + 2 * part);   // x1s == x0s
+                            ax0 = fma(v0[s2].x, xv.x, ax0); ax0 = fma(v0[s2].y, xv.y, ax0);
+                            ax1 = fma(v1[s2].x, xv.x, ax1); ax1 = fma(v1[s2].y, xv.y, ax1);
                         }
                     } else {
                         for (int k = part; k < n; k += 4) { ax0 = fma(A0[k], x0s[k], ax0); ax1 = fma(A1[k], x1s[k], ax1); }
                     }
-                    const double* B0 = M.B + (pa * n + i0) * m;
-                    const double* B1 = M.B + (pb * n + i1) * m;
-                    for (int k = part; k < m; k += 4) {
-                        bu0 = fma(B0[k], su[tr0 * m + k], bu0);
-                        bu1 = fma(B1[k], su[tr1 * m + k], bu1);
+                    if (CM > 0 && CM <= 4) {
+                        if (part < m) {
+                            bu0 = fma(b0v, su[tr0 * m + part], bu0);
+                            bu1 = fma(b1v, su[tr1 * m + part], bu1);
+                        }
+                    } else {
+                        for (int k = part; k < m; k += 4) {
+                            bu0 = fma(B0[k], su[tr0 * m + k], bu0);
+                            bu1 = fma(B1[k], su[tr1 * m + k], bu1);
+                        }
                     }
-                    const double d0 = M.d[pa * n + i0], d1 = M.d[pb * n + i1];
                     ax0 += __shfl_xor_sync(0xffffffffu, ax0, 1);  ax1 += __shfl_xor_sync(0xffffffffu, ax1, 1);
                     bu0 += __shfl_xor_sync(0xffffffffu, bu0, 1);  bu1 += __shfl_xor_sync(0xffffffffu, bu1, 1);
                     ax0 += __shfl_xor_sync(0xffffffffu, ax0, 2);  ax1 += __shfl_xor_sync(0xffffffffu, ax1, 2);
@@ -350,6 +391,7 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                 }
             }
             half_sync(half);
+            NN_PH(5);
             for (int e = ht; e < kST * n; e += kSHalf) {
                 const int tr = e / n, i = e - tr * n;
                 const double v = sxn[e];
@@ -358,6 +400,7 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
             }
             if (ht < kST * m) su[ht] = u_next;
             half_sync(half);
+            NN_PH(6);
         }
     }
 }
@@ -389,14 +432,27 @@ int tpwl_rollout_nn_screen_launch(const TpwlDev& M, long long batch, int N, cons
     const long long groups = (batch + tpg - 1) / tpg;
     const long long ctas = (groups + 1) / 2;
     const int grid = (int)(ctas < sms ? ctas : sms);
+    int stagger = 9000;
+    if (const char* e2 = getenv("SRCB200_NN_STAGGER")) stagger = atoi(e2);
     if (M.r == 36 && M.m == 4) {
         SRCB_CUDA(cudaFuncSetAttribute(tpwl_rollout_nn_screen_kernel<36, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
-        tpwl_rollout_nn_screen_kernel<36, 4><<<grid, kSThreads, S.total, st>>>(M, batch, N, x0, u, x, idx, useq ? 1 : 0, tpg);
+        tpwl_rollout_nn_screen_kernel<36, 4><<<grid, kSThreads, S.total, st>>>(M, batch, N, x0, u, x, idx, useq ? 1 : 0, tpg, stagger);
     } else {
         SRCB_CUDA(cudaFuncSetAttribute(tpwl_rollout_nn_screen_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
-        tpwl_rollout_nn_screen_kernel<0, 0><<<grid, kSThreads, S.total, st>>>(M, batch, N, x0, u, x, idx, useq ? 1 : 0, tpg);
+        tpwl_rollout_nn_screen_kernel<0, 0><<<grid, kSThreads, S.total, st>>>(M, batch, N, x0, u, x, idx, useq ? 1 : 0, tpg, stagger);
     }
     SRCB_LAUNCH_CHECK("tpwl_rollout_nn_screen_kernel");
+#ifdef SRCB_NN_PHASES
+    {
+        unsigned long long h[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_nn_phase, sizeof(h));
+        const char* nm[7] = {"state copy + norm", "dot products + min", "threshold", "candidates", "stage 2 / fallback", "gather + affine step", "state update"};
+        for (int i = 0; i < 7; ++i) fprintf(stderr, "  nn phase %-22s %8.0f cycles per step\n", nm[i], h[7] ? (double)h[i] / h[7] : 0.0);
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(g_nn_phase, h, sizeof(h));
+    }
+#endif
     *handled = true;
     return 0;
 }

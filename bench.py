@@ -370,19 +370,19 @@ def run_tpwl_rollout(args, rank, world, dev_index, method):
     n, m, P, r = 72, 4, 1000, 36
     if method == 'nn':
         byt = batch * N * ((n * n + n * m + n) * 8 + (2 * n + m) * 8) + N * P * r * 8
-        ops = batch * N * 2.0 * P * r
+        ops = batch * N * 2.0 * P * r              # one FMA per point-coordinate (dot-product screen)
         dram = 0.25e9 * batch / 4096.0          # ncu dram read+write of one launch (profiles/ncu_tpwl_screen_r01.txt)
         l2_peak = 17978.0                       # GB/s, tools/l2_bw_microbench.cu gather pattern (profiles/l2_bw_microbench_r2.txt)
         roof = {"kernel": "tpwl_rollout_nn_screen_kernel<36,4>", "bound": "l2/lsu (on-chip: the 44 MB bank is L2 resident)",
                 "achieved": byt / (t_dev / args.steps) / 1e9, "peak": l2_peak, "unit": "GB/s (L2 -> SM, algorithmic)",
                 "traffic": dram, "hbm_frac": dram / (t_dev / args.steps) / 1e9 / hbm,
-                "l1tex_pct_ncu": 65.0, "lts_pct_ncu": 12.0, "issue_active_pct_ncu": 52.0,
+                "l1tex_pct_ncu": 74.2, "lts_pct_ncu": 24.7, "issue_active_pct_ncu": 43.8,
                 "fp32_screen_tops": ops / (t_dev / args.steps) / 1e12,
                 "note": "algorithmic bytes per trajectory-step = gathered bank entry 44352 B + state I/O, distance bank "
                         "288000 B once per time step for the whole batch (SURVEY 8d).  These bytes move L2 -> SM, not HBM -> "
-                        "L2: DRAM traffic is 0.25 GB per launch (hbm_frac, of " + hsrc + "); the limiters ncu reports are the "
-                        "L1/LSU pipe (65 %) and FP32 issue of the exact two-stage search (52 %), "
-                        "profiles/ncu_tpwl_screen_r01.txt.  peak = L2 -> SM bandwidth measured on this pool for the same "
+                        "L2: DRAM traffic is 0.25 GB per launch (hbm_frac, of " + hsrc + "); ncu (profiles/ncu_tpwl_screen_r2.txt): "
+                        "L1 74 %, issue slots 43.8 % at 4 warps per scheduler -- latency-bound at this occupancy "
+                        "(profiles/phase_clocks_tpwl_nn_r2.txt).  peak = L2 -> SM bandwidth measured on this pool for the same "
                         "access pattern (random 44 KB entries, 16-byte loads, all SMs: 18.0 TB/s; coalesced sweep 20.5 TB/s; "
                         "tools/l2_bw_microbench.cu), of measured; frac = achieved / peak."}
         roof["frac"] = roof["achieved"] / l2_peak

@@ -27,6 +27,30 @@ def test_dgemm_vs_numpy(shape, transA):
     assert np.max(np.abs(C - ref)) <= 1e-12 * max(1.0, np.abs(ref).max()) * max(K, 1)
 
 
+def test_dgemm_mbarrier_pipeline_is_deterministic_under_load():
+    """The K loop hands its shared-memory stages over through full / empty mbarriers (no CTA barrier).  A stage read
+    before its copies landed or refilled while a slow warp still reads it would show up as run-to-run differences:
+    a many-tile GEMM (persistent CTAs walk ten tiles each, 129 K chunks per tile) and a long-K SYRK are repeated and
+    must reproduce their own bits every time, next to the float64 reference; odd leading dimensions take the 8-byte
+    copy path."""
+    import torch
+    from sofacontrol_b200.mor import pod
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for (M, N, K) in ((2048, 1536, 2056), (1111, 777, 1001)):
+        A = torch.randn((M, K), device="cuda", dtype=torch.float64, generator=g)
+        B = torch.randn((K, N), device="cuda", dtype=torch.float64, generator=g)
+        ref = A @ B
+        first = pod.dgemm_device(A, B)
+        assert float((first - ref).abs().max()) <= 1e-12 * K
+        for _ in range(12):
+            assert torch.equal(pod.dgemm_device(A, B), first)
+    X = torch.randn((40000, 700), device="cuda", dtype=torch.float64, generator=g)
+    G0 = pod.gram_device(X)
+    assert float((G0 - X.t() @ X).abs().max()) <= 1e-12 * 40000
+    for _ in range(8):
+        assert torch.equal(pod.gram_device(X), G0)
+
+
 @pytest.mark.parametrize("nf,ns", [(100, 3), (333, 129), (4884, 306), (1000, 257)])
 def test_gram_vs_numpy(nf, ns):
     from sofacontrol_b200.mor import pod

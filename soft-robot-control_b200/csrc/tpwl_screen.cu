@@ -323,6 +323,104 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                 const int tr = ht / m, i = ht - tr * m;
                 if (tr < nt) u_next = u[((b0 + tr) * (long long)N + t + 1) * m + i];
             }
+            if constexpr (RT == 36 && CM == 4) {
+                // Warp hw gathers the entry of trajectory hw.  Two consecutive rows of A_i are 1152 contiguous bytes
+                // = nine full 128-byte lines: sixteen lanes sweep such a ROW PAIR with five 16-byte loads each (the
+                // fifth by eight lanes), so a warp-wide load touches four full lines (the row-per-four-lanes layout
+                // touched eight half lines), and because all pairs of a lane belong to ONE trajectory the lane's ten
+                // state values stay in registers for the whole step.  The memory-instruction queue of the SM is the
+                // limiter of this phase (L1 74 % busy; shared-memory loads and shuffles wait behind the global loads).
+                // A lane's elements of a pair fall into row A (offset < 72) or row B; B_i u rides in the same sums; the
+                // six totals of a pass (three pairs) are reduced over the sixteen lanes by an eight-shuffle butterfly
+                // that leaves total 2 q + r on the lanes whose bits 3..1 spell that index; the even lanes store.
+                constexpr int PPT = n / 2, GP = 3, PASSES = PPT / 2 / GP;        // 18 pairs per half-warp, 6 passes
+                static_assert(PASSES * GP * 2 == PPT, "pairs split evenly");
+                const int l16 = lane & 15, hsel = lane >> 4;
+                const bool gact = hw < tpg;                                      // warp-uniform
+                const double* xsrc = sx + hw * n;
+                const bool toA2 = l16 < 4;
+                double2 xr[5];
+                xr[0] = *reinterpret_cast<const double2*>(xsrc + 2 * l16);
+                xr[1] = *reinterpret_cast<const double2*>(xsrc + 32 + 2 * l16);
+                xr[2] = *reinterpret_cast<const double2*>(xsrc + (toA2 ? 64 + 2 * l16 : 2 * l16 - 8));
+                xr[3] = *reinterpret_cast<const double2*>(xsrc + 24 + 2 * l16);
+                xr[4] = (l16 < 8) ? *reinterpret_cast<const double2*>(xsrc + 56 + 2 * l16) : make_double2(0.0, 0.0);
+                const double2 uv = (l16 < 4) ? *reinterpret_cast<const double2*>(su + hw * m + ((2 * l16) & 3)) : make_double2(0.0, 0.0);
+                const long long p = sel[hw];
+                const double* Ab = M.A + p * n * n + (long long)hsel * (PPT / 2) * 2 * n;
+                const double* Bb = M.B + p * n * m + (long long)hsel * (PPT / 2) * 2 * m;
+                const double* db = M.d + p * n + hsel * (PPT / 2) * 2;
+                const int own = ((l16 >> 3) & 1) * 4 + ((l16 >> 2) & 1) * 2 + ((l16 >> 1) & 1);   // value index 2 q + r
+                const bool sown = gact && own < 2 * GP && !(l16 & 1);
+#pragma unroll 1
+                for (int ps = 0; ps < PASSES; ++ps) {
+                    double2 v[GP][5], bv[GP];
+#pragma unroll
+                    for (int q = 0; q < GP; ++q) {
+                        const double* Ap = Ab + (long long)(ps * GP + q) * 2 * n;
+#pragma unroll
+                        for (int c = 0; c < 5; ++c)
+                            v[q][c] = (gact && (c < 4 || l16 < 8)) ? __ldcg(reinterpret_cast<const double2*>(Ap + 32 * c + 2 * l16))
+                                                                   : make_double2(0.0, 0.0);
+                        bv[q] = (gact && l16 < 4) ? __ldcg(reinterpret_cast<const double2*>(Bb + (ps * GP + q) * 2 * m + 2 * l16))
+                                                  : make_double2(0.0, 0.0);
+                    }
+                    const int rloc = (ps * GP + (own >> 1)) * 2 + (own & 1);     // row (within this half-warp's 36) the lane stores
+                    const double down = sown ? __ldcg(db + rloc) : 0.0;
+                    double val[8];
+#pragma unroll
+                    for (int q = 0; q < GP; ++q) {
+                        double accA = 0.0, accB = 0.0;
+                        accA = fma(v[q][0].x, xr[0].x, accA); accA = fma(v[q][0].y, xr[0].y, accA);
+                        accA = fma(v[q][1].x, xr[1].x, accA); accA = fma(v[q][1].y, xr[1].y, accA);
+                        {
+                            double t = toA2 ? accA : accB;
+                            t = fma(v[q][2].x, xr[2].x, t); t = fma(v[q][2].y, xr[2].y, t);
+                            if (toA2) accA = t; else accB = t;
+                        }
+                        accB = fma(v[q][3].x, xr[3].x, accB); accB = fma(v[q][3].y, xr[3].y, accB);
+                        if (l16 < 8) { accB = fma(v[q][4].x, xr[4].x, accB); accB = fma(v[q][4].y, xr[4].y, accB); }
+                        if (l16 < 4) {   // B_i u: elements 2 l16, 2 l16 + 1 of the pair's 2 x 4 block
+                            double t = (l16 < 2) ? accA : accB;
+                            t = fma(bv[q].x, uv.x, t); t = fma(bv[q].y, uv.y, t);
+                            if (l16 < 2) accA = t; else accB = t;
+                        }
+                        val[2 * q] = accA;
+                        val[2 * q + 1] = accB;
+                    }
+#pragma unroll
+                    for (int i = 2 * GP; i < 8; ++i) val[i] = 0.0;
+                    // (issuing the next pass's loads here, ahead of the reduction, was measured: slower -- the shuffles then
+                    // queue behind the loads in the SM's memory-instruction pipe)
+                    double k4[4], k2[2], k1;
+                    {
+                        const bool hi = (l16 & 8) != 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const double send = hi ? val[i] : val[i + 4];
+                            const double recv = __shfl_xor_sync(0xffffffffu, send, 8);
+                            k4[i] = (hi ? val[i + 4] : val[i]) + recv;
+                        }
+                    }
+                    {
+                        const bool hi = (l16 & 4) != 0;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const double send = hi ? k4[i] : k4[i + 2];
+                            const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                            k2[i] = (hi ? k4[i + 2] : k4[i]) + recv;
+                        }
+                    }
+                    {
+                        const bool hi = (l16 & 2) != 0;
+                        const double send = hi ? k2[0] : k2[1];
+                        const double recv = __shfl_xor_sync(0xffffffffu, send, 2);
+                        k1 = (hi ? k2[1] : k2[0]) + recv;
+                    }
+                    k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+                    if (sown) sxn[hw * n + hsel * (PPT / 2) * 2 + rloc] = __dadd_rn(k1, down);
+                }
+            } else
             {
                 const int part = ht & 3;
                 constexpr int QROWS = kSHalf / 4;
@@ -416,7 +514,7 @@ int tpwl_rollout_nn_screen_launch(const TpwlDev& M, long long batch, int N, cons
     if (useq == usev) return 0;                                    // both or none
     if ((useq ? M.wq : M.wv) < 0.0) return 0;
     if (M.P > kSPts * kSHalf || M.P < 1 || M.r > 128 || M.m > 32 || M.n != 2 * M.r) return 0;
-    if (reinterpret_cast<uintptr_t>(M.A) & 15) return 0;            // the gather uses 16-byte loads
+    if ((reinterpret_cast<uintptr_t>(M.A) | reinterpret_cast<uintptr_t>(M.B)) & 15) return 0;   // the gather uses 16-byte loads
     const ScreenPlan S = make_screen_plan(M.n, M.m, M.r, M.P);
     if (S.total > 220 * 1024) return 0;
     int dev = 0, sms = 148;

@@ -201,26 +201,41 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
             NN_PH(0);
             if (screen_ok) {
                 // ---- stage 1: FP32 dot products of this thread's (centred) points with the 8 (centred) states
+                // packed pairs: FFMA2 (fma.rn.f32x2, two IEEE FMAs per instruction, the point coordinate as the broadcast
+                // operand) halves the instruction count of the loop the kernel issues most
                 float a[kSPts][kST];
+                unsigned long long a2[kSPts][kST / 2];
 #pragma unroll
                 for (int k = 0; k < kSPts; ++k)
 #pragma unroll
-                    for (int tr = 0; tr < kST; ++tr) a[k][tr] = 0.f;
+                    for (int h = 0; h < kST / 2; ++h) a2[k][h] = 0ull;
                 const float* bp[kSPts];
 #pragma unroll
                 for (int k = 0; k < kSPts; ++k) bp[k] = bank + (has[k] ? pt[k] : 0);
 #pragma unroll 2
                 for (int j = 0; j < r; ++j) {
-                    const float4 xa = *reinterpret_cast<const float4*>(xfT + j * kST);
-                    const float4 xb = *reinterpret_cast<const float4*>(xfT + j * kST + 4);
-                    const float xs[kST] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                    const ulonglong2 xa = *reinterpret_cast<const ulonglong2*>(xfT + j * kST);
+                    const ulonglong2 xb = *reinterpret_cast<const ulonglong2*>(xfT + j * kST + 4);
+                    const unsigned long long xp[kST / 2] = {xa.x, xa.y, xb.x, xb.y};
 #pragma unroll
                     for (int k = 0; k < kSPts; ++k) {
                         const float q = bp[k][j * P];
+                        unsigned long long qq;
+                        asm("mov.b64 %0, {%1, %1};" : "=l"(qq) : "f"(q));
 #pragma unroll
-                        for (int tr = 0; tr < kST; ++tr) a[k][tr] = fmaf(q, xs[tr], a[k][tr]);
+                        for (int h = 0; h < kST / 2; ++h)
+                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a2[k][h]) : "l"(qq), "l"(xp[h]));
                     }
                 }
+#pragma unroll
+                for (int k = 0; k < kSPts; ++k)
+#pragma unroll
+                    for (int h = 0; h < kST / 2; ++h) {
+                        float lo, hi;
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a2[k][h]));
+                        a[k][2 * h] = lo;
+                        a[k][2 * h + 1] = hi;
+                    }
                 // a^ = (|b|^2 + |c|^2) - 2 b.c
                 {
                     const float4 na = *reinterpret_cast<const float4*>(ncf);

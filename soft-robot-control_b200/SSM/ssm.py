@@ -189,6 +189,23 @@ class SSM:
         x, z = L.to_host(xd), L.to_host(zd)
         return (x[0], z[0]) if single else (x, z)
 
+    def rollout_pinned(self, x0_h, u_h, dt, out_h=None):
+        """Extension (end-to-end batched rollout on PINNED host torch tensors): async H2D of x0 / u, one rollout, async
+        D2H of x, z into pinned outputs -- allocated on first use, cached on the model and REUSED by the next call of
+        the same shape --, one synchronisation."""
+        torch = L.torch_mod()
+        xd, zd = self.rollout_device(x0_h.cuda(non_blocking=True), u_h.cuda(non_blocking=True), dt)
+        if out_h is None:
+            cache = self.__dict__.setdefault('_pin_out', {})
+            out_h = cache.get(tuple(xd.shape))
+            if out_h is None:
+                out_h = cache[tuple(xd.shape)] = {'x': torch.empty(xd.shape, dtype=xd.dtype, pin_memory=True),
+                                                  'z': torch.empty(zd.shape, dtype=zd.dtype, pin_memory=True)}
+        out_h['x'].copy_(xd, non_blocking=True)
+        out_h['z'].copy_(zd, non_blocking=True)
+        torch.cuda.synchronize()
+        return out_h
+
     def rollout_device(self, x0, u, dt, want_z=True):
         """CUDA tensors x0 (Bt, n), u (Bt, N, m) -> CUDA tensors x (Bt, N+1, n), z (Bt, N+1, n_z)."""
         Bt, N = u.shape[0], u.shape[1]

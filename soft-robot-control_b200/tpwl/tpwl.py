@@ -296,6 +296,26 @@ class TPWL:
         return x, z
 
 
+    def rollout_pinned(self, x0_h, u_h, dt, out_h=None):
+        """Extension (end-to-end batched rollout on PINNED host torch tensors): async H2D of x0 (Bt, n) / u (Bt, N, m),
+        one rollout, async D2H of x (and z) into pinned outputs -- allocated on first use, cached on the model and REUSED
+        by the next call of the same shape (copy them out if they must survive it) --, one synchronisation."""
+        torch = L.torch_mod()
+        xd, zd = self.rollout_device(x0_h.cuda(non_blocking=True), u_h.cuda(non_blocking=True), dt)
+        if out_h is None:
+            key = (tuple(xd.shape), None if zd is None else tuple(zd.shape))
+            cache = self.__dict__.setdefault('_pin_out', {})
+            out_h = cache.get(key)
+            if out_h is None:
+                out_h = cache[key] = {'x': torch.empty(xd.shape, dtype=xd.dtype, pin_memory=True),
+                                      'z': None if zd is None else torch.empty(zd.shape, dtype=zd.dtype, pin_memory=True)}
+        out_h['x'].copy_(xd, non_blocking=True)
+        if zd is not None and out_h.get('z') is not None:
+            out_h['z'].copy_(zd, non_blocking=True)
+        torch.cuda.synchronize()
+        return out_h
+
+
 class TPWLATV(TPWL):
     """tpwl.py:219-342."""
 

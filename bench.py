@@ -318,7 +318,7 @@ def run_ilqr(args, rank, world, dev_index):
                              "measured on this pool (profiles/fp64_peaks_r01.json), of measured; the kernel is bound by the "
                              "dependent-issue latency of one warp (n = 6: issue slots 32 %, L1/shared 58-72 %, FP64 pipe "
                              "16 %) and, at 4096 problems, by the serial chain of the longest solves (22 % of the warp-time "
-                             "idle in the task queue): profiles/ncu_ilqr_r2_l2.txt, ncu_ilqr_r2_l2_lines.txt, DESIGN.md 4.1"},
+                             "idle in the task queue): profiles/ncu_ilqr_r2_l2.txt, ncu_ilqr_r2_l2_lines.txt, launches_bench_r2.csv, DESIGN.md 4.1"},
     }
     if strong is not None:
         res["strong"] = strong

@@ -1613,12 +1613,17 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // Persistent launch, three shapes (SRCB200_ILQR_SHAPE): 0 (default) two CTAs of 8 warps per SM, 128 registers, Jacobian
+    // Persistent launch, three shapes (SRCB200_ILQR_SHAPE forces one): 0 two CTAs of 8 warps per SM, 128 registers, Jacobian
     // table read from shared memory; 1: one CTA of 12 warps, 168 registers, table row `lane` in registers; 2: one CTA of
     // 8 warps, 255 registers, rows `lane` and `32 + lane` in registers (each warp ~1.8 x faster, half as many run).  Small
     // batches are spread over the SMs: the task queue feeds any number of warps.
+    // Without the switch the shape follows the batch (tools/shape_sweep.py, N = 100, one B200, ms per batch, shapes 0 / 1 / 2:
+    // 512: 27.3 / 23.3 / 21.7, 1024: 28.1 / 25.2 / 22.5, 2048: 34.5 / 30.6 / 28.3, 2368: 37.5 / 34.0 / 32.3, 3072: 39.6 / 35.3 /
+    // 39.0, 3584: 41.2 / 39.5 / 43.2, 4096: 45.1 / 45.0 / 48.5, 6144: 61.6 / 60.7 / 69.2, 8192: 77.2 / 78.3 / -): few problems
+    // are bound by the speed of a single warp (registers instead of shared-memory reads), many by the SM's throughput.
     const char* shp = getenv("SRCB200_ILQR_SHAPE");
-    const int cr = (shp && shp[0] >= '0' && shp[0] <= '2') ? shp[0] - '0' : 0;
+    const int cr = (shp && shp[0] >= '0' && shp[0] <= '2') ? shp[0] - '0'
+                   : (a.batch <= 2560 ? 2 : (a.batch <= 3840 ? 1 : 0));
     const int nw = fast::shape_warps(cr);
     const size_t smem = sizeof(double) * (fast::SH_END + nw * fast::W_SIZE);
     const long long slots = (long long)sms * (cr == 0 ? 2 : 1);

@@ -304,9 +304,9 @@ def run_ilqr(args, rank, world, dev_index):
                    "mean_forward_passes": float((trials + 1).mean()),
                    "total_iterations_per_rank": int(iters.sum())},
         "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": 2 * args.steps,         # ilqr_queue_init_kernel + ilqr_ssm_fast_kernel<8> per step
+        "gpu_launches": 3 * args.steps,         # queue_init_kernel + ilqr_ssm_fast_kernel<8,0> (until 1776 problems are left) + <8,2> (tail) per step
         "clocks": clocks,
-        "roofline": {"kernel": "ilqr_ssm_fast_kernel<8>", "bound": "tensor", "achieved": ach, "peak": fp64,
+        "roofline": {"kernel": "ilqr_ssm_fast_kernel<8,0> + <8,2> (tail hand-over)", "bound": "tensor", "achieved": ach, "peak": fp64,
                      "unit": "TFLOP/s", "frac": ach / fp64,
                      "traffic": traffic_model,
                      "traffic_source": "modelled from the executed passes (bench.py:ilqr_record_traffic: record + gain "

@@ -96,6 +96,8 @@ struct IlqrArgs {
     double prio_frac;           // HIGH class: initial cost > prio_frac * running mean
     int* work_counter;          // fast kernel's task queue: ints [head, tail, remaining, pad..64) then `queue_cap` slots
     int queue_cap;
+    int stop_at;                // fast kernel: warps stop taking tasks once this many problems (or fewer) are unfinished
+                                // (0: run to the end) -- the tail of a large batch is handed to a launch shape with faster warps
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -133,9 +135,11 @@ __device__ __forceinline__ bool try_acquire(int* avail) {
 }
 
 // one thread: next task id (HIGH ring first), or -1 when every problem is finished
-__device__ __forceinline__ int pop_one(int* q, int cap) {
+__device__ __forceinline__ int pop_one(int* q, int cap, int stop_at = 0) {
     unsigned ns = 256;                          // back off: an idle warp / CTA must not compete with working ones
     while (true) {
+        // hand-over: nothing is taken any more, the tasks stay in the rings for the next launch
+        if (stop_at > 0 && *(volatile int*)(q + Q_REMAINING) <= stop_at) return -1;
         int cls = -1;
         if (try_acquire(q + 2)) cls = 0;
         else if (try_acquire(q + 4 + 2)) cls = 1;

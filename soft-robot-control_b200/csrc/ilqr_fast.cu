@@ -939,9 +939,9 @@ __device__ __noinline__ BwdResult bwd_fast(const Ctx c, const IlqrArgs& a, const
 // ilqr.cuh, namespace ilqrq.
 using namespace ilqrq;
 
-__device__ __forceinline__ int queue_pop(int* q, int cap, int lane) {
+__device__ __forceinline__ int queue_pop(int* q, int cap, int lane, int stop_at) {
     int id = -1;
-    if (lane == 0) id = pop_one(q, cap);
+    if (lane == 0) id = pop_one(q, cap, stop_at);
     id = __shfl_sync(FULL, id, 0);
     __threadfence();            // acquire: what the previous owner of this problem wrote is visible (L1 invalidated)
     return id;
@@ -975,7 +975,7 @@ ilqr_ssm_fast_kernel(const __grid_constant__ SsmDev Mdl, const __grid_constant__
     __syncwarp();
 
     while (true) {
-        const long long b = queue_pop(a.work_counter, a.queue_cap, lane);
+        const long long b = queue_pop(a.work_counter, a.queue_cap, lane, a.stop_at);
         if (b < 0) break;
         double* wsb = a.ws + b * a.L.total;
         double* kbuf = wsb + a.L.k;
@@ -1624,23 +1624,52 @@ int ilqr_ssm_fast_launch(const SsmDev& M, const IlqrArgs& a, cudaStream_t st, bo
     const char* shp = getenv("SRCB200_ILQR_SHAPE");
     const int cr = (shp && shp[0] >= '0' && shp[0] <= '2') ? shp[0] - '0'
                    : (a.batch <= 2560 ? 2 : (a.batch <= 3840 ? 1 : 0));
-    const int nw = fast::shape_warps(cr);
-    const size_t smem = sizeof(double) * (fast::SH_END + nw * fast::W_SIZE);
-    const long long slots = (long long)sms * (cr == 0 ? 2 : 1);
-    int grid = (int)(a.batch < slots ? a.batch : slots);
-    if (grid * nw > kIlqrQueueWaiters) grid = kIlqrQueueWaiters / nw;
     ilqrq::queue_init_kernel<<<(a.queue_cap + 255) / 256, 256, 0, st>>>(a.work_counter, a.queue_cap, (int)a.batch, a.ws,
                                                                                  a.L.total, a.L.state);
     SRCB_LAUNCH_CHECK("ilqr_queue_init_kernel");
+    // Large batches: the throughput shape runs until `handover` problems are left, then its warps stop taking tasks (every
+    // problem is suspended in global memory between iterations anyway) and a second launch in shape 2 -- half as many
+    // warps, each ~1.8 x faster -- finishes the tail, which is bound by the speed of single warps (SRCB200_ILQR_HANDOVER=0
+    // disables, =n sets the threshold).
+    long long handover = (cr == 2 || shp) ? 0 : 1776;     // tools/handover_sweep.py: 4096 problems 44.6 -> 42.6 ms (1776 / 2368), 8192: 77.0 -> 76.1
+    if (const char* ho = getenv("SRCB200_ILQR_HANDOVER")) handover = (cr == 2) ? 0 : atoll(ho);
+    if (handover >= a.batch) handover = 0;
+    auto launch = [&](int shape, int stop_at) -> int {
+        IlqrArgs aa = a;
+        aa.stop_at = stop_at;
+        const int nw = fast::shape_warps(shape);
+        const size_t smem = sizeof(double) * (fast::SH_END + nw * fast::W_SIZE);
+        const long long slots = (long long)sms * (shape == 0 ? 2 : 1);
+        int grid = (int)(a.batch < slots ? a.batch : slots);
+        if (grid * nw > kIlqrQueueWaiters) grid = kIlqrQueueWaiters / nw;
 #define SRCB_LAUNCH_SHAPE(MM, CRR)                                                                                         \
     do {                                                                                                                   \
         SRCB_CUDA(cudaFuncSetAttribute(fast::ilqr_ssm_fast_kernel<MM, CRR>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                        (int)smem));                                                                        \
-        fast::ilqr_ssm_fast_kernel<MM, CRR><<<grid, nw * 32, smem, st>>>(M, a);                                            \
+        fast::ilqr_ssm_fast_kernel<MM, CRR><<<grid, nw * 32, smem, st>>>(M, aa);                                           \
     } while (0)
-    if (M.m == 8) { if (cr == 0) SRCB_LAUNCH_SHAPE(8, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(8, 1); else SRCB_LAUNCH_SHAPE(8, 2); }
-    else          { if (cr == 0) SRCB_LAUNCH_SHAPE(4, 0); else if (cr == 1) SRCB_LAUNCH_SHAPE(4, 1); else SRCB_LAUNCH_SHAPE(4, 2); }
+        if (M.m == 8) { if (shape == 0) SRCB_LAUNCH_SHAPE(8, 0); else if (shape == 1) SRCB_LAUNCH_SHAPE(8, 1); else SRCB_LAUNCH_SHAPE(8, 2); }
+        else          { if (shape == 0) SRCB_LAUNCH_SHAPE(4, 0); else if (shape == 1) SRCB_LAUNCH_SHAPE(4, 1); else SRCB_LAUNCH_SHAPE(4, 2); }
 #undef SRCB_LAUNCH_SHAPE
+        SRCB_LAUNCH_CHECK("ilqr_ssm_fast_kernel");
+        return 0;
+    };
+    if (const char* chain = getenv("SRCB200_ILQR_CHAIN")) {
+        // experiments: "shape:stop_at,shape:stop_at,...", the last entry with stop_at 0
+        const char* pch = chain;
+        while (*pch) {
+            const int shape = *pch - '0';
+            const long long stop = atoll(pch + 2);
+            if (shape < 0 || shape > 2) break;
+            if (stop < a.batch) if (int e = launch(shape, (int)stop)) return e;
+            while (*pch && *pch != ',') ++pch;
+            if (*pch == ',') ++pch;
+            if (stop == 0) break;
+        }
+    } else {
+        if (int e = launch(cr, (int)handover)) return e;
+        if (handover > 0) if (int e = launch(2, 0)) return e;
+    }
     SRCB_LAUNCH_CHECK("ilqr_ssm_fast_kernel");
     *handled = true;
     return 0;

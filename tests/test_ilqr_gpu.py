@@ -262,6 +262,33 @@ def test_launch_shapes_of_the_fast_kernel_agree(m, monkeypatch):
             assert relerr(a, b) < 1e-12
 
 
+def test_tail_handover_between_launch_shapes_is_bit_identical(monkeypatch):
+    """Large batches: the throughput launch shape stops taking tasks when 1776 problems are left and a second launch in
+    the 8-warp shape finishes them from the same task rings (csrc/ilqr_fast.cu).  Suspended problems carry their whole
+    state in global memory, so the schedule must not change a bit: x, u, K, costs, iterations, statuses with the
+    hand-over (default), without it, and at an odd threshold -- for the shape-1 and the shape-0 range of batch sizes."""
+    import torch
+    import sofacontrol_b200.synth as synth
+    from sofacontrol_b200 import _lib as L
+    _, model = _ssm(8)
+    for batch in (2700, 4000):
+        w = synth.trunk_ilqr_batch(batch, N=24, seed=31, m=8)
+        s = _solver(model, 8, w['z_target'])
+        x0, zt = L.to_dev(w['x0']), L.to_dev(w['z_target'])
+        res = {}
+        for tag, ho in (("default", None), ("off", "0"), ("odd", "777")):
+            if ho is None:
+                monkeypatch.delenv("SRCB200_ILQR_HANDOVER", raising=False)
+            else:
+                monkeypatch.setenv("SRCB200_ILQR_HANDOVER", ho)
+            out = s.solve_device(x0, zt)
+            res[tag] = {k: out[k].clone() for k in ('x', 'u', 'K', 'cost', 'iterations', 'status')}
+        for tag in ("off", "odd"):
+            for k, v in res["default"].items():
+                assert torch.equal(v, res[tag][k]), (batch, tag, k)
+        assert int(res["default"]['iterations'].max()) > int(res["default"]['iterations'].min())
+
+
 def test_pinned_stream_api_equals_single_calls():
     """iLQR.solve_pinned_stream (double-buffered D2H) returns, batch by batch, exactly what solve_pinned returns."""
     import torch

@@ -310,8 +310,8 @@ def run_ilqr(args, rank, world, dev_index):
                      "unit": "TFLOP/s", "frac": ach / fp64,
                      "traffic": traffic_model,
                      "traffic_source": "modelled from the executed passes (bench.py:ilqr_record_traffic: record + gain "
-                                       "bytes per pass-step); ncu dram read+write of one launch of this workload: 35.5e9 "
-                                       "(profiles/ncu_ilqr_r2_l2.txt)",
+                                       "bytes per pass-step); ncu dram read+write of the two launches of one step of this workload: "
+                                       "31.6e9 + 4.0e9 (profiles/ncu_ilqr_r2_final.txt)",
                      "algorithmic_io_bytes": float(batch * (55e3)),
                      "note": "FP64 pipe (DMMA + DFMA): algorithmic flops of the executed passes (dense counts, bench.py:"
                              "ilqr_flops, DESIGN.md) / event time of the single launch; peak = cuBLAS DGEMM 8192^3 "

@@ -274,15 +274,24 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                 half_sync(half);
             NN_PH(2);
                 // ---- candidates
+                // (32 compares folded into one hit mask without branches; a thread owns a candidate once in ~250 steps,
+                // so the atomics sit behind one rarely taken branch instead of 32 branch regions)
+                {
+                    const float4 t0 = *reinterpret_cast<const float4*>(thr2);
+                    const float4 t1 = *reinterpret_cast<const float4*>(thr2 + 4);
+                    const float ths[kST] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                    unsigned hits = 0u;
 #pragma unroll
-                for (int tr = 0; tr < kST; ++tr) {
-                    const float th = thr2[tr];
+                    for (int tr = 0; tr < kST; ++tr)
 #pragma unroll
-                    for (int k = 0; k < kSPts; ++k) {
-                        if (has[k] && a[k][tr] <= th) {
-                            const int pos = atomicAdd(&cnt[tr], 1);
-                            if (pos < kSCand) cand[tr * kSCand + pos] = pt[k];
-                        }
+                        for (int k = 0; k < kSPts; ++k)
+                            hits |= (has[k] && a[k][tr] <= ths[tr]) ? (1u << (tr * kSPts + k)) : 0u;
+                    while (hits) {
+                        const int bit = __ffs(hits) - 1;
+                        hits &= hits - 1u;
+                        const int tr = bit / kSPts, k = bit - tr * kSPts;
+                        const int pos = atomicAdd(&cnt[tr], 1);
+                        if (pos < kSCand) cand[tr * kSCand + pos] = ht + k * kSHalf;       // == pt[k]
                     }
                 }
                 half_sync(half);

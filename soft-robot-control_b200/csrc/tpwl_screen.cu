@@ -178,25 +178,27 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
         long long tph_ = clock64();
         if (tid == 0 && blockIdx.x == 0) atomicAdd(&g_nn_phase[7], (unsigned long long)N);
 #endif
-        for (int t = 0; t < N; ++t) {
-            // ---- FP32 copy and norm of the screened part of every state (warp hw <-> trajectory slot hw)
-            {
-                double s2 = 0.0;
-                for (int j = lane; j < r; j += 32) {
-                    const double v = sx[hw * n + xoff + j] - smu[j];
-                    xfT[j * kST + hw] = (float)v;
-                    s2 = fma(v, v, s2);
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-                if (lane == 0) {
-                    xnorm[hw] = sqrt(s2) * (1.0 + 1e-9);
-                    ncf[hw] = (float)s2;
-                    cnt[hw] = 0;
-                    fb[hw] = screen_ok ? 0 : 1;
-                }
+        // ---- FP32 copy and norm of the screened part of every state (warp hw <-> trajectory slot hw); for step t + 1 it
+        //      runs in the state-update phase of step t, straight from the new state (one barrier and one pass less)
+        auto prep_state = [&](const double* __restrict__ xs) {
+            double s2 = 0.0;
+            for (int j = lane; j < r; j += 32) {
+                const double v = xs[hw * n + xoff + j] - smu[j];
+                xfT[j * kST + hw] = (float)v;
+                s2 = fma(v, v, s2);
             }
-            half_sync(half);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+            if (lane == 0) {
+                xnorm[hw] = sqrt(s2) * (1.0 + 1e-9);
+                ncf[hw] = (float)s2;
+                cnt[hw] = 0;
+                fb[hw] = screen_ok ? 0 : 1;
+            }
+        };
+        prep_state(sx);
+        half_sync(half);
+        for (int t = 0; t < N; ++t) {
             NN_PH(0);
             if (screen_ok) {
                 // ---- stage 1: FP32 dot products of this thread's (centred) points with the 8 (centred) states
@@ -520,6 +522,7 @@ tpwl_rollout_nn_screen_kernel(TpwlDev M, long long batch, int N, const double* _
                 if (tr < nt) xo[((b0 + tr) * (long long)(N + 1) + t + 1) * n + i] = v;
             }
             if (ht < kST * m) su[ht] = u_next;
+            if (t + 1 < N) prep_state(sxn);
             half_sync(half);
             NN_PH(6);
         }
